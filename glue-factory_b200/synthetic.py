@@ -1,0 +1,189 @@
+"""Seeded synthetic weights, keypoint pairs and ground-truth labels.
+
+Everything here is host-side input construction (numpy `RandomState`, whose
+stream is frozen across numpy versions, so the same seed gives the same
+tensors in the build container and on the GPU box).  It is shared by
+`bench.py`, the tests and `oracle/make_golden.py`.
+
+The pair recipe follows SURVEY.md section 8(d): N uniformly drawn keypoints in
+a 1024x1024 image, a random homography, 40 % planted correspondences with
+0.5 px noise and correlated descriptors, the rest random; view 1 permuted.
+Ground truth restates `gt_matches_from_homography`
+(/root/reference/gluefactory/geometry/gt_generation.py:109-161) with the
+thresholds of configs/superpoint+lightglue_homography.yaml:22-25.
+"""
+import math
+
+import numpy as np
+import torch
+
+DEFAULT_CONF = {
+    "name": "lightglue",
+    "input_dim": 256,
+    "descriptor_dim": 256,
+    "n_layers": 9,
+    "num_heads": 4,
+    "filter_threshold": 0.0,
+    "loss": {"gamma": 1.0, "fn": "nll", "nll_balancing": 0.5},
+}
+
+
+def state_dict_spec(conf):
+    """(name, shape) list in the reference's state_dict order
+    (/root/reference/gluefactory/models/matchers/lightglue.py:343-372)."""
+    D, L, Din = conf["descriptor_dim"], conf["n_layers"], conf["input_dim"]
+    H = conf["num_heads"]
+    dh = D // H
+    spec = []
+    if Din != D:
+        spec += [("input_proj.weight", (D, Din)), ("input_proj.bias", (D,))]
+    spec += [("posenc.Wr.weight", (dh // 2, 2))]
+    for i in range(L):
+        p = f"transformers.{i}.self_attn"
+        spec += [(p + ".Wqkv.weight", (3 * D, D)), (p + ".Wqkv.bias", (3 * D,)),
+                 (p + ".out_proj.weight", (D, D)), (p + ".out_proj.bias", (D,)),
+                 (p + ".ffn.0.weight", (2 * D, 2 * D)), (p + ".ffn.0.bias", (2 * D,)),
+                 (p + ".ffn.1.weight", (2 * D,)), (p + ".ffn.1.bias", (2 * D,)),
+                 (p + ".ffn.3.weight", (D, 2 * D)), (p + ".ffn.3.bias", (D,))]
+        p = f"transformers.{i}.cross_attn"
+        spec += [(p + ".to_qk.weight", (D, D)), (p + ".to_qk.bias", (D,)),
+                 (p + ".to_v.weight", (D, D)), (p + ".to_v.bias", (D,)),
+                 (p + ".to_out.weight", (D, D)), (p + ".to_out.bias", (D,)),
+                 (p + ".ffn.0.weight", (2 * D, 2 * D)), (p + ".ffn.0.bias", (2 * D,)),
+                 (p + ".ffn.1.weight", (2 * D,)), (p + ".ffn.1.bias", (2 * D,)),
+                 (p + ".ffn.3.weight", (D, 2 * D)), (p + ".ffn.3.bias", (D,))]
+    for i in range(L):
+        p = f"log_assignment.{i}"
+        spec += [(p + ".matchability.weight", (1, D)), (p + ".matchability.bias", (1,)),
+                 (p + ".final_proj.weight", (D, D)), (p + ".final_proj.bias", (D,))]
+    for i in range(L - 1):
+        p = f"token_confidence.{i}.token.0"
+        spec += [(p + ".weight", (1, D)), (p + ".bias", (1,))]
+    return spec
+
+
+def make_weights(conf, seed=0, dtype=torch.float32):
+    """Deterministic random-init weights under the reference's parameter names.
+
+    Linear layers: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias
+    (torch's default nn.Linear init); LayerNorm affine perturbed away from
+    (1, 0) so that its gradients are exercised; posenc.Wr ~ N(0, 1)
+    (lightglue.py:58 with gamma = 1).
+    """
+    rs = np.random.RandomState(seed)
+    out = {}
+    spec = state_dict_spec(conf)
+    shapes = dict(spec)
+    for name, shape in spec:
+        if name == "posenc.Wr.weight":
+            a = rs.standard_normal(shape)
+        elif ".ffn.1." in name:
+            a = (1.0 if name.endswith("weight") else 0.0) + 0.1 * rs.standard_normal(shape)
+        else:
+            wshape = shape if name.endswith("weight") else shapes[name[: -len("bias")] + "weight"]
+            bound = 1.0 / math.sqrt(wshape[-1])
+            a = rs.uniform(-bound, bound, size=shape)
+        out[name] = torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+    return out
+
+
+# ----------------------------------------------------------------------------
+# ground truth (restated; runs on whatever device the keypoints live on)
+# ----------------------------------------------------------------------------
+def warp_points(pts, Hm):
+    """pts [B,N,2] -> H . pts (homogeneous divide, eps as geometry/utils.from_homogeneous)."""
+    ones = torch.ones_like(pts[..., :1])
+    ph = torch.cat([pts, ones], -1) @ Hm.transpose(-1, -2)
+    return ph[..., :2] / (ph[..., 2:] + 1e-5)
+
+
+@torch.no_grad()
+def gt_matches_from_homography(kp0, kp1, Hm, pos_th=3.0, neg_th=3.0):
+    """Restates geometry/gt_generation.py:109-161: reprojection distance both
+    ways, mutual nearest neighbours below pos_th are positives, points whose
+    best reprojection error exceeds neg_th are unmatched (-1), the rest are
+    ignored (-2)."""
+    kp0_1 = warp_points(kp0, Hm)
+    kp1_0 = warp_points(kp1, torch.inverse(Hm))
+    d0 = ((kp0_1[:, :, None] - kp1[:, None]) ** 2).sum(-1)
+    d1 = ((kp0[:, :, None] - kp1_0[:, None]) ** 2).sum(-1)
+    dist = torch.max(d0, d1)
+    min0 = dist.min(-1).indices
+    min1 = dist.min(-2).indices
+    ismin0 = torch.zeros_like(dist, dtype=torch.bool).scatter_(-1, min0[..., None], True)
+    ismin1 = torch.zeros_like(dist, dtype=torch.bool).scatter_(-2, min1[:, None], True)
+    positive = ismin0 & ismin1 & (dist < pos_th**2)
+    neg0 = d0.min(-1).values > neg_th**2
+    neg1 = d1.min(-2).values > neg_th**2
+    m0 = torch.where(positive.any(-1), min0, torch.full_like(min0, -2))
+    m1 = torch.where(positive.any(-2), min1, torch.full_like(min1, -2))
+    m0 = torch.where(neg0, torch.full_like(m0, -1), m0)
+    m1 = torch.where(neg1, torch.full_like(m1, -1), m1)
+    return positive, m0, m1
+
+
+def _random_homography(rs, size, difficulty=0.7):
+    """4-corner perturbation homography (in the spirit of
+    geometry/homography.py:40-107), solved by DLT."""
+    s = float(size)
+    src = np.array([[0, 0], [s, 0], [s, s], [0, s]], dtype=np.float64)
+    dst = src + rs.uniform(-0.25 * difficulty * s / 2, 0.25 * difficulty * s / 2, size=(4, 2))
+    A = []
+    for (x, y), (u, v) in zip(src, dst):
+        A.append([-x, -y, -1, 0, 0, 0, u * x, u * y, u])
+        A.append([0, 0, 0, -x, -y, -1, v * x, v * y, v])
+    _, _, vt = np.linalg.svd(np.asarray(A))
+    Hm = vt[-1].reshape(3, 3)
+    return Hm / Hm[2, 2]
+
+
+def make_pairs(B, N, seed=1234, D=256, image_size=1024, frac=0.4, M=None, with_gt=True,
+               dtype=torch.float32):
+    """Synthetic batch in the matcher's input contract
+    (models/two_view_pipeline.py:80-81; lightglue.py:416-455)."""
+    M = N if M is None else M
+    rs = np.random.RandomState(seed)
+    S = float(image_size)
+    kp0 = np.zeros((B, M, 2)); kp1 = np.zeros((B, N, 2))
+    de0 = np.zeros((B, M, D)); de1 = np.zeros((B, N, D))
+    Hs = np.zeros((B, 3, 3))
+    for b in range(B):
+        Hm = _random_homography(rs, S)
+        Hs[b] = Hm
+        k0 = rs.uniform(0.5, S - 0.5, size=(M, 2))
+        K = int(frac * min(M, N))
+        ph = np.concatenate([k0[:K], np.ones((K, 1))], 1) @ Hm.T
+        w1 = ph[:, :2] / ph[:, 2:] + 0.5 * rs.standard_normal((K, 2))
+        k1 = rs.uniform(0.5, S - 0.5, size=(N, 2))
+        inside = np.all((w1 > 0.5) & (w1 < S - 0.5), 1)
+        k1[:K][inside] = w1[inside]
+        f0 = rs.standard_normal((M, D))
+        f0 /= np.linalg.norm(f0, axis=1, keepdims=True)
+        f1 = rs.standard_normal((N, D))
+        f1[:K][inside] = (f0[:K] + 0.3 * rs.standard_normal((K, D)) / math.sqrt(D))[inside]
+        f1 /= np.linalg.norm(f1, axis=1, keepdims=True)
+        perm = rs.permutation(N)
+        kp0[b], kp1[b], de0[b], de1[b] = k0, k1[perm], f0, f1[perm]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+    size = torch.full((B, 2), S, dtype=dtype)
+    data = {
+        "keypoints0": t(kp0), "keypoints1": t(kp1),
+        "descriptors0": t(de0), "descriptors1": t(de1),
+        "view0": {"image_size": size.clone()}, "view1": {"image_size": size.clone()},
+        "H_0to1": t(Hs),
+    }
+    if with_gt:
+        ga, m0, m1 = gt_matches_from_homography(
+            data["keypoints0"].double(), data["keypoints1"].double(), data["H_0to1"].double())
+        data.update({"gt_assignment": ga, "gt_matches0": m0, "gt_matches1": m1})
+    return data
+
+
+def to_device(data, device, non_blocking=False):
+    """Recursive .to(device) over the nested batch dict
+    (utils/tensor.py:30-34 batch_to_device)."""
+    if isinstance(data, dict):
+        return {k: to_device(v, device, non_blocking) for k, v in data.items()}
+    if torch.is_tensor(data):
+        return data.to(device, non_blocking=non_blocking)
+    return data

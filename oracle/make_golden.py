@@ -1,0 +1,129 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED
+reference (TEST INFRASTRUCTURE ONLY; runs in the build container, where
+/root/reference exists -- the GPU box only ever sees the committed .npz files).
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz
+
+The reference modules are imported from /root/reference with the omegaconf
+stand-in of oracle/_shim on sys.path (omegaconf is not installed here).
+Weights and inputs come from gluefactory_b200.synthetic (numpy RandomState
+streams), so tests regenerate the exact same inputs from the seeds stored in
+each fixture.  Big matrices (parameter gradients) are stored as a fixed
+sub-sample plus two scalar functionals, see `summarise`.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("GLUEFACTORY_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "_shim"))
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+from gluefactory_b200 import synthetic  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def summarise(name, g):
+    """Compact, order-sensitive summary of a gradient tensor."""
+    g = g.detach().double().cpu()
+    out = {f"{name}|norm": np.array(g.norm().item())}
+    if g.numel() <= 4096:
+        out[f"{name}|full"] = g.numpy()
+    else:
+        flat = g.reshape(-1)
+        idx = probe_index(flat.numel())
+        out[f"{name}|sample"] = flat[idx].numpy()
+        out[f"{name}|proj"] = np.array((flat * probe_vector(flat.numel())).sum().item())
+    return out
+
+
+def probe_index(n, k=512):
+    return torch.from_numpy(np.random.RandomState(n % 65521).randint(0, n, size=k))
+
+
+def probe_vector(n):
+    return torch.from_numpy(np.random.RandomState((n * 7919) % 65521).standard_normal(n))
+
+
+def build_reference(conf, weights, dtype):
+    from gluefactory.models import get_model
+
+    cls = get_model("matchers.lightglue")
+    model = cls(dict(conf))
+    sd = {k: v.to(dtype) for k, v in weights.items()}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert missing == [] or missing == ["confidence_thresholds"], missing
+    return model.to(dtype).train()
+
+
+def run_case(name, conf, B, N, M, seed, dtype=torch.float64, sub=1):
+    weights = synthetic.make_weights(conf, seed=seed)
+    data = synthetic.make_pairs(B, N, seed=seed + 1, D=conf["input_dim"], M=M, dtype=dtype)
+    model = build_reference(conf, weights, dtype)
+    pred = model(data)
+    losses, _ = model.loss(pred, data)
+    loss = losses["total"].mean()
+    loss.backward()
+    out = {
+        "meta|B": np.array(B), "meta|N": np.array(N), "meta|M": np.array(M), "meta|seed": np.array(seed),
+        "meta|conf": np.array(repr(conf)),
+    }
+    for k in ["matches0", "matches1", "matching_scores0", "matching_scores1"]:
+        out["pred|" + k] = pred[k].detach().cpu().numpy()
+    la = pred["log_assignment"].detach()
+    out["pred|log_assignment"] = la[:, ::sub, ::sub].cpu().numpy()
+    out["pred|log_assignment_rowmax"] = la[:, :-1, :-1].max(2).values.cpu().numpy()
+    out["pred|log_assignment_colmax"] = la[:, :-1, :-1].max(1).values.cpu().numpy()
+    rd0 = pred["ref_descriptors0"].detach()
+    out["pred|ref_descriptors0_sub"] = rd0[:, :, :: max(1, N // 16)].cpu().numpy()
+    out["pred|ref_descriptors1_sub"] = pred["ref_descriptors1"].detach()[:, :, :: max(1, N // 16)].cpu().numpy()
+    for k, v in losses.items():
+        out["loss|" + k] = v.detach().cpu().numpy() if torch.is_tensor(v) else np.array(v)
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        out.update(summarise("grad|" + k, p.grad))
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: loss={loss.item():.6f} matches={int((pred['matches0'] > -1).sum())} -> {path} "
+          f"({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
+def run_heads():
+    """Golden vectors for the two other assignment heads on the path."""
+    from gluefactory.models.matchers.gluestick import log_double_softmax
+    from gluefactory_nonfree.superglue import log_optimal_transport
+
+    rs = np.random.RandomState(7)
+    out = {}
+    for tag, (B, M, N) in {"a": (2, 37, 53), "b": (1, 128, 96)}.items():
+        sim = torch.from_numpy(rs.standard_normal((B, M, N)) * 3.0)
+        bin_score = torch.tensor(0.7, dtype=torch.float64)
+        out[f"{tag}|sim"] = sim.numpy()
+        out[f"{tag}|lds"] = log_double_softmax(sim, bin_score).numpy()
+        out[f"{tag}|lot"] = log_optimal_transport(sim, bin_score, 50).numpy()
+    path = os.path.join(OUT, "heads.npz")
+    np.savez_compressed(path, **out)
+    print("heads ->", path)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    small = dict(synthetic.DEFAULT_CONF, descriptor_dim=128, input_dim=128, num_heads=2, n_layers=2)
+    run_case("lg_small_d128_l2_n96", small, B=2, N=96, M=96, seed=11)
+    run_case("lg_small_d128_l2_m80_n112", small, B=2, N=112, M=80, seed=12)
+    mid = dict(synthetic.DEFAULT_CONF, n_layers=3, filter_threshold=0.1)
+    run_case("lg_d256_l3_n160", mid, B=2, N=160, M=160, seed=13)
+    disk = dict(synthetic.DEFAULT_CONF, n_layers=2, input_dim=128)
+    run_case("lg_disk_d256_l2_n128", disk, B=1, N=128, M=128, seed=14)
+    full = dict(synthetic.DEFAULT_CONF)
+    run_case("lg_full_l9_n512", full, B=1, N=512, M=512, seed=15, sub=8)
+    run_heads()
