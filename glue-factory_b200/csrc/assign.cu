@@ -1,0 +1,468 @@
+// Assignment head kernels: sigmoid_log_double_softmax, deep-supervision NLL
+// terms, row/col argmax and match filtering -- the HBM-bound part of the
+// LightGlue matcher (reference: gluefactory/models/matchers/lightglue.py:256-309,
+// gluefactory/models/utils/losses.py:6-73).
+//
+// Layout: sim [B,M,N] fp32 row-major.  A CTA of 256 threads (8 warps) owns a
+// strip of 32 consecutive rows and walks it in 128-column chunks; lane l of a
+// warp owns 4 consecutive columns (one 128-bit load), warp w owns rows
+// w, w+8, w+16, w+24 of the strip.  Row statistics stay in registers and are
+// reduced with warp shuffles; column statistics are reduced across the 8 warps
+// through shared memory and written as per-strip partials that a tiny second
+// kernel merges in strip order (deterministic, no atomics).
+#include <math.h>
+
+#include "common.cuh"
+#include "lgb200.h"
+
+namespace lgb {
+
+constexpr int kStripRows = 32;
+constexpr int kChunk = 128;
+constexpr int kWarps = 8;
+constexpr int kRowsPerWarp = kStripRows / kWarps;  // 4
+constexpr float kNegInf = -INFINITY;
+
+__device__ __forceinline__ float4 ld4(const float* p, bool vec, int valid) {
+  // loads up to 4 floats starting at p; lanes beyond `valid` are -inf
+  float4 r;
+  if (vec && valid >= 4) {
+    r = *reinterpret_cast<const float4*>(p);
+  } else {
+    r.x = valid > 0 ? p[0] : kNegInf;
+    r.y = valid > 1 ? p[1] : kNegInf;
+    r.z = valid > 2 ? p[2] : kNegInf;
+    r.w = valid > 3 ? p[3] : kNegInf;
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1: row LSE (final) and per-strip column (max, sumexp) partials
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) assign_lse_kernel(const float* __restrict__ sim, float* __restrict__ lse_row,
+                                                        float* __restrict__ colpart_m,
+                                                        float* __restrict__ colpart_s, int M, int N, int nstrips) {
+  __shared__ float s_cmax[2][kWarps][kChunk];
+  __shared__ float s_csum[2][kWarps][kChunk];
+  const int b = blockIdx.y, strip = blockIdx.x;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vec = (N & 3) == 0;
+  const float* base = sim + (int64_t)b * M * N;
+
+  float rm[kRowsPerWarp], rs[kRowsPerWarp];
+  int rows[kRowsPerWarp];
+#pragma unroll
+  for (int t = 0; t < kRowsPerWarp; ++t) {
+    rm[t] = kNegInf;
+    rs[t] = 0.f;
+    rows[t] = strip * kStripRows + w + kWarps * t;
+  }
+  int buf = 0;
+  for (int c0 = 0; c0 < N; c0 += kChunk, buf ^= 1) {
+    const int col = c0 + lane * 4;
+    const int valid = min(4, N - col);  // may be <= 0
+    float4 x[kRowsPerWarp];
+#pragma unroll
+    for (int t = 0; t < kRowsPerWarp; ++t) {
+      x[t] = (rows[t] < M && valid > 0) ? ld4(base + (int64_t)rows[t] * N + col, vec, valid)
+                                         : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+    }
+    // ---- row statistics (online, rescale only when the running max moves)
+#pragma unroll
+    for (int t = 0; t < kRowsPerWarp; ++t) {
+      float cm = fmaxf(fmaxf(x[t].x, x[t].y), fmaxf(x[t].z, x[t].w));
+      if (cm > rm[t]) {
+        rs[t] *= __expf(rm[t] - cm);  // rm=-inf -> exp(-inf)=0, rs is 0 anyway
+        rm[t] = cm;
+      }
+      const float ref = (rm[t] == kNegInf) ? 0.f : rm[t];
+      rs[t] += (__expf(x[t].x - ref) + __expf(x[t].y - ref)) + (__expf(x[t].z - ref) + __expf(x[t].w - ref));
+    }
+    // ---- column statistics of this strip: max first (no exp), then one exp per element
+    float4 cm4;
+    cm4.x = fmaxf(fmaxf(x[0].x, x[1].x), fmaxf(x[2].x, x[3].x));
+    cm4.y = fmaxf(fmaxf(x[0].y, x[1].y), fmaxf(x[2].y, x[3].y));
+    cm4.z = fmaxf(fmaxf(x[0].z, x[1].z), fmaxf(x[2].z, x[3].z));
+    cm4.w = fmaxf(fmaxf(x[0].w, x[1].w), fmaxf(x[2].w, x[3].w));
+    *reinterpret_cast<float4*>(&s_cmax[buf][w][lane * 4]) = cm4;
+    __syncthreads();
+    float4 mx = *reinterpret_cast<float4*>(&s_cmax[buf][0][lane * 4]);
+#pragma unroll
+    for (int ww = 1; ww < kWarps; ++ww) {
+      float4 o = *reinterpret_cast<float4*>(&s_cmax[buf][ww][lane * 4]);
+      mx.x = fmaxf(mx.x, o.x); mx.y = fmaxf(mx.y, o.y); mx.z = fmaxf(mx.z, o.z); mx.w = fmaxf(mx.w, o.w);
+    }
+    float4 rf;  // reference (0 when the whole strip column is -inf)
+    rf.x = mx.x == kNegInf ? 0.f : mx.x; rf.y = mx.y == kNegInf ? 0.f : mx.y;
+    rf.z = mx.z == kNegInf ? 0.f : mx.z; rf.w = mx.w == kNegInf ? 0.f : mx.w;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < kRowsPerWarp; ++t) {
+      cs.x += __expf(x[t].x - rf.x); cs.y += __expf(x[t].y - rf.y);
+      cs.z += __expf(x[t].z - rf.z); cs.w += __expf(x[t].w - rf.w);
+    }
+    *reinterpret_cast<float4*>(&s_csum[buf][w][lane * 4]) = cs;
+    __syncthreads();
+    if (threadIdx.x < kChunk && c0 + threadIdx.x < N) {
+      float m = s_cmax[buf][0][threadIdx.x], s = s_csum[buf][0][threadIdx.x];
+#pragma unroll
+      for (int ww = 1; ww < kWarps; ++ww) {
+        m = fmaxf(m, s_cmax[buf][ww][threadIdx.x]);
+        s += s_csum[buf][ww][threadIdx.x];
+      }
+      const int64_t o = ((int64_t)b * nstrips + strip) * N + c0 + threadIdx.x;
+      colpart_m[o] = m;
+      colpart_s[o] = s;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < kRowsPerWarp; ++t) {
+    float m = rm[t], s = rs[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      lse_merge(m, s, m2, s2);
+    }
+    if (lane == 0 && rows[t] < M) lse_row[(int64_t)b * M + rows[t]] = m + logf(s);
+  }
+}
+
+__global__ void assign_col_lse_merge_kernel(const float* __restrict__ colpart_m, const float* __restrict__ colpart_s,
+                                            float* __restrict__ lse_col, int N, int nstrips) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float m = kNegInf, s = 0.f;
+  for (int st = 0; st < nstrips; ++st) {
+    const int64_t o = ((int64_t)b * nstrips + st) * N + j;
+    lse_merge(m, s, colpart_m[o], colpart_s[o]);
+  }
+  lse_col[(int64_t)b * N + j] = m + logf(s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2: scores (optional dense write), row/col max+argmax, positive-weighted sums
+// ---------------------------------------------------------------------------------------------
+struct ScoreArgs {
+  const float* sim;
+  const float* lse_row;
+  const float* lse_col;
+  const float* ls0;   // log sigmoid(z0)   [B,M]
+  const float* ls1;   // log sigmoid(z1)   [B,N]
+  const float* dust0; // log sigmoid(-z0)  [B,M]  (dustbin column)
+  const float* dust1; // log sigmoid(-z1)  [B,N]  (dustbin row)
+  const uint8_t* gt;  // [B,M,N] or null
+  float* scores;      // [B,M+1,N+1] or null
+  float* rowmax; int* rowarg;       // [B,M]
+  float* colpart_v; int* colpart_i; // [B,nstrips,N]
+  float* pos_row_sum;  // [B,M] or null : sum_j gt_ij * (2 sim_ij - lse_row_i - lse_col_j)
+  float* row_expsum;   // [B,M] or null : sum_{j<=N} exp(scores_ij)
+  int M, N, nstrips;
+};
+
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+__global__ void __launch_bounds__(256) assign_scores_kernel(ScoreArgs a) {
+  __shared__ float s_v[2][kWarps][kChunk];
+  __shared__ int s_i[2][kWarps][kChunk];
+  const int b = blockIdx.y, strip = blockIdx.x;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = a.M, N = a.N;
+  const bool vec = (N & 3) == 0;
+  const float* base = a.sim + (int64_t)b * M * N;
+  const uint8_t* gbase = a.gt ? a.gt + (int64_t)b * M * N : nullptr;
+
+  int rows[kRowsPerWarp];
+  float lr[kRowsPerWarp], l0[kRowsPerWarp], bestv[kRowsPerWarp], psum[kRowsPerWarp], esum[kRowsPerWarp];
+  int besti[kRowsPerWarp];
+#pragma unroll
+  for (int t = 0; t < kRowsPerWarp; ++t) {
+    rows[t] = strip * kStripRows + w + kWarps * t;
+    const bool ok = rows[t] < M;
+    lr[t] = ok ? a.lse_row[(int64_t)b * M + rows[t]] : 0.f;
+    l0[t] = ok ? a.ls0[(int64_t)b * M + rows[t]] : 0.f;
+    bestv[t] = kNegInf;
+    besti[t] = 0x7fffffff;
+    psum[t] = 0.f;
+    esum[t] = 0.f;
+  }
+  int buf = 0;
+  for (int c0 = 0; c0 < N; c0 += kChunk, buf ^= 1) {
+    const int col = c0 + lane * 4;
+    const int valid = min(4, N - col);
+    float lc[4], l1[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      lc[e] = e < valid ? a.lse_col[(int64_t)b * N + col + e] : 0.f;
+      l1[e] = e < valid ? a.ls1[(int64_t)b * N + col + e] : 0.f;
+    }
+    float cbv[4];
+    int cbi[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { cbv[e] = kNegInf; cbi[e] = 0x7fffffff; }
+#pragma unroll
+    for (int t = 0; t < kRowsPerWarp; ++t) {
+      if (rows[t] >= M || valid <= 0) continue;
+      const int64_t roff = (int64_t)rows[t] * N + col;
+      float4 x4 = ld4(base + roff, vec, valid);
+      float x[4] = {x4.x, x4.y, x4.z, x4.w};
+      uint32_t g = 0;
+      if (gbase) {
+        if (vec && valid >= 4) g = *reinterpret_cast<const uint32_t*>(gbase + roff);
+        else
+          for (int e = 0; e < valid; ++e) g |= (uint32_t)gbase[roff + e] << (8 * e);
+      }
+      float sc[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        // same association as the reference: (log_softmax_row + log_softmax_col) + (lsig0 + lsig1)
+        sc[e] = ((x[e] - lr[t]) + (x[e] - lc[e])) + (l0[t] + l1[e]);
+        if (e < valid) {
+          if (sc[e] > bestv[t]) { bestv[t] = sc[e]; besti[t] = col + e; }
+          if (better(sc[e], rows[t], cbv[e], cbi[e])) { cbv[e] = sc[e]; cbi[e] = rows[t]; }
+          if ((g >> (8 * e)) & 0xffu) psum[t] += (x[e] - lr[t]) + (x[e] - lc[e]);
+          if (a.row_expsum) esum[t] += __expf(sc[e]);
+        }
+      }
+      if (a.scores) {
+        float* o = a.scores + ((int64_t)b * (M + 1) + rows[t]) * (N + 1) + col;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (e < valid) o[e] = sc[e];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { s_v[buf][w][lane * 4 + e] = cbv[e]; s_i[buf][w][lane * 4 + e] = cbi[e]; }
+    __syncthreads();
+    if (threadIdx.x < kChunk && c0 + threadIdx.x < N) {
+      float v = s_v[buf][0][threadIdx.x];
+      int i = s_i[buf][0][threadIdx.x];
+#pragma unroll
+      for (int ww = 1; ww < kWarps; ++ww) {
+        float v2 = s_v[buf][ww][threadIdx.x];
+        int i2 = s_i[buf][ww][threadIdx.x];
+        if (better(v2, i2, v, i)) { v = v2; i = i2; }
+      }
+      const int64_t o = ((int64_t)b * a.nstrips + strip) * N + c0 + threadIdx.x;
+      a.colpart_v[o] = v;
+      a.colpart_i[o] = i;
+    }
+    // s_v/s_i[buf] are rewritten two chunks later, after the next __syncthreads
+  }
+#pragma unroll
+  for (int t = 0; t < kRowsPerWarp; ++t) {
+    float v = bestv[t];
+    int i = besti[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+      int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+      if (better(v2, i2, v, i)) { v = v2; i = i2; }
+    }
+    float ps = warp_sum(psum[t]);
+    float es = a.row_expsum ? warp_sum(esum[t]) : 0.f;
+    if (lane == 0 && rows[t] < M) {
+      const int64_t r = (int64_t)b * M + rows[t];
+      a.rowmax[r] = v;
+      a.rowarg[r] = i;
+      if (a.pos_row_sum) a.pos_row_sum[r] = ps;
+      const float d0 = a.dust0[r];
+      if (a.row_expsum) a.row_expsum[r] = es + __expf(d0);
+      if (a.scores) a.scores[((int64_t)b * (M + 1) + rows[t]) * (N + 1) + N] = d0;
+    }
+  }
+}
+
+__global__ void assign_col_arg_merge_kernel(const float* __restrict__ colpart_v, const int* __restrict__ colpart_i,
+                                            const float* __restrict__ dust1, float* __restrict__ colmax,
+                                            int* __restrict__ colarg, float* __restrict__ scores, int M, int N,
+                                            int nstrips) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > N) return;
+  if (j == N) {
+    if (scores) scores[((int64_t)b * (M + 1) + M) * (N + 1) + N] = 0.f;
+    return;
+  }
+  float v = kNegInf;
+  int i = 0x7fffffff;
+  for (int st = 0; st < nstrips; ++st) {
+    const int64_t o = ((int64_t)b * nstrips + st) * N + j;
+    const float v2 = colpart_v[o];
+    const int i2 = colpart_i[o];
+    if (better(v2, i2, v, i)) { v = v2; i = i2; }
+  }
+  colmax[(int64_t)b * N + j] = v;
+  colarg[(int64_t)b * N + j] = i;
+  if (scores) scores[((int64_t)b * (M + 1) + M) * (N + 1) + j] = dust1[(int64_t)b * N + j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward of S_pos(sim) = sum_ij gt_ij (2 sim_ij - lse_row_i - lse_col_j):
+//   dsim_ij = 2 c_b gt_ij - exp(sim_ij - lse_row_i) a_row_i - exp(sim_ij - lse_col_j) a_col_j
+// (a_row = c_b * rowcount(gt), a_col = c_b * colcount(gt))
+// ---------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void __launch_bounds__(256) assign_bwd_kernel(const float* __restrict__ sim,
+                                                        const float* __restrict__ lse_row,
+                                                        const float* __restrict__ lse_col,
+                                                        const uint8_t* __restrict__ gt, const float* __restrict__ gcoef,
+                                                        const float* __restrict__ a_row,
+                                                        const float* __restrict__ a_col, OutT* __restrict__ dsim, int M,
+                                                        int N) {
+  const int b = blockIdx.y;
+  const int row = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const bool vec = (N & 3) == 0;
+  const float c2 = 2.f * gcoef[b];
+  const float lr = lse_row[(int64_t)b * M + row];
+  const float ar = a_row[(int64_t)b * M + row];
+  const int64_t roff = ((int64_t)b * M + row) * N;
+  for (int col = lane * 4; col < N; col += 128) {
+    const int valid = min(4, N - col);
+    float4 x4 = ld4(sim + roff + col, vec, valid);
+    float x[4] = {x4.x, x4.y, x4.z, x4.w};
+    uint32_t g = 0;
+    if (vec && valid >= 4) g = *reinterpret_cast<const uint32_t*>(gt + roff + col);
+    else
+      for (int e = 0; e < valid; ++e) g |= (uint32_t)gt[roff + col + e] << (8 * e);
+    float d[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      d[e] = 0.f;
+      if (e < valid) {
+        const float ac = a_col[(int64_t)b * N + col + e];
+        float v = ((g >> (8 * e)) & 0xffu) ? c2 : 0.f;
+        if (ar != 0.f) v -= __expf(x[e] - lr) * ar;
+        if (ac != 0.f) v -= __expf(x[e] - lse_col[(int64_t)b * N + col + e]) * ac;
+        d[e] = v;
+      }
+    }
+    OutT* o = dsim + roff + col;
+    if constexpr (sizeof(OutT) == 4) {
+      if (vec && valid >= 4) *reinterpret_cast<float4*>(o) = make_float4(d[0], d[1], d[2], d[3]);
+      else
+        for (int e = 0; e < valid; ++e) o[e] = d[e];
+    } else {
+      if (vec && valid >= 4) {
+        uint2 p;
+        p.x = pack_bf16(d[0], d[1]);
+        p.y = pack_bf16(d[2], d[3]);
+        *reinterpret_cast<uint2*>(o) = p;
+      } else {
+        for (int e = 0; e < valid; ++e) o[e] = __float2bfloat16(d[e]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// filter_matches (lightglue.py:293-309) from the row/col argmax of pass 2
+// ---------------------------------------------------------------------------------------------
+__global__ void filter_matches_kernel(const float* __restrict__ rowmax, const int* __restrict__ rowarg,
+                                      const int* __restrict__ colarg, float th, int64_t* __restrict__ m0,
+                                      int64_t* __restrict__ m1, float* __restrict__ ms0, float* __restrict__ ms1,
+                                      int M, int N) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int* ra = rowarg + (int64_t)b * M;
+  const int* ca = colarg + (int64_t)b * N;
+  const float* rm = rowmax + (int64_t)b * M;
+  if (t < M) {
+    const int j = ra[t];
+    const bool mutual = (j >= 0 && j < N) && ca[j] == t;
+    const float s = mutual ? expf(rm[t]) : 0.f;
+    const bool valid = mutual && s > th;
+    m0[(int64_t)b * M + t] = valid ? j : -1;
+    ms0[(int64_t)b * M + t] = s;
+  }
+  if (t < N) {
+    const int i = ca[t];
+    const bool mutual1 = (i >= 0 && i < M) && ra[i] == t;
+    float s = 0.f;
+    bool valid = false;
+    if (mutual1) {
+      // mutual1 implies mutual0 of row i (ca[ra[i]] == i)
+      s = expf(rm[i]);
+      valid = s > th;
+    }
+    m1[(int64_t)b * N + t] = valid ? i : -1;
+    ms1[(int64_t)b * N + t] = s;
+  }
+}
+
+}  // namespace lgb
+
+using namespace lgb;
+
+extern "C" {
+
+size_t lgb200_assign_ws_bytes(int B, int M, int N) {
+  const int nstrips = (M + kStripRows - 1) / kStripRows;
+  return (size_t)B * nstrips * N * 8;
+}
+
+int lgb200_assign_lse(const float* sim, float* lse_row, float* lse_col, void* ws, int B, int M, int N,
+                      cudaStream_t stream) {
+  LGB_REQUIRE(sim && lse_row && lse_col && ws, kErrInvalid, "assign_lse: null pointer");
+  LGB_REQUIRE(B > 0 && M > 0 && N > 0, kErrInvalid, "assign_lse: empty input B=%d M=%d N=%d", B, M, N);
+  const int nstrips = (M + kStripRows - 1) / kStripRows;
+  float* pm = static_cast<float*>(ws);
+  float* ps = pm + (size_t)B * nstrips * N;
+  assign_lse_kernel<<<dim3(nstrips, B), 256, 0, stream>>>(sim, lse_row, pm, ps, M, N, nstrips);
+  assign_col_lse_merge_kernel<<<dim3((N + 127) / 128, B), 128, 0, stream>>>(pm, ps, lse_col, N, nstrips);
+  return check_launch("assign_lse");
+}
+
+int lgb200_assign_scores(const float* sim, const float* lse_row, const float* lse_col, const float* ls0,
+                         const float* ls1, const float* dust0, const float* dust1, const uint8_t* gt, float* scores,
+                         float* rowmax, int* rowarg, float* colmax, int* colarg, float* pos_row_sum,
+                         float* row_expsum, void* ws, int B, int M, int N, cudaStream_t stream) {
+  LGB_REQUIRE(sim && lse_row && lse_col && ls0 && ls1 && dust0 && dust1 && rowmax && rowarg && colmax && colarg && ws,
+              kErrInvalid, "assign_scores: null pointer");
+  LGB_REQUIRE(B > 0 && M > 0 && N > 0, kErrInvalid, "assign_scores: empty input");
+  LGB_REQUIRE(!pos_row_sum || gt, kErrInvalid, "assign_scores: pos_row_sum requested without gt");
+  const int nstrips = (M + kStripRows - 1) / kStripRows;
+  ScoreArgs a;
+  a.sim = sim; a.lse_row = lse_row; a.lse_col = lse_col; a.ls0 = ls0; a.ls1 = ls1; a.dust0 = dust0; a.dust1 = dust1;
+  a.gt = gt; a.scores = scores; a.rowmax = rowmax; a.rowarg = rowarg;
+  a.colpart_v = static_cast<float*>(ws);
+  a.colpart_i = reinterpret_cast<int*>(a.colpart_v + (size_t)B * nstrips * N);
+  a.pos_row_sum = pos_row_sum; a.row_expsum = row_expsum; a.M = M; a.N = N; a.nstrips = nstrips;
+  assign_scores_kernel<<<dim3(nstrips, B), 256, 0, stream>>>(a);
+  assign_col_arg_merge_kernel<<<dim3((N + 1 + 127) / 128, B), 128, 0, stream>>>(a.colpart_v, a.colpart_i, dust1, colmax,
+                                                                                colarg, scores, M, N, nstrips);
+  return check_launch("assign_scores");
+}
+
+int lgb200_assign_bwd(const float* sim, const float* lse_row, const float* lse_col, const uint8_t* gt,
+                      const float* gcoef, const float* a_row, const float* a_col, void* dsim, int out_dtype, int B,
+                      int M, int N, cudaStream_t stream) {
+  LGB_REQUIRE(sim && lse_row && lse_col && gt && gcoef && a_row && a_col && dsim, kErrInvalid,
+              "assign_bwd: null pointer");
+  LGB_REQUIRE(B > 0 && M > 0 && N > 0, kErrInvalid, "assign_bwd: empty input");
+  dim3 grid((M + kWarps - 1) / kWarps, B);
+  if (out_dtype == LGB200_F32)
+    assign_bwd_kernel<float><<<grid, 256, 0, stream>>>(sim, lse_row, lse_col, gt, gcoef, a_row, a_col,
+                                                       static_cast<float*>(dsim), M, N);
+  else if (out_dtype == LGB200_BF16)
+    assign_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(sim, lse_row, lse_col, gt, gcoef, a_row, a_col,
+                                                               static_cast<__nv_bfloat16*>(dsim), M, N);
+  else
+    LGB_REQUIRE(false, kErrInvalid, "assign_bwd: bad out_dtype %d", out_dtype);
+  return check_launch("assign_bwd");
+}
+
+int lgb200_filter_matches(const float* rowmax, const int* rowarg, const int* colarg, float th, int64_t* m0,
+                          int64_t* m1, float* ms0, float* ms1, int B, int M, int N, cudaStream_t stream) {
+  LGB_REQUIRE(rowmax && rowarg && colarg && m0 && m1 && ms0 && ms1, kErrInvalid, "filter_matches: null pointer");
+  LGB_REQUIRE(B > 0 && M > 0 && N > 0, kErrInvalid, "filter_matches: empty input");
+  const int L = M > N ? M : N;
+  filter_matches_kernel<<<dim3((L + 255) / 256, B), 256, 0, stream>>>(rowmax, rowarg, colarg, th, m0, m1, ms0, ms1, M,
+                                                                      N);
+  return check_launch("filter_matches");
+}
+
+}  // extern "C"

@@ -1,0 +1,463 @@
+// Memory-bound helpers of the matcher layer:
+//   * rope_split  : de-interleave the Wqkv output (feature = h*192 + d*3 + {q,k,v}) and apply the
+//                   cached rotary encoding to q and k   (lightglue.py:42-49, 156-160)
+//   * ln_gelu     : LayerNorm(2D) + exact-erf GELU of the FFN (lightglue.py:143-148)
+//   * adam_flat   : Adam on the flat parameter buffer (train.py:358-361, 513)
+// All use 128-bit loads/stores; row reductions are warp shuffles.
+#include <math.h>
+
+#include "common.cuh"
+#include "lgb200.h"
+
+namespace lgb {
+
+template <typename T> struct Vec8;  // 8 consecutive elements
+template <> struct Vec8<float> {
+  float v[8];
+  __device__ static Vec8 load(const float* p) {
+    Vec8 r;
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+  }
+  __device__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  float v[8];
+  __device__ static Vec8 load(const __nv_bfloat16* p) {
+    Vec8 r;
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r.v[2 * i] = __uint_as_float(w[i] << 16);
+      r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+    return r;
+  }
+  __device__ void store(__nv_bfloat16* p) const {
+    uint4 u;
+    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// rope_split: thread <-> (token, group of 4 rotary pairs = 8 channels), loops over heads.
+// qkv row layout per head: [q0 k0 v0 q1 k1 v1 ... q63 k63 v63]; the 8 channels of a group are 24
+// consecutive elements.  Outputs are token-major [T, H*64].
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) rope_split_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ theta,
+                                                            T* __restrict__ q, T* __restrict__ k, T* __restrict__ v,
+                                                            int64_t ntok, int H) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tok = gid >> 3;
+  const int grp = (int)(gid & 7);
+  if (tok >= ntok) return;
+  float c[4], s[4];
+  {
+    const float4 th = *reinterpret_cast<const float4*>(theta + tok * 32 + grp * 4);
+    sincosf(th.x, &s[0], &c[0]); sincosf(th.y, &s[1], &c[1]); sincosf(th.z, &s[2], &c[2]); sincosf(th.w, &s[3], &c[3]);
+  }
+  for (int h = 0; h < H; ++h) {
+    const T* src = qkv + tok * (int64_t)(H * 192) + h * 192 + grp * 24;
+    Vec8<T> a = Vec8<T>::load(src), b = Vec8<T>::load(src + 8), d = Vec8<T>::load(src + 16);
+    float f[24];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { f[i] = a.v[i]; f[8 + i] = b.v[i]; f[16 + i] = d.v[i]; }
+    Vec8<T> oq, ok, ov;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float q0 = f[6 * p + 0], k0 = f[6 * p + 1], v0 = f[6 * p + 2];
+      const float q1 = f[6 * p + 3], k1 = f[6 * p + 4], v1 = f[6 * p + 5];
+      oq.v[2 * p] = q0 * c[p] - q1 * s[p];
+      oq.v[2 * p + 1] = q1 * c[p] + q0 * s[p];
+      ok.v[2 * p] = k0 * c[p] - k1 * s[p];
+      ok.v[2 * p + 1] = k1 * c[p] + k0 * s[p];
+      ov.v[2 * p] = v0;
+      ov.v[2 * p + 1] = v1;
+    }
+    const int64_t o = tok * (int64_t)(H * 64) + h * 64 + grp * 8;
+    oq.store(q + o);
+    ok.store(k + o);
+    ov.store(v + o);
+  }
+}
+
+// backward: dq,dk are gradients w.r.t. the ROTATED q,k; q,k are the rotated values saved by forward.
+//   d(unrotated) = R(-theta) d(rotated);  dtheta_p += sum_heads ( dq'[2p+1] q'[2p] - dq'[2p] q'[2p+1] ) + same for k
+template <typename T>
+__global__ void __launch_bounds__(256) rope_split_bwd_kernel(const T* __restrict__ dq, const T* __restrict__ dk,
+                                                            const T* __restrict__ dv, const T* __restrict__ q,
+                                                            const T* __restrict__ k, const float* __restrict__ theta,
+                                                            T* __restrict__ dqkv, float* __restrict__ dtheta,
+                                                            int64_t ntok, int H) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tok = gid >> 3;
+  const int grp = (int)(gid & 7);
+  if (tok >= ntok) return;
+  float c[4], s[4], dth[4] = {0.f, 0.f, 0.f, 0.f};
+  {
+    const float4 th = *reinterpret_cast<const float4*>(theta + tok * 32 + grp * 4);
+    sincosf(th.x, &s[0], &c[0]); sincosf(th.y, &s[1], &c[1]); sincosf(th.z, &s[2], &c[2]); sincosf(th.w, &s[3], &c[3]);
+  }
+  for (int h = 0; h < H; ++h) {
+    const int64_t o = tok * (int64_t)(H * 64) + h * 64 + grp * 8;
+    Vec8<T> gq = Vec8<T>::load(dq + o), gk = Vec8<T>::load(dk + o), gv = Vec8<T>::load(dv + o);
+    Vec8<T> rq = Vec8<T>::load(q + o), rk = Vec8<T>::load(k + o);
+    float f[24];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float a0 = gq.v[2 * p], a1 = gq.v[2 * p + 1], b0 = gk.v[2 * p], b1 = gk.v[2 * p + 1];
+      dth[p] += (a1 * rq.v[2 * p] - a0 * rq.v[2 * p + 1]) + (b1 * rk.v[2 * p] - b0 * rk.v[2 * p + 1]);
+      f[6 * p + 0] = a0 * c[p] + a1 * s[p];
+      f[6 * p + 3] = a1 * c[p] - a0 * s[p];
+      f[6 * p + 1] = b0 * c[p] + b1 * s[p];
+      f[6 * p + 4] = b1 * c[p] - b0 * s[p];
+      f[6 * p + 2] = gv.v[2 * p];
+      f[6 * p + 5] = gv.v[2 * p + 1];
+    }
+    Vec8<T> a, b, d;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a.v[i] = f[i]; b.v[i] = f[8 + i]; d.v[i] = f[16 + i]; }
+    T* dst = dqkv + tok * (int64_t)(H * 192) + h * 192 + grp * 24;
+    a.store(dst);
+    b.store(dst + 8);
+    d.store(dst + 16);
+  }
+  float4* pt = reinterpret_cast<float4*>(dtheta + tok * 32 + grp * 4);
+  float4 acc = *pt;  // accumulated across layers; this thread is the only writer of these 4 floats
+  acc.x += dth[0]; acc.y += dth[1]; acc.z += dth[2]; acc.w += dth[3];
+  *pt = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm + GELU: one warp per token, W = 128 * VPL channels (VPL float4/bf16x4 groups per lane)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+template <typename T> __device__ __forceinline__ void load4(const T* p, float* o);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float* o) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+}
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float* o) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  o[0] = __uint_as_float(u.x << 16); o[1] = __uint_as_float(u.x & 0xffff0000u);
+  o[2] = __uint_as_float(u.y << 16); o[3] = __uint_as_float(u.y & 0xffff0000u);
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, const float* o);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float* o) {
+  *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float* o) {
+  uint2 u;
+  u.x = pack_bf16(o[0], o[1]);
+  u.y = pack_bf16(o[2], o[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256) ln_gelu_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, T* __restrict__ y,
+                                                         float* __restrict__ mean, float* __restrict__ rstd,
+                                                         int64_t ntok, float eps) {
+  constexpr int W = 128 * VPL;
+  const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tok >= ntok) return;
+  float v[VPL][4];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    load4<T>(x + tok * W + i * 128 + lane * 4, v[i]);
+    sum += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+  }
+  const float mu = warp_sum(sum) * (1.f / W);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float d = v[i][e] - mu;
+      sq += d * d;
+    }
+  const float rs = rsqrtf(warp_sum(sq) * (1.f / W) + eps);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    float g[4], bb[4], o[4];
+    load4<float>(gamma + i * 128 + lane * 4, g);
+    load4<float>(beta + i * 128 + lane * 4, bb);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = gelu_f((v[i][e] - mu) * rs * g[e] + bb[e]);
+    store4<T>(y + tok * W + i * 128 + lane * 4, o);
+  }
+  if (lane == 0) {
+    mean[tok] = mu;
+    rstd[tok] = rs;
+  }
+}
+
+// backward: each CTA (8 warps) walks tokens blockIdx.x*8 + warp, + gridDim.x*8, ... and keeps per-lane
+// partial dgamma/dbeta; the 8 warps are reduced through smem and written as one partial row per CTA.
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, const float* __restrict__ mean,
+                                                         const float* __restrict__ rstd, T* __restrict__ dx,
+                                                         float* __restrict__ dgamma_part,
+                                                         float* __restrict__ dbeta_part, int64_t ntok) {
+  constexpr int W = 128 * VPL;
+  __shared__ float s_red[8][W];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float g[VPL][4], bb[VPL][4], dg[VPL][4], db[VPL][4];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    load4<float>(gamma + i * 128 + lane * 4, g[i]);
+    load4<float>(beta + i * 128 + lane * 4, bb[i]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dg[i][e] = db[i][e] = 0.f;
+  }
+  for (int64_t tok = (int64_t)blockIdx.x * 8 + warp; tok < ntok; tok += (int64_t)gridDim.x * 8) {
+    const float mu = mean[tok], rs = rstd[tok];
+    float xh[VPL][4], dz[VPL][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float xv[4], gy[4];
+      load4<T>(x + tok * W + i * 128 + lane * 4, xv);
+      load4<T>(dy + tok * W + i * 128 + lane * 4, gy);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        xh[i][e] = (xv[e] - mu) * rs;
+        const float z = xh[i][e] * g[i][e] + bb[i][e];
+        const float dzz = gy[e] * gelu_grad(z);  // dL/dz (LN output)
+        dg[i][e] += dzz * xh[i][e];
+        db[i][e] += dzz;
+        dz[i][e] = dzz * g[i][e];  // dL/dxhat
+        s1 += dz[i][e];
+        s2 += dz[i][e] * xh[i][e];
+      }
+    }
+    s1 = warp_sum(s1) * (1.f / W);
+    s2 = warp_sum(s2) * (1.f / W);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = rs * (dz[i][e] - s1 - xh[i][e] * s2);
+      store4<T>(dx + tok * W + i * 128 + lane * 4, o);
+    }
+  }
+  // reduce dgamma then dbeta over the 8 warps
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s_red[warp][i * 128 + lane * 4 + e] = pass == 0 ? dg[i][e] : db[i][e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < W; c += 256) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) acc += s_red[w][c];
+      (pass == 0 ? dgamma_part : dbeta_part)[(int64_t)blockIdx.x * W + c] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam on the flat buffer.  g is multiplied by grad_scale (1/world for the summed all-reduce, or the
+// inverse AMP loss scale).  Matches torch.optim.Adam (no amsgrad, L2 weight decay added to the grad).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                       const float* __restrict__ lr_per_elem_or_null, float lr,
+                                                       float beta1, float beta2, float eps, float wd, float bc1,
+                                                       float bc2_sqrt, float grad_scale) {
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= n) return;
+  if (i0 + 4 <= n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i0), gg = *reinterpret_cast<const float4*>(g + i0);
+    float4 mm = *reinterpret_cast<float4*>(m + i0), vv = *reinterpret_cast<float4*>(v + i0);
+    float P[4] = {pp.x, pp.y, pp.z, pp.w}, G[4] = {gg.x, gg.y, gg.z, gg.w};
+    float Mm[4] = {mm.x, mm.y, mm.z, mm.w}, V[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float l = lr_per_elem_or_null ? lr_per_elem_or_null[i0 + e] : lr;
+      float gr = G[e] * grad_scale + wd * P[e];
+      Mm[e] = beta1 * Mm[e] + (1.f - beta1) * gr;
+      V[e] = beta2 * V[e] + (1.f - beta2) * gr * gr;
+      const float denom = sqrtf(V[e]) / bc2_sqrt + eps;
+      P[e] -= (l / bc1) * (Mm[e] / denom);
+    }
+    *reinterpret_cast<float4*>(p + i0) = make_float4(P[0], P[1], P[2], P[3]);
+    *reinterpret_cast<float4*>(m + i0) = make_float4(Mm[0], Mm[1], Mm[2], Mm[3]);
+    *reinterpret_cast<float4*>(v + i0) = make_float4(V[0], V[1], V[2], V[3]);
+  } else {
+    for (int64_t i = i0; i < n; ++i) {
+      const float l = lr_per_elem_or_null ? lr_per_elem_or_null[i] : lr;
+      float gr = g[i] * grad_scale + wd * p[i];
+      m[i] = beta1 * m[i] + (1.f - beta1) * gr;
+      v[i] = beta2 * v[i] + (1.f - beta2) * gr * gr;
+      const float denom = sqrtf(v[i]) / bc2_sqrt + eps;
+      p[i] -= (l / bc1) * (m[i] / denom);
+    }
+  }
+}
+
+// fp32 -> bf16 cast of a flat buffer (bf16 shadow of the weights / activations)
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                       int64_t n) {
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i0 >= n) return;
+  if (i0 + 8 <= n) {
+    Vec8<float> a = Vec8<float>::load(src + i0);
+    Vec8<__nv_bfloat16> b;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) b.v[e] = a.v[e];
+    b.store(dst + i0);
+  } else {
+    for (int64_t i = i0; i < n; ++i) dst[i] = __float2bfloat16(src[i]);
+  }
+}
+
+}  // namespace lgb
+
+using namespace lgb;
+
+extern "C" {
+
+int lgb200_rope_split_fwd(const void* qkv, const float* theta, void* q, void* k, void* v, int64_t ntok, int H,
+                          int dtype, cudaStream_t stream) {
+  LGB_REQUIRE(qkv && theta && q && k && v, kErrInvalid, "rope_split_fwd: null pointer");
+  LGB_REQUIRE(ntok > 0 && H > 0, kErrInvalid, "rope_split_fwd: empty input");
+  const int64_t nthr = ntok * 8;
+  const unsigned grid = (unsigned)((nthr + 255) / 256);
+  if (dtype == LGB200_F32)
+    rope_split_fwd_kernel<float><<<grid, 256, 0, stream>>>((const float*)qkv, theta, (float*)q, (float*)k, (float*)v,
+                                                           ntok, H);
+  else if (dtype == LGB200_BF16)
+    rope_split_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)qkv, theta, (__nv_bfloat16*)q,
+                                                                   (__nv_bfloat16*)k, (__nv_bfloat16*)v, ntok, H);
+  else
+    LGB_REQUIRE(false, kErrInvalid, "rope_split_fwd: bad dtype %d", dtype);
+  return check_launch("rope_split_fwd");
+}
+
+int lgb200_rope_split_bwd(const void* dq, const void* dk, const void* dv, const void* q, const void* k,
+                          const float* theta, void* dqkv, float* dtheta, int64_t ntok, int H, int dtype,
+                          cudaStream_t stream) {
+  LGB_REQUIRE(dq && dk && dv && q && k && theta && dqkv && dtheta, kErrInvalid, "rope_split_bwd: null pointer");
+  LGB_REQUIRE(ntok > 0 && H > 0, kErrInvalid, "rope_split_bwd: empty input");
+  const int64_t nthr = ntok * 8;
+  const unsigned grid = (unsigned)((nthr + 255) / 256);
+  if (dtype == LGB200_F32)
+    rope_split_bwd_kernel<float><<<grid, 256, 0, stream>>>((const float*)dq, (const float*)dk, (const float*)dv,
+                                                           (const float*)q, (const float*)k, theta, (float*)dqkv,
+                                                           dtheta, ntok, H);
+  else if (dtype == LGB200_BF16)
+    rope_split_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        (const __nv_bfloat16*)dq, (const __nv_bfloat16*)dk, (const __nv_bfloat16*)dv, (const __nv_bfloat16*)q,
+        (const __nv_bfloat16*)k, theta, (__nv_bfloat16*)dqkv, dtheta, ntok, H);
+  else
+    LGB_REQUIRE(false, kErrInvalid, "rope_split_bwd: bad dtype %d", dtype);
+  return check_launch("rope_split_bwd");
+}
+
+}  // extern "C"
+
+template <typename T>
+static int ln_gelu_fwd_dispatch(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                float* rstd, int64_t ntok, int W, float eps, cudaStream_t stream) {
+  const unsigned grid = (unsigned)((ntok + 7) / 8);
+  switch (W) {
+    case 256: ln_gelu_fwd_kernel<T, 2><<<grid, 256, 0, stream>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, ntok, eps); break;
+    case 512: ln_gelu_fwd_kernel<T, 4><<<grid, 256, 0, stream>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, ntok, eps); break;
+    case 1024: ln_gelu_fwd_kernel<T, 8><<<grid, 256, 0, stream>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, ntok, eps); break;
+    default: LGB_REQUIRE(false, kErrUnsupported, "ln_gelu: width %d not in {256,512,1024}", W);
+  }
+  return check_launch("ln_gelu_fwd");
+}
+
+extern "C" {
+
+int lgb200_ln_gelu_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                       int64_t ntok, int W, float eps, int dtype, cudaStream_t stream) {
+  LGB_REQUIRE(x && gamma && beta && y && mean && rstd, kErrInvalid, "ln_gelu_fwd: null pointer");
+  LGB_REQUIRE(ntok > 0, kErrInvalid, "ln_gelu_fwd: empty input");
+  if (dtype == LGB200_F32) return ln_gelu_fwd_dispatch<float>(x, gamma, beta, y, mean, rstd, ntok, W, eps, stream);
+  if (dtype == LGB200_BF16) return ln_gelu_fwd_dispatch<__nv_bfloat16>(x, gamma, beta, y, mean, rstd, ntok, W, eps, stream);
+  LGB_REQUIRE(false, kErrInvalid, "ln_gelu_fwd: bad dtype %d", dtype);
+}
+
+int lgb200_ln_gelu_bwd_parts(int64_t ntok) {
+  int64_t p = (ntok + 7) / 8;
+  return (int)(p < 296 ? p : 296);  // 2 CTAs per SM on 148 SMs
+}
+
+}  // extern "C"
+
+template <typename T>
+static int ln_gelu_bwd_dispatch(const void* dy, const void* x, const float* gamma, const float* beta,
+                                const float* mean, const float* rstd, void* dx, float* dgp, float* dbp, int64_t ntok,
+                                int W, cudaStream_t stream) {
+  const unsigned grid = (unsigned)lgb200_ln_gelu_bwd_parts(ntok);
+  switch (W) {
+    case 256: ln_gelu_bwd_kernel<T, 2><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, ntok); break;
+    case 512: ln_gelu_bwd_kernel<T, 4><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, ntok); break;
+    case 1024: ln_gelu_bwd_kernel<T, 8><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, ntok); break;
+    default: LGB_REQUIRE(false, kErrUnsupported, "ln_gelu: width %d not in {256,512,1024}", W);
+  }
+  return check_launch("ln_gelu_bwd");
+}
+
+extern "C" {
+
+int lgb200_ln_gelu_bwd(const void* dy, const void* x, const float* gamma, const float* beta, const float* mean,
+                       const float* rstd, void* dx, float* dgamma_part, float* dbeta_part, int64_t ntok, int W,
+                       int dtype, cudaStream_t stream) {
+  LGB_REQUIRE(dy && x && gamma && beta && mean && rstd && dx && dgamma_part && dbeta_part, kErrInvalid,
+              "ln_gelu_bwd: null pointer");
+  LGB_REQUIRE(ntok > 0, kErrInvalid, "ln_gelu_bwd: empty input");
+  if (dtype == LGB200_F32)
+    return ln_gelu_bwd_dispatch<float>(dy, x, gamma, beta, mean, rstd, dx, dgamma_part, dbeta_part, ntok, W, stream);
+  if (dtype == LGB200_BF16)
+    return ln_gelu_bwd_dispatch<__nv_bfloat16>(dy, x, gamma, beta, mean, rstd, dx, dgamma_part, dbeta_part, ntok, W, stream);
+  LGB_REQUIRE(false, kErrInvalid, "ln_gelu_bwd: bad dtype %d", dtype);
+}
+
+int lgb200_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_per_elem, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                     cudaStream_t stream) {
+  LGB_REQUIRE(p && g && m && v, kErrInvalid, "adam_flat: null pointer");
+  LGB_REQUIRE(n > 0 && step >= 1, kErrInvalid, "adam_flat: bad n/step");
+  LGB_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+               reinterpret_cast<uintptr_t>(v)) % 16 == 0,
+              kErrInvalid, "adam_flat: buffers must be 16-byte aligned");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  const unsigned grid = (unsigned)(((n + 3) / 4 + 255) / 256);
+  adam_flat_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n, lr_per_elem, lr, beta1, beta2, eps, weight_decay, bc1, bc2s,
+                                             grad_scale);
+  return check_launch("adam_flat");
+}
+
+int lgb200_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream) {
+  LGB_REQUIRE(src && dst && n > 0, kErrInvalid, "cast_bf16: bad arguments");
+  const unsigned grid = (unsigned)(((n + 7) / 8 + 255) / 256);
+  cast_bf16_kernel<<<grid, 256, 0, stream>>>(src, (__nv_bfloat16*)dst, n);
+  return check_launch("cast_bf16");
+}
+
+}  // extern "C"

@@ -1,0 +1,387 @@
+"""B200-native LightGlue matcher -- drop-in for gluefactory's in-tree matcher.
+
+Select it from a glue-factory config with
+
+    model:
+      matcher:
+        name: gluefactory_b200.matchers.lightglue     # instead of matchers.lightglue
+
+`get_model` (reference gluefactory/models/__init__.py:7-30) imports this module,
+finds no BaseModel subclass and returns `__main_model__`, exactly as it does for
+the reference matcher (gluefactory/models/matchers/lightglue.py:312, 630).
+
+Same constructor (`cls(conf_dict)`), same `forward(data) -> pred`, same
+`loss(pred, data) -> (losses, metrics)`, same parameter names (state_dict /
+checkpoints are interchangeable).  The arithmetic of
+the N x N path -- rotary split, self / cross attention, LayerNorm+GELU, the
+assignment head, its NLL terms, argmax and match filtering, and all of their
+backward passes -- runs in the hand-written sm_100a kernels behind the C ABI
+of include/lgb200.h.  The small dense projections (nn.Linear) go through
+cuBLAS via torch.  There is no CPU path: without the built library and a B200
+`forward` raises.
+
+conf additions over the reference's default_conf:
+    precision: "bf16" -> bf16 operands / fp32 accumulation on the tcgen05 tensor cores (default)
+               "fp32" -> full-precision parity path (CUDA cores + fp32 cuBLAS)
+"""
+import copy
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import _lib, ops
+
+
+class _Conf(dict):
+    """Attribute-access view of a (nested) plain dict (stands in for OmegaConf's DictConfig)."""
+
+    def __getattr__(self, k):
+        try:
+            v = self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+        return _Conf(v) if isinstance(v, dict) and not isinstance(v, _Conf) else v
+
+
+def _to_plain(conf):
+    if conf is None:
+        return {}
+    try:  # OmegaConf DictConfig, when the host framework passes one
+        from omegaconf import OmegaConf  # type: ignore
+
+        if OmegaConf.is_config(conf):
+            return OmegaConf.to_container(conf, resolve=True)
+    except Exception:
+        pass
+    return {k: (_to_plain(v) if isinstance(v, dict) else v) for k, v in dict(conf).items()}
+
+
+def _merge(base, new):
+    out = copy.deepcopy(base)
+    for k, v in new.items():
+        if isinstance(v, dict) and isinstance(out.get(k), dict):
+            out[k] = _merge(out[k], v)
+        else:
+            out[k] = copy.deepcopy(v)
+    return out
+
+
+def normalize_keypoints(kpts, size):
+    """lightglue.py:27-39 (always fp32, like the reference's custom_fwd cast)."""
+    kpts = kpts.float()
+    if size is None:
+        size = 1 + kpts.max(-2).values - kpts.min(-2).values
+    elif not isinstance(size, torch.Tensor):
+        size = torch.tensor(size, device=kpts.device, dtype=kpts.dtype)
+    size = size.to(kpts)
+    shift = size / 2
+    scale = size.max(-1).values / 2
+    return (kpts - shift[..., None, :]) / scale[..., None, None]
+
+
+# ---- parameter containers: same module tree / names as the reference (lightglue.py:52-65, 131-148,
+# ---- 166-183, 271-276, 68-72).  They only hold parameters; the math lives in LightGlue below.
+class LearnableFourierPositionalEncoding(nn.Module):
+    def __init__(self, M, dim, F_dim=None, gamma=1.0):
+        super().__init__()
+        F_dim = F_dim if F_dim is not None else dim
+        self.Wr = nn.Linear(M, F_dim // 2, bias=False)
+        nn.init.normal_(self.Wr.weight.data, mean=0, std=gamma**-2)
+
+
+def _ffn(d):
+    return nn.Sequential(nn.Linear(2 * d, 2 * d), nn.LayerNorm(2 * d, elementwise_affine=True), nn.GELU(),
+                         nn.Linear(2 * d, d))
+
+
+class SelfBlock(nn.Module):
+    def __init__(self, d, h):
+        super().__init__()
+        self.Wqkv = nn.Linear(d, 3 * d)
+        self.out_proj = nn.Linear(d, d)
+        self.ffn = _ffn(d)
+
+
+class CrossBlock(nn.Module):
+    def __init__(self, d, h):
+        super().__init__()
+        self.to_qk = nn.Linear(d, d)
+        self.to_v = nn.Linear(d, d)
+        self.to_out = nn.Linear(d, d)
+        self.ffn = _ffn(d)
+
+
+class TransformerLayer(nn.Module):
+    def __init__(self, d, h):
+        super().__init__()
+        self.self_attn = SelfBlock(d, h)
+        self.cross_attn = CrossBlock(d, h)
+
+
+class MatchAssignment(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.matchability = nn.Linear(d, 1)
+        self.final_proj = nn.Linear(d, d)
+
+
+class TokenConfidence(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.token = nn.Sequential(nn.Linear(d, 1), nn.Sigmoid())
+
+
+class LightGlue(nn.Module):
+    default_conf = {
+        "name": "lightglue",
+        "input_dim": 256,
+        "add_scale_ori": False,
+        "descriptor_dim": 256,
+        "n_layers": 9,
+        "num_heads": 4,
+        "flash": False,  # accepted for config compatibility; attention is always the fused kernel
+        "mp": False,
+        "depth_confidence": -1,
+        "width_confidence": -1,
+        "filter_threshold": 0.0,
+        "checkpointed": False,  # accepted; the fused attention keeps no N x N activations to checkpoint
+        "weights": None,
+        "weights_from_version": "v0.1_arxiv",
+        "loss": {"gamma": 1.0, "fn": "nll", "nll_balancing": 0.5},
+        "precision": "bf16",
+    }
+    required_data_keys = ["keypoints0", "keypoints1", "descriptors0", "descriptors1"]
+
+    def __init__(self, conf=None):
+        super().__init__()
+        self.conf = conf = _Conf(_merge(self.default_conf, _to_plain(conf)))
+        assert conf.precision in ("bf16", "fp32"), conf.precision
+        d, h, n = conf.descriptor_dim, conf.num_heads, conf.n_layers
+        assert d % h == 0 and d // h == 64, "the lgb200 kernels are built for head_dim 64"
+        if conf.add_scale_ori:
+            raise NotImplementedError("add_scale_ori (SIFT scale/orientation encoding) is not built yet")
+        self.input_proj = nn.Linear(conf.input_dim, d) if conf.input_dim != d else nn.Identity()
+        self.posenc = LearnableFourierPositionalEncoding(2, 64, 64)
+        self.transformers = nn.ModuleList([TransformerLayer(d, h) for _ in range(n)])
+        self.log_assignment = nn.ModuleList([MatchAssignment(d) for _ in range(n)])
+        self.token_confidence = nn.ModuleList([TokenConfidence(d) for _ in range(n - 1)])
+        self.register_buffer(
+            "confidence_thresholds",
+            torch.tensor([min(max(0.8 + 0.1 * math.exp(-4.0 * i / n), 0.0), 1.0) for i in range(n)]))
+        if conf.weights is not None:
+            state_dict = torch.load(conf.weights, map_location="cpu")
+            for i in range(n):  # legacy names, lightglue.py:384-391
+                state_dict = {k.replace(f"self_attn.{i}", f"transformers.{i}.self_attn"): v for k, v in state_dict.items()}
+                state_dict = {k.replace(f"cross_attn.{i}", f"transformers.{i}.cross_attn"): v for k, v in state_dict.items()}
+            self.load_state_dict(state_dict, strict=False)
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def _bf16(self):
+        return self.conf.precision == "bf16"
+
+    def _lin(self, x, layer):
+        """nn.Linear through cuBLAS; bf16 operands in bf16 mode (fp32 accumulate inside cuBLAS)."""
+        if self._bf16:
+            return F.linear(x.to(torch.bfloat16), layer.weight.to(torch.bfloat16), layer.bias.to(torch.bfloat16))
+        return F.linear(x, layer.weight, layer.bias)
+
+    def _ffn(self, x, msg, ffn):
+        """x + Linear(GELU(LN(Linear([x, msg]))))   (lightglue.py:163, 219-220); x is the fp32 residual."""
+        cdt = torch.bfloat16 if self._bf16 else torch.float32
+        h = self._lin(torch.cat([x.to(cdt), msg.to(cdt)], -1), ffn[0])
+        h = ops.LnGelu.apply(h.contiguous(), ffn[1].weight, ffn[1].bias, ffn[1].eps)
+        return x + self._lin(h, ffn[3]).float()
+
+    def _attend(self, q, k, v, sizes, cross):
+        """q,k,v [T, D] token-major over the concatenated tokens [image0 (B*M) ; image1 (B*N)]."""
+        B, M, N = sizes
+        H = self.conf.num_heads
+        scale = 64**-0.5
+        if M == N:
+            shp = (2 * B, M, H, 64)
+            return ops.Attention.apply(q.view(shp), k.view(shp), v.view(shp), B if cross else 0, scale).view(q.shape)
+        t0 = B * M
+        q0, q1 = q[:t0].view(B, M, H, 64), q[t0:].view(B, N, H, 64)
+        k0, k1 = k[:t0].view(B, M, H, 64), k[t0:].view(B, N, H, 64)
+        v0, v1 = v[:t0].view(B, M, H, 64), v[t0:].view(B, N, H, 64)
+        if cross:
+            o0 = ops.Attention.apply(q0, k1, v1, 0, scale)
+            o1 = ops.Attention.apply(q1, k0, v0, 0, scale)
+        else:
+            o0 = ops.Attention.apply(q0, k0, v0, 0, scale)
+            o1 = ops.Attention.apply(q1, k1, v1, 0, scale)
+        return torch.cat([o0.reshape(t0, -1), o1.reshape(B * N, -1)], 0)
+
+    def _layer(self, x, theta, layer, sizes):
+        H = self.conf.num_heads
+        sa, ca = layer.self_attn, layer.cross_attn
+        # ---- self block (lightglue.py:150-163)
+        qkv = self._lin(x, sa.Wqkv).contiguous()
+        q, k, v = ops.RopeSplit.apply(qkv, theta, H)
+        ctx = self._attend(q, k, v, sizes, cross=False)
+        x = self._ffn(x, self._lin(ctx, sa.out_proj), sa.ffn)
+        # ---- cross block (lightglue.py:195-221); both directions share to_qk / to_v
+        qk = self._lin(x, ca.to_qk).contiguous()
+        vv = self._lin(x, ca.to_v).contiguous()
+        m = self._attend(qk, qk, vv, sizes, cross=True)
+        return self._ffn(x, self._lin(m, ca.to_out), ca.ffn)
+
+    def _head_inputs(self, d0, d1, i):
+        """final_proj / matchability of layer i (lightglue.py:280-285)."""
+        la = self.log_assignment[i]
+        D = d0.shape[-1]
+        md0 = self._lin(d0, la.final_proj).float() / D**0.25
+        md1 = self._lin(d1, la.final_proj).float() / D**0.25
+        z0 = F.linear(d0, la.matchability.weight, la.matchability.bias).squeeze(-1)
+        z1 = F.linear(d1, la.matchability.weight, la.matchability.bias).squeeze(-1)
+        return md0.contiguous(), md1.contiguous(), z0, z1
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, data):
+        for key in self.required_data_keys:
+            assert key in data, f"Missing key {key} in data"
+        _lib.load()  # raises unless the CUDA library is built and the device is a B200 (no CPU fallback)
+        conf = self.conf
+        if not self.training and (conf.depth_confidence > 0 or conf.width_confidence > 0):
+            raise NotImplementedError("adaptive depth/width (early stop, point pruning) is not built yet; "
+                                      "set depth_confidence = width_confidence = -1")
+        kpts0, kpts1 = data["keypoints0"], data["keypoints1"]
+        B, M, _ = kpts0.shape
+        N = kpts1.shape[1]
+        assert M > 0 and N > 0, "empty keypoint sets are not supported"
+        size0 = data["view0"].get("image_size") if "view0" in data else None
+        size1 = data["view1"].get("image_size") if "view1" in data else None
+        kpts0, kpts1 = normalize_keypoints(kpts0, size0), normalize_keypoints(kpts1, size1)
+        desc0, desc1 = data["descriptors0"].contiguous(), data["descriptors1"].contiguous()
+        assert desc0.shape[-1] == conf.input_dim and desc1.shape[-1] == conf.input_dim
+        D = conf.descriptor_dim
+        x = torch.cat([desc0.reshape(B * M, -1), desc1.reshape(B * N, -1)], 0).float()
+        if not isinstance(self.input_proj, nn.Identity):
+            x = self._lin(x, self.input_proj).float()
+        # rotary angles, cached for all layers (lightglue.py:456-458); cos/sin are taken in-kernel
+        kp = torch.cat([kpts0.reshape(B * M, 2), kpts1.reshape(B * N, 2)], 0)
+        theta = F.linear(kp, self.posenc.Wr.weight.float()).contiguous()
+        sizes = (B, M, N)
+        all0, all1 = [], []
+        L = conf.n_layers
+        for i in range(L):
+            x = self._layer(x, theta, self.transformers[i], sizes)
+            if self.training or i == L - 1:
+                all0.append(x[: B * M].view(B, M, D))
+                all1.append(x[B * M:].view(B, N, D))
+        d0, d1 = all0[-1], all1[-1]
+        with torch.no_grad():
+            md0, md1, z0, z1 = self._head_inputs(d0, d1, L - 1)
+            sim = ops._similarity(md0, md1, self._bf16)
+            st = ops.assign_stats(sim, F.logsigmoid(z0), F.logsigmoid(z1), F.logsigmoid(-z0), F.logsigmoid(-z1),
+                                  dense=True)
+            m0, m1, ms0, ms1 = ops.filter_matches(st["rowmax"], st["rowarg"], st["colarg"], conf.filter_threshold)
+        pred = {
+            "matches0": m0,
+            "matches1": m1,
+            "matching_scores0": ms0,
+            "matching_scores1": ms1,
+            "ref_descriptors0": torch.stack(all0, 1),
+            "ref_descriptors1": torch.stack(all1, 1),
+            "log_assignment": st["scores"],
+            "prune0": torch.ones_like(ms0) * L,
+            "prune1": torch.ones_like(ms1) * L,
+        }
+        return pred
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _argmax_with_dustbin(val, arg, dust, width):
+        """argmax over [inner scores | dustbin]: the dustbin (highest index) wins only when strictly larger."""
+        return torch.where(dust > val, torch.full_like(arg, width), arg)
+
+    def loss(self, pred, data):
+        """lightglue.py:578-627 without materialising any of the per-layer log-assignment matrices."""
+        conf = self.conf
+        ref0, ref1 = pred["ref_descriptors0"], pred["ref_descriptors1"]
+        B, L, M, D = ref0.shape
+        N = ref1.shape[2]
+        gt = data["gt_assignment"]
+        gt_u8 = gt.contiguous().view(torch.uint8) if gt.dtype == torch.bool else gt.to(torch.uint8).contiguous()
+        rowcnt = gt.sum(2).float()
+        colcnt = gt.sum(1).float()
+        neg0 = (data["gt_matches0"] == -1).float()
+        neg1 = (data["gt_matches1"] == -1).float()
+        num_pos = rowcnt.sum(1).clamp(min=1.0)
+        num_neg0, num_neg1 = neg0.sum(1).clamp(min=1.0), neg1.sum(1).clamp(min=1.0)
+        bal = conf.loss.nll_balancing
+
+        def head(i):
+            d0, d1 = ref0[:, i], ref1[:, i]
+            md0, md1, z0, z1 = self._head_inputs(d0, d1, i)
+            ls0, ls1, du0, du1 = F.logsigmoid(z0), F.logsigmoid(z1), F.logsigmoid(-z0), F.logsigmoid(-z1)
+            s_pos, rmax, rarg, cmax, carg = ops.AssignPositives.apply(md0, md1, ls0, ls1, du0, du1, gt_u8, rowcnt,
+                                                                      colcnt, self._bf16)
+            pos = s_pos + (rowcnt * ls0).sum(1) + (colcnt * ls1).sum(1)
+            nll_pos = -pos / num_pos
+            nll_neg = -((neg0 * du0).sum(1) + (neg1 * du1).sum(1)) / (num_neg0 + num_neg1)
+            nll = bal * nll_pos + (1 - bal) * nll_neg
+            arg0 = self._argmax_with_dustbin(rmax, rarg, du0.detach(), N)
+            arg1 = self._argmax_with_dustbin(cmax, carg, du1.detach(), M)
+            return nll, nll_pos, nll_neg, arg0, arg1
+
+        nll, nll_pos, nll_neg, _, _ = head(L - 1)
+        losses = {
+            "total": nll,
+            "last": nll.clone().detach(),
+            "assignment_nll": nll,
+            "nll_pos": nll_pos,
+            "nll_neg": nll_neg,
+            "num_matchable": num_pos,
+            "num_unmatchable": (num_neg0 + num_neg1) / 2.0,
+        }
+        if self.training:
+            losses["confidence"] = 0.0
+        la = pred["log_assignment"].detach()
+        losses["row_norm"] = la.exp()[:, :-1].sum(2).mean(1)
+        if L > 1:
+            fin0 = la[:, :-1, :].max(-1).indices.to(torch.int32)
+            fin1 = la[:, :, :-1].max(-2).indices.to(torch.int32)
+        sum_weights = 1.0
+        for i in range(L - 1):
+            nll_i, _, _, arg0, arg1 = head(i)
+            weight = conf.loss.gamma ** (L - i - 1) if conf.loss.gamma > 0.0 else i + 1
+            sum_weights += weight
+            losses["total"] = losses["total"] + nll_i * weight
+            tok = self.token_confidence[i].token[0]
+            logit0 = F.linear(ref0[:, i].detach(), tok.weight, tok.bias).squeeze(-1)
+            logit1 = F.linear(ref1[:, i].detach(), tok.weight, tok.bias).squeeze(-1)
+            bce = F.binary_cross_entropy_with_logits
+            conf_i = (bce(logit0, (fin0 == arg0).float(), reduction="none").mean(-1)
+                      + bce(logit1, (fin1 == arg1).float(), reduction="none").mean(-1)) / 2.0
+            losses["confidence"] = losses["confidence"] + conf_i / (L - 1)
+        losses["total"] = losses["total"] / sum_weights
+        if self.training:
+            losses["total"] = losses["total"] + losses["confidence"]
+        metrics = {} if self.training else matcher_metrics(pred, data)
+        return losses, metrics
+
+
+@torch.no_grad()
+def matcher_metrics(pred, data):
+    """models/utils/metrics.py:4-50 restated (recall / precision / accuracy / ranking AP of matches0)."""
+    m, gt_m, scores = pred["matches0"], data["gt_matches0"], pred["matching_scores0"]
+    hit = (m == gt_m).float()
+    r_mask = (gt_m > -1).float()
+    a_mask = (gt_m >= -1).float()
+    p_mask = ((m > -1) & (gt_m >= -1)).float()
+    rec = (hit * r_mask).sum(1) / (1e-8 + r_mask.sum(1))
+    acc = (hit * a_mask).sum(1) / (1e-8 + a_mask.sum(1))
+    prec = (hit * p_mask).sum(1) / (1e-8 + p_mask.sum(1))
+    order = torch.argsort(-scores)
+    sp, sr, st = (torch.gather(t, -1, order) for t in (p_mask, r_mask, hit))
+    p_pts = torch.cumsum(st * sp, -1) / (1e-8 + torch.cumsum(sp, -1))
+    r_pts = torch.cumsum(st * sr, -1) / (1e-8 + sr.sum(-1)[:, None])
+    ap = torch.sum((r_pts[..., 1:] - r_pts[..., :-1]) * p_pts[:, None, -1], dim=-1)
+    return {"match_recall": rec, "match_precision": prec, "accuracy": acc, "average_precision": ap}
+
+
+__main_model__ = LightGlue

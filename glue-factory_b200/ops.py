@@ -1,0 +1,259 @@
+"""torch.autograd bindings of the lgb200 kernels.
+
+PyTorch is used here only as plumbing: it owns the device buffers, the stream
+and the autograd tape; every numerical step of the N x N path is one of the
+C-ABI entry points of include/lgb200.h.  Nothing in this file has a CPU
+branch: on a machine without the built library or without a B200 the first
+call raises `Lgb200Error`.
+"""
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, call, ptr, stream_ptr
+
+
+def _code(dtype):
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"lgb200 kernels take float32 or bfloat16 tensors, got {dtype}")
+
+
+def _chk(t, dtype=None):
+    if not t.is_cuda:
+        raise _lib.Lgb200Error("lgb200 ops take CUDA tensors only: there is no CPU fallback")
+    assert t.is_contiguous(), "lgb200 ops need contiguous tensors"
+    if dtype is not None:
+        assert t.dtype == dtype, (t.dtype, dtype)
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# rotary split (lightglue.py:157-160)
+# ------------------------------------------------------------------------------------------------
+class RopeSplit(torch.autograd.Function):
+    """qkv [T, H*192] (interleaved) , theta [T, 32] -> rotated q, rotated k, v  each [T, H*64]."""
+
+    @staticmethod
+    def forward(ctx, qkv, theta, H):
+        _chk(qkv)
+        _chk(theta, torch.float32)
+        T = qkv.shape[0]
+        q = torch.empty(T, H * 64, device=qkv.device, dtype=qkv.dtype)
+        k, v = torch.empty_like(q), torch.empty_like(q)
+        call("lgb200_rope_split_fwd", ptr(qkv), ptr(theta), ptr(q), ptr(k), ptr(v), T, H, _code(qkv.dtype), stream_ptr())
+        ctx.save_for_backward(q, k, theta)
+        ctx.H = H
+        return q, k, v
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        q, k, theta = ctx.saved_tensors
+        T, H = q.shape[0], ctx.H
+        dq, dk, dv = (g.contiguous() for g in (dq, dk, dv))
+        dqkv = torch.empty(T, H * 192, device=q.device, dtype=q.dtype)
+        dtheta = torch.zeros_like(theta)
+        call("lgb200_rope_split_bwd", ptr(dq), ptr(dk), ptr(dv), ptr(q), ptr(k), ptr(theta), ptr(dqkv), ptr(dtheta),
+             T, H, _code(q.dtype), stream_ptr())
+        return dqkv, dtheta, None
+
+
+# ------------------------------------------------------------------------------------------------
+# attention (lightglue.py:118-121, 207-216)
+# ------------------------------------------------------------------------------------------------
+class Attention(torch.autograd.Function):
+    """q [B,Nq,H,64], k,v [B,Nk,H,64] -> softmax(q k^T / 8) v, keys of batch b taken from batch
+    (b + kv_shift) % B."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, kv_shift, scale):
+        _chk(q), _chk(k), _chk(v)
+        B, Nq, H, D = q.shape
+        Nk = k.shape[1]
+        assert D == 64, "head_dim must be 64"
+        out = torch.empty_like(q)
+        lse = torch.empty(B, H, Nq, device=q.device, dtype=torch.float32)
+        call("lgb200_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, Nq, Nk, H, kv_shift, float(scale),
+             _code(q.dtype), stream_ptr())
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.meta = (kv_shift, float(scale))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse = ctx.saved_tensors
+        kv_shift, scale = ctx.meta
+        B, Nq, H, _ = q.shape
+        Nk = k.shape[1]
+        dout = dout.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        delta = torch.empty(B, H, Nq, device=q.device, dtype=torch.float32)
+        call("lgb200_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(dout), ptr(dq), ptr(dk), ptr(dv),
+             ptr(delta), B, Nq, Nk, H, kv_shift, scale, _code(q.dtype), stream_ptr())
+        return dq, dk, dv, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm + GELU (lightglue.py:143-148)
+# ------------------------------------------------------------------------------------------------
+class LnGelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        _chk(x)
+        g, b = gamma.float().contiguous(), beta.float().contiguous()
+        T, W = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(T, device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        call("lgb200_ln_gelu_fwd", ptr(x), ptr(g), ptr(b), ptr(y), ptr(mean), ptr(rstd), T, W, float(eps),
+             _code(x.dtype), stream_ptr())
+        ctx.save_for_backward(x, g, b, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, b, mean, rstd = ctx.saved_tensors
+        T, W = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        parts = _lib.load().lgb200_ln_gelu_bwd_parts(T)
+        dg = torch.empty(parts, W, device=x.device, dtype=torch.float32)
+        db = torch.empty_like(dg)
+        call("lgb200_ln_gelu_bwd", ptr(dy), ptr(x), ptr(g), ptr(b), ptr(mean), ptr(rstd), ptr(dx), ptr(dg), ptr(db),
+             T, W, _code(x.dtype), stream_ptr())
+        return dx, dg.sum(0), db.sum(0), None
+
+
+# ------------------------------------------------------------------------------------------------
+# batched GEMM on tcgen05 (lightglue.py:283)
+# ------------------------------------------------------------------------------------------------
+def gemm_bf16(a, b, a_mn_major=False, b_mn_major=False, out_dtype=torch.float32):
+    """C[i] = opA(a[i]) @ opB(b[i])^T-style contraction on the tensor cores (see lgb200.h).
+    a: [batch, M, K] (or [batch, K, M] when a_mn_major); b: [batch, N, K] (or [batch, K, N])."""
+    _chk(a, torch.bfloat16), _chk(b, torch.bfloat16)
+    batch = a.shape[0]
+    M, K = (a.shape[2], a.shape[1]) if a_mn_major else (a.shape[1], a.shape[2])
+    N, Kb = (b.shape[2], b.shape[1]) if b_mn_major else (b.shape[1], b.shape[2])
+    assert K == Kb and b.shape[0] == batch
+    c = torch.empty(batch, M, N, device=a.device, dtype=out_dtype)
+    call("lgb200_gemm_bf16", ptr(a), ptr(b), ptr(c), batch, M, N, K, int(a_mn_major), int(b_mn_major),
+         a.shape[2], b.shape[2], N, a.shape[1] * a.shape[2], b.shape[1] * b.shape[2], M * N, _code(out_dtype),
+         stream_ptr())
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# assignment head (lightglue.py:256-290, losses.py)
+# ------------------------------------------------------------------------------------------------
+def _similarity(md0, md1, bf16):
+    if bf16:
+        return gemm_bf16(md0.to(torch.bfloat16).contiguous(), md1.to(torch.bfloat16).contiguous())
+    return torch.bmm(md0, md1.transpose(1, 2))
+
+
+def assign_stats(sim, ls0, ls1, dust0, dust1, gt_u8=None, dense=False):
+    """Runs the two assignment passes on sim [B,M,N].  Returns a dict with lse_row/lse_col,
+    rowmax/rowarg/colmax/colarg (int32, dustbin excluded), optional pos_row_sum, and when
+    `dense` the full scores [B,M+1,N+1] and row_expsum."""
+    _chk(sim, torch.float32)
+    B, M, N = sim.shape
+    dev = sim.device
+    f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+    lse_row, lse_col = f(B, M), f(B, N)
+    ws = torch.empty(_lib.load().lgb200_assign_ws_bytes(B, M, N), device=dev, dtype=torch.uint8)
+    call("lgb200_assign_lse", ptr(sim), ptr(lse_row), ptr(lse_col), ptr(ws), B, M, N, stream_ptr())
+    out = {"lse_row": lse_row, "lse_col": lse_col, "rowmax": f(B, M), "colmax": f(B, N),
+           "rowarg": torch.empty(B, M, device=dev, dtype=torch.int32),
+           "colarg": torch.empty(B, N, device=dev, dtype=torch.int32)}
+    scores = f(B, M + 1, N + 1) if dense else None
+    row_expsum = f(B, M) if dense else None
+    pos_row_sum = f(B, M) if gt_u8 is not None else None
+    ls0, ls1, dust0, dust1 = (t.detach().float().contiguous() for t in (ls0, ls1, dust0, dust1))
+    call("lgb200_assign_scores", ptr(sim), ptr(lse_row), ptr(lse_col), ptr(ls0), ptr(ls1), ptr(dust0), ptr(dust1),
+         ptr(gt_u8), ptr(scores), ptr(out["rowmax"]), ptr(out["rowarg"]), ptr(out["colmax"]), ptr(out["colarg"]),
+         ptr(pos_row_sum), ptr(row_expsum), ptr(ws), B, M, N, stream_ptr())
+    out.update(scores=scores, row_expsum=row_expsum, pos_row_sum=pos_row_sum)
+    return out
+
+
+class AssignPositives(torch.autograd.Function):
+    """(mdesc0 [B,M,D], mdesc1 [B,N,D]) -> S_pos [B] = sum_ij gt_ij (2 sim_ij - lse_row_i - lse_col_j)
+    with sim = mdesc0 mdesc1^T, i.e. the similarity-dependent part of sum_P log_assignment
+    (the matchability terms are O(M+N) and are added by the caller).  Also returns the
+    (non-differentiable) row / column argmax of the full scores.  The dense log-assignment is
+    never written; backward recomputes the two softmaxes from the saved sim and LSE vectors
+    (SURVEY.md Appendix A.4)."""
+
+    @staticmethod
+    def forward(ctx, md0, md1, ls0, ls1, dust0, dust1, gt_u8, rowcnt, colcnt, bf16):
+        sim = _similarity(md0, md1, bf16)
+        st = assign_stats(sim, ls0, ls1, dust0, dust1, gt_u8=gt_u8, dense=False)
+        ctx.save_for_backward(md0, md1, sim, st["lse_row"], st["lse_col"], gt_u8, rowcnt, colcnt)
+        ctx.bf16 = bf16
+        for k in ("rowmax", "rowarg", "colmax", "colarg"):
+            ctx.mark_non_differentiable(st[k])
+        return st["pos_row_sum"].sum(1), st["rowmax"], st["rowarg"], st["colmax"], st["colarg"]
+
+    @staticmethod
+    def backward(ctx, g, *_):
+        md0, md1, sim, lse_row, lse_col, gt_u8, rowcnt, colcnt = ctx.saved_tensors
+        B, M, N = sim.shape
+        g = g.float().contiguous()
+        a_row = (g[:, None] * rowcnt).contiguous()
+        a_col = (g[:, None] * colcnt).contiguous()
+        tc = ctx.bf16 and N % 8 == 0 and M % 8 == 0
+        dsim = torch.empty(B, M, N, device=sim.device, dtype=torch.bfloat16 if tc else torch.float32)
+        call("lgb200_assign_bwd", ptr(sim), ptr(lse_row), ptr(lse_col), ptr(gt_u8), ptr(g), ptr(a_row), ptr(a_col),
+             ptr(dsim), _code(dsim.dtype), B, M, N, stream_ptr())
+        if tc:
+            b0 = md0.to(torch.bfloat16).contiguous()
+            b1 = md1.to(torch.bfloat16).contiguous()
+            dmd0 = gemm_bf16(dsim, b1, a_mn_major=False, b_mn_major=True)  # dsim @ md1
+            dmd1 = gemm_bf16(dsim, b0, a_mn_major=True, b_mn_major=True)   # dsim^T @ md0
+        else:
+            dmd0 = torch.bmm(dsim, md1.float())
+            dmd1 = torch.bmm(dsim.transpose(1, 2), md0.float())
+        return dmd0.to(md0.dtype), dmd1.to(md1.dtype), None, None, None, None, None, None, None, None
+
+
+def filter_matches(rowmax, rowarg, colarg, th):
+    """lightglue.py:293-309 from the pass-2 argmax."""
+    B, M = rowmax.shape
+    N = colarg.shape[1]
+    dev = rowmax.device
+    m0 = torch.empty(B, M, device=dev, dtype=torch.int64)
+    m1 = torch.empty(B, N, device=dev, dtype=torch.int64)
+    ms0 = torch.empty(B, M, device=dev, dtype=torch.float32)
+    ms1 = torch.empty(B, N, device=dev, dtype=torch.float32)
+    call("lgb200_filter_matches", ptr(rowmax), ptr(rowarg), ptr(colarg), float(th), ptr(m0), ptr(m1), ptr(ms0),
+         ptr(ms1), B, M, N, stream_ptr())
+    return m0, m1, ms0, ms1
+
+
+def log_double_softmax(sim, bin_score):
+    """gluestick.py:772-783."""
+    _chk(sim, torch.float32)
+    B, M, N = sim.shape
+    out = torch.empty(B, M + 1, N + 1, device=sim.device, dtype=torch.float32)
+    ws = torch.empty(_lib.load().lgb200_heads_ws_bytes(B, M, N), device=sim.device, dtype=torch.uint8)
+    call("lgb200_log_double_softmax", ptr(sim), float(bin_score), ptr(out), ptr(ws), B, M, N, stream_ptr())
+    return out
+
+
+def log_optimal_transport(sim, alpha, iters):
+    """gluefactory_nonfree/superglue.py:198-214 (forward)."""
+    _chk(sim, torch.float32)
+    B, M, N = sim.shape
+    out = torch.empty(B, M + 1, N + 1, device=sim.device, dtype=torch.float32)
+    ws = torch.empty(_lib.load().lgb200_heads_ws_bytes(B, M, N), device=sim.device, dtype=torch.uint8)
+    call("lgb200_sinkhorn", ptr(sim), float(alpha), int(iters), ptr(out), ptr(ws), B, M, N, stream_ptr())
+    return out
+
+
+def adam_flat_(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0, lr_per_elem=None):
+    """In-place Adam on flat fp32 buffers (train.py:358-361, 513)."""
+    for t in (p, g, m, v):
+        _chk(t, torch.float32)
+    call("lgb200_adam_flat", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), ptr(lr_per_elem), float(lr), float(betas[0]),
+         float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale), stream_ptr())

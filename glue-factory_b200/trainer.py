@@ -1,0 +1,85 @@
+"""Data-parallel training step around the matcher (one process per GPU).
+
+Restates the per-iteration body of the reference trainer
+(/root/reference/gluefactory/train.py:456-517: zero_grad -> forward -> loss ->
+mean -> backward -> gradient exchange -> Adam) with the two B200-specific
+changes SURVEY.md section 2.2 (C1) calls for:
+
+  * every parameter lives in ONE flat fp32 buffer and every gradient in one flat
+    gradient buffer (the nn.Parameters are views), so the gradient exchange is a
+    single `all_reduce` over NVLink per optimiser step instead of DDP's bucketed
+    hooks plus the extra scalar all-reduce of train.py:483-488;
+  * Adam runs as one kernel over the flat buffers (`lgb200_adam_flat`), with the
+    1/world averaging folded into it.
+
+The matcher is per-pair, so image pairs shard across ranks with no other
+collective.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .synthetic import to_device
+
+_ALIGN = 64  # elements; keeps every parameter view 256-byte aligned
+
+
+class FlatParams:
+    """Re-homes the trainable parameters of `module` into one flat buffer (+ flat grad buffer)."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        assert self.params, "no trainable parameters"
+        dev, dt = self.params[0].device, torch.float32
+        self.offsets, n = [], 0
+        for p in self.params:
+            assert p.dtype == dt and p.device == dev
+            self.offsets.append(n)
+            n += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = n
+        self.flat = torch.zeros(n, device=dev, dtype=dt)
+        self.grad = torch.zeros(n, device=dev, dtype=dt)
+        for p, off in zip(self.params, self.offsets):
+            self.flat[off:off + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + p.numel()].view_as(p)
+            p.grad = self.grad[off:off + p.numel()].view_as(p)
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p, off in zip(self.params, self.offsets):  # re-attach in case something detached the views
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + off * 4:
+                p.grad = self.grad[off:off + p.numel()].view_as(p)
+
+
+class MatcherTrainer:
+    """model: a matcher with forward(data)->pred and loss(pred, data)->(losses, metrics)."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None):
+        self.model = model.train()
+        self.fp = FlatParams(model)
+        self.m = torch.zeros_like(self.fp.flat)
+        self.v = torch.zeros_like(self.fp.flat)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.t = 0
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+
+    def exchange_gradients(self):
+        """The ONE collective of the step: sum-all-reduce of the flat gradient buffer."""
+        if self.world > 1:
+            dist.all_reduce(self.fp.grad, op=dist.ReduceOp.SUM, group=self.group)
+
+    def step(self, data, device=None):
+        """One optimiser step on one batch; `data` may live in (pinned) host memory."""
+        if device is not None:
+            data = to_device(data, device, non_blocking=True)
+        self.fp.zero_grad()
+        pred = self.model(data)
+        losses, _ = self.model.loss(pred, data)
+        loss = losses["total"].mean()
+        loss.backward()
+        self.exchange_gradients()
+        self.t += 1
+        ops.adam_flat_(self.fp.flat, self.fp.grad, self.m, self.v, self.t, self.lr, self.betas, self.eps, self.wd,
+                       grad_scale=1.0 / self.world)
+        return loss.detach(), losses

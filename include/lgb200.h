@@ -1,0 +1,143 @@
+/* lgb200 -- C ABI of the B200-native LightGlue matcher hot path.
+ *
+ * The reference (cvg/glue-factory) is pure Python/PyTorch: its "FFI" for this
+ * path is the set of PyTorch operator calls inside
+ * gluefactory/models/matchers/lightglue.py and gluefactory/models/utils/losses.py.
+ * Each entry point below replaces one such group of calls; the citation on each
+ * names the reference lines it stands in for.  The host-side plugin
+ * (glue-factory_b200/matchers/lightglue.py) binds these with ctypes, see
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers to DEVICE memory + extents + the CUDA stream to launch on;
+ *    no torch types.  The caller owns every buffer; kernels keep no state.
+ *  - every function returns 0 on success or a negative LGB200_ERR_* code;
+ *    lgb200_last_error() returns the message of the last failure on this thread.
+ *  - activations are token-major: [batch, tokens, heads, 64] for q/k/v/ctx,
+ *    [batch, rows, cols] row-major for similarity/score matrices.
+ *  - `dtype` is LGB200_F32 (full-precision parity path, CUDA cores) or
+ *    LGB200_BF16 (bf16 operands, fp32 accumulation, tcgen05 tensor cores).
+ *  - head dimension is fixed to 64 (descriptor_dim / num_heads in every
+ *    LightGlue configuration, lightglue.py:349).
+ */
+#ifndef LGB200_H_
+#define LGB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define LGB200_ABI_VERSION 1
+
+#define LGB200_F32 0
+#define LGB200_BF16 1
+
+#define LGB200_OK 0
+#define LGB200_ERR_INVALID (-1)     /* bad argument (null pointer, empty or misaligned input) */
+#define LGB200_ERR_CUDA (-2)        /* a CUDA runtime / driver call failed */
+#define LGB200_ERR_UNSUPPORTED (-3) /* shape or device not supported by this build */
+
+int lgb200_abi_version(void);
+const char* lgb200_last_error(void);
+/* 0 when the current device is sm_100 (B200); LGB200_ERR_UNSUPPORTED otherwise. */
+int lgb200_check_device(void);
+
+/* ---- rotary encoding + QKV de-interleave ------------------------------------------------------
+ * replaces lightglue.py:157-160 (unflatten(H,-1,3), q/k/v slices, apply_cached_rotary_emb) and
+ * lightglue.py:42-49.  qkv [ntok, H*192] with feature = h*192 + d*3 + {q,k,v};
+ * theta [ntok, 32] fp32 = posenc.Wr(kpts) (lightglue.py:62); q,k,v [ntok, H*64].           */
+int lgb200_rope_split_fwd(const void* qkv, const float* theta, void* q, void* k, void* v, int64_t ntok, int H,
+                          int dtype, cudaStream_t stream);
+/* dq,dk are gradients w.r.t. the rotated q,k (saved by forward as q,k); writes dqkv [ntok, H*192]
+ * and ACCUMULATES dtheta [ntok, 32] (the gradient that reaches posenc.Wr from every layer).   */
+int lgb200_rope_split_bwd(const void* dq, const void* dk, const void* dv, const void* q, const void* k,
+                          const float* theta, void* dqkv, float* dtheta, int64_t ntok, int H, int dtype,
+                          cudaStream_t stream);
+
+/* ---- attention ----------------------------------------------------------------------------------
+ * replaces F.scaled_dot_product_attention (lightglue.py:118-121) and the cross-attention einsum/
+ * softmax block (lightglue.py:207-216).  out = softmax(scale * q k^T) v per (batch, head).
+ * q,out [B,Nq,H,64]; k,v [B,Nk,H,64]; lse [B,H,Nq] fp32.  Keys/values of query batch b are taken
+ * from batch (b + kv_shift) % B (kv_shift = B/2 on the [image0; image1] batch = both cross
+ * directions in one launch; 0 = self-attention).                                                */
+int lgb200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Nq, int Nk, int H,
+                    int kv_shift, float scale, int dtype, cudaStream_t stream);
+/* dq [B,Nq,H,64]; dk,dv [B,Nk,H,64] (indexed by KEY batch); delta_ws: B*H*Nq floats of scratch. */
+int lgb200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
+                    void* dq, void* dk, void* dv, float* delta_ws, int B, int Nq, int Nk, int H, int kv_shift,
+                    float scale, int dtype, cudaStream_t stream);
+
+/* ---- FFN LayerNorm + GELU -------------------------------------------------------------------------
+ * replaces nn.LayerNorm(2D) + nn.GELU() of the ffn Sequential (lightglue.py:143-148, 178-183).
+ * x,y [ntok, W], W in {256,512,1024}; mean,rstd [ntok] saved for backward.                       */
+int lgb200_ln_gelu_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                       int64_t ntok, int W, float eps, int dtype, cudaStream_t stream);
+/* number of partial rows written to dgamma_part/dbeta_part [parts, W] (caller sums over parts)  */
+int lgb200_ln_gelu_bwd_parts(int64_t ntok);
+int lgb200_ln_gelu_bwd(const void* dy, const void* x, const float* gamma, const float* beta, const float* mean,
+                       const float* rstd, void* dx, float* dgamma_part, float* dbeta_part, int64_t ntok, int W,
+                       int dtype, cudaStream_t stream);
+
+/* ---- batched bf16 tensor-core GEMM (tcgen05, fp32 accumulate) ---------------------------------------
+ * replaces torch.einsum("bmd,bnd->bmn") of MatchAssignment (lightglue.py:283) and its two backward
+ * contractions.  C[b] (M x N) = opA(A[b]) * opB(B[b]):
+ *   a_mn_major = 0: A is [M,K] row-major (lda);  1: A is stored [K,M] row-major (lda)
+ *   b_mn_major = 0: B is [N,K] row-major (ldb);  1: B is stored [K,N] row-major (ldb)
+ * lda/ldb in elements, multiples of 8; base pointers 16-byte aligned; C row-major with ldc.      */
+int lgb200_gemm_bf16(const void* A, const void* B, void* C, int batch, int M, int N, int K, int a_mn_major,
+                     int b_mn_major, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
+                     int64_t strideC, int c_dtype, cudaStream_t stream);
+
+/* ---- assignment head: sigmoid_log_double_softmax + NLL terms + argmax --------------------------------
+ * replaces lightglue.py:256-268 (two log_softmax, transposed copy, slice assignment),
+ * losses.py:6-25,62-73 (dense weight matrix and product) and the max() calls of
+ * lightglue.py:86-90, 295-296.  sim [B,M,N] fp32.                                                 */
+size_t lgb200_assign_ws_bytes(int B, int M, int N);
+/* pass 1: lse_row [B,M] = logsumexp_j sim, lse_col [B,N] = logsumexp_i sim                         */
+int lgb200_assign_lse(const float* sim, float* lse_row, float* lse_col, void* ws, int B, int M, int N,
+                      cudaStream_t stream);
+/* pass 2: scores_ij = (sim-lse_row_i) + (sim-lse_col_j) + (ls0_i + ls1_j) for i<M, j<N;
+ *   scores [B,M+1,N+1] (optional dense output incl. dustbin column dust0, dustbin row dust1, corner 0)
+ *   rowmax/rowarg [B,M]: max_j / argmax_j over j<N (lowest index wins ties); colmax/colarg [B,N] likewise
+ *   pos_row_sum [B,M] (optional, needs gt [B,M,N] uint8): sum_j gt_ij (2 sim_ij - lse_row_i - lse_col_j)
+ *   row_expsum [B,M] (optional): sum_{j<=N} exp(scores_ij)  (row_norm monitor, lightglue.py:596)     */
+int lgb200_assign_scores(const float* sim, const float* lse_row, const float* lse_col, const float* ls0,
+                         const float* ls1, const float* dust0, const float* dust1, const uint8_t* gt, float* scores,
+                         float* rowmax, int* rowarg, float* colmax, int* colarg, float* pos_row_sum,
+                         float* row_expsum, void* ws, int B, int M, int N, cudaStream_t stream);
+/* backward of sum_ij gt_ij (2 sim_ij - lse_row_i - lse_col_j) scaled by gcoef[b]:
+ *   dsim_ij = 2 gcoef_b gt_ij - exp(sim_ij-lse_row_i) a_row_i - exp(sim_ij-lse_col_j) a_col_j          */
+int lgb200_assign_bwd(const float* sim, const float* lse_row, const float* lse_col, const uint8_t* gt,
+                      const float* gcoef, const float* a_row, const float* a_col, void* dsim, int out_dtype, int B,
+                      int M, int N, cudaStream_t stream);
+/* filter_matches (lightglue.py:293-309): mutual check + threshold; m0,m1 int64, -1 = no match       */
+int lgb200_filter_matches(const float* rowmax, const int* rowarg, const int* colarg, float th, int64_t* m0,
+                          int64_t* m1, float* ms0, float* ms1, int B, int M, int N, cudaStream_t stream);
+
+/* ---- other assignment heads on the path ----------------------------------------------------------
+ * log_double_softmax with a learned bin (gluestick.py:772-783) and log-domain Sinkhorn optimal
+ * transport (gluefactory_nonfree/superglue.py:186-214).  scores/out [B,M+1,N+1].
+ * ws: lgb200_heads_ws_bytes(B, M, N) bytes of scratch.                                               */
+size_t lgb200_heads_ws_bytes(int B, int M, int N);
+int lgb200_log_double_softmax(const float* sim, float bin_score, float* scores, void* ws, int B, int M, int N,
+                              cudaStream_t stream);
+int lgb200_sinkhorn(const float* sim, float alpha, int iters, float* out, void* ws, int B, int M, int N,
+                    cudaStream_t stream);
+
+/* ---- flat-buffer optimiser (train.py:358-361, 513) and casts --------------------------------------- */
+int lgb200_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_per_elem, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                     cudaStream_t stream);
+int lgb200_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGB200_H_ */

@@ -1,0 +1,56 @@
+"""CPU, world_size 2 over gloo: the flat-buffer gradient exchange (the path's one collective).
+The optimiser kernel itself is CUDA-only; here we check the host logic: parameters and gradients are
+views of the flat buffers, autograd accumulates into them in place, and one all_reduce leaves every
+rank with the sum of the per-rank gradients."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gluefactory_b200.trainer import FlatParams, MatcherTrainer
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.LayerNorm(16), torch.nn.Linear(16, 3))
+    net.loss = None
+    tr = MatcherTrainer.__new__(MatcherTrainer)
+    tr.fp = FlatParams(net)
+    tr.world, tr.group = world, None
+    x = torch.full((4, 8), float(rank + 1))
+    tr.fp.zero_grad()
+    net(x).sum().backward()
+    local = tr.fp.grad.clone()
+    # gradients landed in the flat buffer through the parameter views
+    for p, off in zip(tr.fp.params, tr.fp.offsets):
+        assert p.grad.data_ptr() == tr.fp.grad.data_ptr() + off * 4
+        assert torch.equal(p.grad.reshape(-1), tr.fp.grad[off:off + p.numel()])
+    tr.exchange_gradients()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    assert torch.allclose(tr.fp.grad, sum(gathered))
+    # parameter writes through the flat buffer are visible in the module
+    tr.fp.flat.add_(1.0)
+    assert torch.equal(net[0].weight.reshape(-1), tr.fp.flat[: net[0].weight.numel()])
+    out.put((rank, float(tr.fp.grad.abs().sum())))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = dict(q.get() for _ in range(2))
+    assert abs(res[0] - res[1]) < 1e-6 and res[0] > 0

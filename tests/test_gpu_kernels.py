@@ -1,0 +1,225 @@
+"""GPU: every C-ABI kernel against the oracle / an fp64 evaluation of the same operands.
+
+Tolerances: integer outputs (argmax, matches) are bit-exact; fp32 kernels 1e-4..1e-5 relative;
+bf16 tensor-core kernels are compared with an fp64 evaluation of the SAME bf16-rounded operands, so
+the only difference is fp32 accumulation order and the bf16 rounding of the softmax probabilities
+(2^-9 relative per element) -> 1e-2 on outputs/gradients is the stated tolerance there.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gluefactory_b200 import ops
+from oracle import lightglue_oracle as O
+from tests.util import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(*shape, seed=0, dtype=torch.float32, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("shape", [(2, 256, 256, 256), (3, 200, 136, 72), (1, 128, 128, 64), (2, 384, 64, 512)])
+def test_gemm_bf16_tcgen05(a_mn, b_mn, shape):
+    batch, M, N, K = shape
+    a = _rand(batch, K, M, seed=1, dtype=torch.bfloat16) if a_mn else _rand(batch, M, K, seed=1, dtype=torch.bfloat16)
+    b = _rand(batch, K, N, seed=2, dtype=torch.bfloat16) if b_mn else _rand(batch, N, K, seed=2, dtype=torch.bfloat16)
+    A = a.double().transpose(1, 2) if a_mn else a.double()
+    Bm = b.double().transpose(1, 2) if b_mn else b.double()
+    ref = A @ Bm.transpose(1, 2)
+    c = ops.gemm_bf16(a, b, bool(a_mn), bool(b_mn), out_dtype=torch.float32)
+    assert rel_err(c, ref) < 1e-5
+    c16 = ops.gemm_bf16(a, b, bool(a_mn), bool(b_mn), out_dtype=torch.bfloat16)
+    assert rel_err(c16, ref) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------
+def _attn_ref(q, k, v, shift):
+    """fp64 attention on [B,N,H,64] with the kv batch roll."""
+    q, k, v = (t.double().permute(0, 2, 1, 3) for t in (q, k, v))
+    B = q.shape[0]
+    idx = (torch.arange(B, device=q.device) + shift) % B
+    k, v = k[idx], v[idx]
+    s = q @ k.transpose(-1, -2) / 8.0
+    return (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3), torch.logsumexp(s, -1)
+
+
+ATTN_SHAPES = [(2, 128, 128, 4, 0), (2, 256, 256, 4, 1), (2, 200, 200, 2, 1), (1, 72, 300, 4, 0), (4, 512, 512, 4, 2)]
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("B,Nq,Nk,H,shift", ATTN_SHAPES)
+def test_attention_forward_backward(dtype, tol, B, Nq, Nk, H, shift):
+    if shift and Nq != Nk:
+        pytest.skip("shifted launch needs equal lengths")
+    q = _rand(B, Nq, H, 64, seed=1, dtype=dtype, scale=1.5).requires_grad_(True)
+    k = _rand(B, Nk, H, 64, seed=2, dtype=dtype, scale=1.5).requires_grad_(True)
+    v = _rand(B, Nk, H, 64, seed=3, dtype=dtype).requires_grad_(True)
+    go = _rand(B, Nq, H, 64, seed=4, dtype=dtype)
+    out = ops.Attention.apply(q, k, v, shift, 0.125)
+    out.backward(go)
+    qr, kr, vr = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+    ref, _ = _attn_ref(qr, kr, vr, shift)
+    ref.backward(go.double())
+    assert rel_err(out, ref) < tol
+    assert rel_err(q.grad, qr.grad) < tol
+    assert rel_err(k.grad, kr.grad) < tol
+    assert rel_err(v.grad, vr.grad) < tol
+
+
+@pytest.mark.parametrize("B,Nq,Nk,H,shift", ATTN_SHAPES)
+def test_attention_tc_matches_simt_lse(B, Nq, Nk, H, shift):
+    """the tcgen05 forward and the CUDA-core forward must agree on out and on the saved log-sum-exp"""
+    from gluefactory_b200._lib import BF16, call, ptr, stream_ptr
+
+    if shift and Nq != Nk:
+        pytest.skip("shifted launch needs equal lengths")
+    q = _rand(B, Nq, H, 64, seed=1, dtype=torch.bfloat16, scale=1.5)
+    k = _rand(B, Nk, H, 64, seed=2, dtype=torch.bfloat16, scale=1.5)
+    v = _rand(B, Nk, H, 64, seed=3, dtype=torch.bfloat16)
+    out = torch.empty_like(q)
+    lse = torch.empty(B, H, Nq, device=DEV)
+    call("lgb200_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, Nq, Nk, H, shift, 0.125, BF16, stream_ptr())
+    ref, ref_lse = _attn_ref(q, k, v, shift)
+    assert rel_err(out, ref) < 1e-2
+    assert (lse.double() - ref_lse).abs().max().item() < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 8e-3)])
+def test_rope_split(dtype, tol):
+    T, H = 333, 4
+    qkv = _rand(T, H * 192, seed=1, dtype=dtype).requires_grad_(True)
+    theta = _rand(T, 32, seed=2, scale=3.0).requires_grad_(True)
+    q, k, v = ops.RopeSplit.apply(qkv, theta, H)
+    gq, gk, gv = (_rand(T, H * 64, seed=s, dtype=dtype) for s in (3, 4, 5))
+    torch.autograd.backward([q, k, v], [gq, gk, gv])
+    # oracle: lightglue.py:157-160 + 42-49
+    x = qkv.detach().double().requires_grad_(True)
+    th = theta.detach().double().requires_grad_(True)
+    t = x.view(1, T, H, 64, 3).permute(0, 2, 1, 3, 4)
+    rq, rk, rv = O.rope(t[..., 0], th[None]), O.rope(t[..., 1], th[None]), t[..., 2]
+    back = lambda z: z.permute(0, 2, 1, 3).reshape(T, H * 64)  # noqa: E731
+    torch.autograd.backward([back(rq), back(rk), back(rv)], [gq.double(), gk.double(), gv.double()])
+    assert rel_err(q, back(rq)) < tol and rel_err(k, back(rk)) < tol and rel_err(v, back(rv)) < tol
+    assert rel_err(qkv.grad, x.grad) < tol
+    assert rel_err(theta.grad, th.grad) < (1e-5 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 8e-3)])
+@pytest.mark.parametrize("W", [256, 512])
+def test_ln_gelu(dtype, tol, W):
+    T = 1001
+    x = _rand(T, W, seed=1, dtype=dtype, scale=2.0).requires_grad_(True)
+    g = (1 + 0.1 * _rand(W, seed=2)).requires_grad_(True)
+    b = (0.1 * _rand(W, seed=3)).requires_grad_(True)
+    gy = _rand(T, W, seed=4, dtype=dtype)
+    y = ops.LnGelu.apply(x, g, b, 1e-5)
+    y.backward(gy)
+    xr, gr, br = (t.detach().double().requires_grad_(True) for t in (x, g, b))
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(xr, (W,), gr, br, 1e-5))
+    ref.backward(gy.double())
+    assert rel_err(y, ref) < tol
+    assert rel_err(x.grad, xr.grad) < tol
+    assert rel_err(g.grad, gr.grad) < max(tol, 1e-5) and rel_err(b.grad, br.grad) < max(tol, 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,M,N", [(2, 96, 96), (1, 80, 112), (2, 257, 130), (1, 1024, 1024), (3, 33, 515)])
+def test_assignment_head_matches_oracle(B, M, N):
+    sim = _rand(B, M, N, seed=1, scale=4.0)
+    z0, z1 = _rand(B, M, seed=2, scale=2.0), _rand(B, N, seed=3, scale=2.0)
+    gt = (torch.rand(B, M, N, generator=torch.Generator().manual_seed(4)) < 0.01).to(DEV)
+    ls = torch.nn.functional.logsigmoid
+    st = ops.assign_stats(sim, ls(z0), ls(z1), ls(-z0), ls(-z1), gt_u8=gt.view(torch.uint8), dense=True)
+    ref = O.sigmoid_log_double_softmax(sim.double().cpu(), z0.double().cpu(), z1.double().cpu())
+    scores = st["scores"].cpu()
+    np.testing.assert_allclose(scores.numpy(), ref.numpy(), rtol=0, atol=2e-5)
+    np.testing.assert_allclose(st["lse_row"].cpu().numpy(), torch.logsumexp(sim.double(), 2).cpu().numpy(), atol=1e-5)
+    np.testing.assert_allclose(st["lse_col"].cpu().numpy(), torch.logsumexp(sim.double(), 1).cpu().numpy(), atol=1e-5)
+    # argmax: bit-exact against torch's max on the kernel's own fp32 scores (ties -> lowest index)
+    inner = scores[:, :-1, :-1]
+    assert torch.equal(st["rowarg"].cpu().long(), inner.max(2).indices)
+    assert torch.equal(st["colarg"].cpu().long(), inner.max(1).indices)
+    assert torch.equal(st["rowmax"].cpu(), inner.max(2).values)
+    assert torch.equal(st["colmax"].cpu(), inner.max(1).values)
+    # ... and against the fp64 oracle wherever its top-2 margin exceeds fp32 resolution
+    top2 = ref[:, :-1, :-1].topk(2, dim=2).values
+    safe = (top2[..., 0] - top2[..., 1]) > 1e-4
+    assert torch.equal(st["rowarg"].cpu().long()[safe], ref[:, :-1, :-1].max(2).indices[safe])
+    # filter_matches
+    for th in (0.0, 0.05):
+        m0, m1, ms0, ms1 = ops.filter_matches(st["rowmax"], st["rowarg"], st["colarg"], th)
+        r0, r1, rs0, rs1 = O.filter_matches(scores, th)
+        assert torch.equal(m0.cpu(), r0) and torch.equal(m1.cpu(), r1)
+        np.testing.assert_allclose(ms0.cpu().numpy(), rs0.numpy(), rtol=1e-6)
+        np.testing.assert_allclose(ms1.cpu().numpy(), rs1.numpy(), rtol=1e-6)
+    # positive-weighted sum and row_norm monitor
+    pos_ref = ((2 * sim.double() - torch.logsumexp(sim.double(), 2, keepdim=True)
+                - torch.logsumexp(sim.double(), 1, keepdim=True)) * gt).sum(2)
+    np.testing.assert_allclose(st["pos_row_sum"].cpu().numpy(), pos_ref.cpu().numpy(), rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(st["row_expsum"].cpu().numpy(), ref.exp()[:, :-1].sum(2).numpy(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+@pytest.mark.parametrize("B,M,N", [(2, 128, 128), (1, 200, 136), (2, 100, 250)])
+def test_assign_positives_backward(bf16, B, M, N):
+    D = 256
+    md0 = _rand(B, M, D, seed=1, scale=0.3).requires_grad_(True)
+    md1 = _rand(B, N, D, seed=2, scale=0.3).requires_grad_(True)
+    z0, z1 = _rand(B, M, seed=3), _rand(B, N, seed=4)
+    gt = (torch.rand(B, M, N, generator=torch.Generator().manual_seed(5)) < 0.02).to(DEV)
+    ls = torch.nn.functional.logsigmoid
+    s_pos, *_ = ops.AssignPositives.apply(md0, md1, ls(z0), ls(z1), ls(-z0), ls(-z1), gt.view(torch.uint8),
+                                          gt.sum(2).float(), gt.sum(1).float(), bf16)
+    gw = _rand(B, seed=6)
+    (s_pos * gw).sum().backward()
+    rnd = O.bf16_round if bf16 else (lambda t: t)
+    a, b = rnd(md0.detach()).double().requires_grad_(True), rnd(md1.detach()).double().requires_grad_(True)
+    sim = a @ b.transpose(1, 2)
+    ref = ((2 * sim - torch.logsumexp(sim, 2, keepdim=True) - torch.logsumexp(sim, 1, keepdim=True)) * gt).sum((1, 2))
+    (ref * gw.double()).sum().backward()
+    tol = 2e-2 if bf16 else 1e-4
+    assert rel_err(s_pos, ref) < (1e-3 if bf16 else 1e-5)
+    assert rel_err(md0.grad, a.grad) < tol and rel_err(md1.grad, b.grad) < tol
+
+
+def test_other_heads_match_golden():
+    g = dict(np.load(os.path.join(GOLDEN, "heads.npz")))
+    for tag in ["a", "b"]:
+        sim = torch.from_numpy(g[f"{tag}|sim"]).float().to(DEV)
+        np.testing.assert_allclose(ops.log_double_softmax(sim, 0.7).cpu().numpy(), g[f"{tag}|lds"], atol=2e-5)
+        np.testing.assert_allclose(ops.log_optimal_transport(sim, 0.7, 50).cpu().numpy(), g[f"{tag}|lot"], atol=1e-4)
+
+
+def test_adam_flat_matches_torch():
+    n = 100_003
+    p = _rand(n, seed=1)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, weight_decay=0.01)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for t in range(1, 4):
+        g = _rand(n, seed=10 + t)
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_flat_(p, g * 4.0, m, v, t, 1e-3, weight_decay=0.01, grad_scale=0.25)
+    assert rel_err(p, ref.data) < 1e-6
+
+
+def test_errors_are_reported():
+    from gluefactory_b200._lib import Lgb200Error, call, stream_ptr
+
+    with pytest.raises(Lgb200Error, match="null pointer"):
+        call("lgb200_assign_lse", None, None, None, None, 1, 4, 4, stream_ptr())
+    with pytest.raises(Lgb200Error, match="empty"):
+        x = torch.zeros(4, device=DEV)
+        from gluefactory_b200._lib import ptr
+        call("lgb200_assign_lse", ptr(x), ptr(x), ptr(x), ptr(x), 0, 4, 4, stream_ptr())
