@@ -75,13 +75,37 @@ def load(check_device=True):
     return _lib
 
 
+# kernels launched per entry point (for bench.py's gpu_launches accounting)
+KERNELS_PER_CALL = {
+    "lgb200_rope_split_fwd": 1, "lgb200_rope_split_bwd": 1, "lgb200_attn_fwd": 1, "lgb200_attn_bwd": 3,
+    "lgb200_ln_gelu_fwd": 1, "lgb200_ln_gelu_bwd": 1, "lgb200_gemm_bf16": 1, "lgb200_assign_lse": 2,
+    "lgb200_assign_scores": 2, "lgb200_assign_bwd": 1, "lgb200_filter_matches": 1, "lgb200_log_double_softmax": 3,
+    "lgb200_adam_flat": 1, "lgb200_cast_bf16": 1,
+}
+launch_count = 0          # running total of kernels launched through `call`
+timed_entry = None        # when set to an entry-point name, every call of it is bracketed by CUDA events
+timed_events = []         # [(start_event, end_event, tag)]
+timed_tag = None
+
+
 def call(name, *args):
     """Invoke an entry point; a negative return code becomes a Python exception carrying the
     library's message (reference convention: Python exceptions / asserts, lightglue.py:413-414)."""
+    global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if timed_entry == name:
+        import torch
+
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = getattr(lib, name)(*args)
+        e.record()
+        timed_events.append((s, e, timed_tag))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise Lgb200Error(f"{name} failed ({rc}): {lib.lgb200_last_error().decode()}")
+    launch_count += KERNELS_PER_CALL.get(name, 1)
 
 
 def stream_ptr():

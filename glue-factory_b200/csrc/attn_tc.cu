@@ -260,12 +260,387 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* l
   return check_launch("attn_fwd_tc");
 }
 
-// Backward on tensor cores is the next milestone; until it lands the bf16 path uses the CUDA-core
-// kernels (same math, bf16 I/O, fp32 accumulation).
+// ---------------------------------------------------------------------------------------------
+// BACKWARD.  Two kernels, both deterministic (no atomics), both with the forward's structure
+// (TMA producer warp, single-thread MMA issuer, 4 softmax warps with thread == TMEM lane == row):
+//
+//   dKV kernel: CTA owns 128 keys (rows), walks the queries in tiles of 64:
+//       S^T  = K  Q_i^T   (128 x 64)      dP^T = V dO_i^T   (128 x 64)
+//       P^T  = exp2(S^T c - lse_i)        dS^T = P^T (dP^T - delta_i) scale
+//       dV  += P^T dO_i                   dK  += dS^T Q_i         (accumulated in TMEM)
+//   dQ kernel : CTA owns 128 queries (rows), walks the keys in tiles of 64:
+//       S    = Q K_j^T    (128 x 64)      dP   = dO V_j^T   (128 x 64)
+//       dS   = exp2(S c - lse) (dP - delta) scale
+//       dQ  += dS K_j                                        (accumulated in TMEM)
+//
+// S and dP are recomputed in both kernels (7 GEMMs instead of 5 per tile pair) in exchange for a
+// race-free dQ.  P^T / dS^T / dS are rounded to bf16 and handed to the second MMA through shared
+// memory in the K-major 128B-swizzled layout; the 64-row operand tiles (Q_i, dO_i, K_j) are used both
+// as K-major B operands (first GEMMs) and as MN-major B operands (accumulating GEMMs) of the same
+// shared-memory bytes.  256 TMEM columns and < 100 KiB smem per CTA -> two CTAs per SM.
+// ---------------------------------------------------------------------------------------------
+constexpr int FB_R = 128;            // rows owned by the CTA
+constexpr int FB_C = 64;             // inner tile
+constexpr int FB_RBYTES = FB_R * FA_D * 2;  // 16 KiB
+constexpr int FB_CBYTES = FB_C * FA_D * 2;  // 8 KiB
+constexpr int FB_PBYTES = FB_R * FB_C * 2;  // 16 KiB (128 rows x 64 bf16 = one swizzle block per row)
+constexpr int FB_STAGES = 2;
+constexpr int FB_TMEM_COLS = 256;
+constexpr int FB_S_COL = 0, FB_DP_COL = 64, FB_ACC0_COL = 128, FB_ACC1_COL = 192;
+constexpr int FB_DKV_SMEM = 2 * FB_RBYTES + FB_STAGES * 2 * FB_CBYTES + 2 * FB_PBYTES + 2 * 2 * FB_C * 4 + 256;
+constexpr int FB_DQ_SMEM = 2 * FB_RBYTES + FB_STAGES * 2 * FB_CBYTES + FB_PBYTES + 256;
+
+__device__ __forceinline__ void store_row_chunk32(uint8_t* row_base, int sw, int c, const float* v) {
+  // 32 consecutive columns [c*32, c*32+32) of a 64-column bf16 row (128 B, swizzled 16-byte chunks)
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 u;
+    u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+    u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+    const int chunk = c * 4 + g;
+    *reinterpret_cast<uint4*>(row_base + ((chunk ^ sw) << 4)) = u;
+  }
+}
+
+__device__ __forceinline__ void store_out_row64(__nv_bfloat16* dst, uint32_t taddr, bool valid) {
+  // 64 fp32 TMEM columns of this thread's lane -> 64 bf16 (128 contiguous bytes) in global memory.
+  // The TMEM loads are warp-collective: every lane executes them, only valid rows store.
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    float v[32];
+    tmem_ld32(taddr + c * 32, v);
+    tmem_ld_wait();
+    if (!valid) continue;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 u;
+      u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+      u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+      *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(192, 2)
+    attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                           const float* __restrict__ lse, const float* __restrict__ delta,
+                           __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int B, int Nq, int Nk,
+                           int H, int kv_shift, float scale, float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + FB_RBYTES;
+  uint8_t* sQ = sV + FB_RBYTES;                      // [FB_STAGES]
+  uint8_t* sDO = sQ + FB_STAGES * FB_CBYTES;         // [FB_STAGES]
+  uint8_t* sP = sDO + FB_STAGES * FB_CBYTES;
+  uint8_t* sDS = sP + FB_PBYTES;
+  float* sLse = reinterpret_cast<float*>(sDS + FB_PBYTES);  // [2][64]
+  float* sDel = sLse + 2 * FB_C;                            // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDel + 2 * FB_C);
+  uint64_t* kv_full = bars;
+  uint64_t* in_full = bars + 1;               // [FB_STAGES]
+  uint64_t* in_empty = in_full + FB_STAGES;   // [FB_STAGES]
+  uint64_t* sp_full = in_empty + FB_STAGES;
+  uint64_t* pds_full = sp_full + 1;
+  uint64_t* acc_done = pds_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * FB_R, h = blockIdx.y, kb = blockIdx.z;
+  const int qb = ((kb - kv_shift) % B + B) % B;
+  const int ntiles = (Nq + FB_C - 1) / FB_C;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < FB_STAGES; ++s) {
+      mbar_init(&in_full[s], 1);
+      mbar_init(&in_empty[s], 1);
+    }
+    mbar_init(sp_full, 1);
+    mbar_init(pds_full, 4);
+    mbar_init(acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, FB_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * FB_RBYTES);
+      tma_load_4d(sK, &tmK, kv_full, 0, h, k0, kb);
+      tma_load_4d(sV, &tmV, kv_full, 0, h, k0, kb);
+      for (int i = 0; i < ntiles; ++i) {
+        const int s = i % FB_STAGES;
+        mbar_wait(&in_empty[s], ((i / FB_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&in_full[s], 2 * FB_CBYTES);
+        tma_load_4d(sQ + s * FB_CBYTES, &tmQ, &in_full[s], 0, h, i * FB_C, qb);
+        tma_load_4d(sDO + s * FB_CBYTES, &tmDO, &in_full[s], 0, h, i * FB_C, qb);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (K|V) K-major x (Q|dO) K-major
+      constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // (P^T|dS^T) K-major x (dO|Q) MN-major
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aDO = smem_u32(sDO);
+      const uint32_t aP = smem_u32(sP), aDS = smem_u32(sDS);
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < ntiles; ++i) {
+        const int s = i % FB_STAGES;
+        mbar_wait(&in_full[s], (i / FB_STAGES) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk) {
+          umma_bf16(tmem_base + FB_S_COL, make_smem_desc(aK + kk * 32, 16, 1024),
+                    make_smem_desc(aQ + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk) {
+          umma_bf16(tmem_base + FB_DP_COL, make_smem_desc(aV + kk * 32, 16, 1024),
+                    make_smem_desc(aDO + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(sp_full);
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < FB_C / 16; ++kk) {  // contraction over the 64 queries of this tile
+          umma_bf16(tmem_base + FB_ACC0_COL, make_smem_desc(aP + kk * 32, 16, 1024),
+                    make_smem_desc(aDO + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (i | kk) != 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < FB_C / 16; ++kk) {
+          umma_bf16(tmem_base + FB_ACC1_COL, make_smem_desc(aDS + kk * 32, 16, 1024),
+                    make_smem_desc(aQ + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (i | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&in_empty[s]);
+      }
+      umma_commit(acc_done);
+    }
+  } else {
+    const int r = warp * 32 + lane;  // key row within the tile
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    uint8_t* prow = sP + r * 128;
+    uint8_t* dsrow = sDS + r * 128;
+    const int sw = r & 7;
+    for (int i = 0; i < ntiles; ++i) {
+      const int buf = i & 1;
+      {  // stage lse (pre-multiplied by log2 e) and delta of the 64 queries of this tile
+        const int qi = i * FB_C + (r & 63);
+        const int64_t o = ((int64_t)qb * H + h) * Nq + qi;
+        if (r < 64) sLse[buf * FB_C + r] = qi < Nq ? lse[o] * 1.4426950408889634f : INFINITY;
+        else sDel[buf * FB_C + (r - 64)] = qi < Nq ? delta[o] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(sp_full, i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < FB_C / 32; ++c) {
+        float sv[32], dp[32];
+        tmem_ld32(t_lane + FB_S_COL + c * 32, sv);
+        tmem_ld32(t_lane + FB_DP_COL + c * 32, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float p = fast_exp2(fmaf(sv[e], scale_log2, -sLse[buf * FB_C + c * 32 + e]));
+          dp[e] = p * (dp[e] - sDel[buf * FB_C + c * 32 + e]) * scale;
+          sv[e] = p;
+        }
+        store_row_chunk32(prow, sw, c, sv);
+        store_row_chunk32(dsrow, sw, c, dp);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+    }
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    const int row = k0 + r;
+    const int64_t o = (((int64_t)kb * Nk + (row < Nk ? row : 0)) * H + h) * FA_D;
+    store_out_row64(dv + o, t_lane + FB_ACC0_COL, row < Nk);
+    store_out_row64(dk + o, t_lane + FB_ACC1_COL, row < Nk);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, FB_TMEM_COLS);
+}
+
+__global__ void __launch_bounds__(192, 2)
+    attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                          const float* __restrict__ lse, const float* __restrict__ delta,
+                          __nv_bfloat16* __restrict__ dq, int B, int Nq, int Nk, int H, int kv_shift, float scale,
+                          float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sDO = sQ + FB_RBYTES;
+  uint8_t* sK = sDO + FB_RBYTES;                  // [FB_STAGES]
+  uint8_t* sV = sK + FB_STAGES * FB_CBYTES;       // [FB_STAGES]
+  uint8_t* sDS = sV + FB_STAGES * FB_CBYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + FB_PBYTES);
+  uint64_t* q_full = bars;
+  uint64_t* in_full = bars + 1;
+  uint64_t* in_empty = in_full + FB_STAGES;
+  uint64_t* sp_full = in_empty + FB_STAGES;
+  uint64_t* ds_full = sp_full + 1;
+  uint64_t* acc_done = ds_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * FB_R, h = blockIdx.y, b = blockIdx.z;
+  const int kb = (b + kv_shift) % B;
+  const int ntiles = (Nk + FB_C - 1) / FB_C;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(q_full, 1);
+    for (int s = 0; s < FB_STAGES; ++s) {
+      mbar_init(&in_full[s], 1);
+      mbar_init(&in_empty[s], 1);
+    }
+    mbar_init(sp_full, 1);
+    mbar_init(ds_full, 4);
+    mbar_init(acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, FB_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * FB_RBYTES);
+      tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
+      tma_load_4d(sDO, &tmDO, q_full, 0, h, q0, b);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % FB_STAGES;
+        mbar_wait(&in_empty[s], ((j / FB_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&in_full[s], 2 * FB_CBYTES);
+        tma_load_4d(sK + s * FB_CBYTES, &tmK, &in_full[s], 0, h, j * FB_C, kb);
+        tma_load_4d(sV + s * FB_CBYTES, &tmV, &in_full[s], 0, h, j * FB_C, kb);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (Q|dO) K-major x (K|V) K-major
+      constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // dS K-major x K_j MN-major
+      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV);
+      const uint32_t aDS = smem_u32(sDS);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % FB_STAGES;
+        mbar_wait(&in_full[s], (j / FB_STAGES) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk) {
+          umma_bf16(tmem_base + FB_S_COL, make_smem_desc(aQ + kk * 32, 16, 1024),
+                    make_smem_desc(aK + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk) {
+          umma_bf16(tmem_base + FB_DP_COL, make_smem_desc(aDO + kk * 32, 16, 1024),
+                    make_smem_desc(aV + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(sp_full);
+        mbar_wait(ds_full, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < FB_C / 16; ++kk) {  // contraction over the 64 keys of this tile
+          umma_bf16(tmem_base + FB_ACC0_COL, make_smem_desc(aDS + kk * 32, 16, 1024),
+                    make_smem_desc(aK + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&in_empty[s]);
+      }
+      umma_commit(acc_done);
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    uint8_t* dsrow = sDS + r * 128;
+    const int sw = r & 7;
+    const int row = q0 + r;
+    const int64_t lo = ((int64_t)b * H + h) * Nq + row;
+    const float lse2 = row < Nq ? lse[lo] * 1.4426950408889634f : INFINITY;
+    const float dl = row < Nq ? delta[lo] : 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(sp_full, j & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < FB_C / 32; ++c) {
+        float sv[32], dp[32];
+        tmem_ld32(t_lane + FB_S_COL + c * 32, sv);
+        tmem_ld32(t_lane + FB_DP_COL + c * 32, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float p = fast_exp2(fmaf(sv[e], scale_log2, -lse2));
+          dp[e] = p * (dp[e] - dl) * scale;
+        }
+        store_row_chunk32(dsrow, sw, c, dp);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    store_out_row64(dq + (((int64_t)b * Nq + (row < Nq ? row : 0)) * H + h) * FA_D, t_lane + FB_ACC0_COL, row < Nq);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, FB_TMEM_COLS);
+}
+
 int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
                 void* dq, void* dk, void* dv, float* delta, int B, int Nq, int Nk, int H, int kv_shift, float scale,
                 cudaStream_t stream) {
-  return attn_bwd_simt<__nv_bfloat16>(q, k, v, out, lse, dout, dq, dk, dv, delta, B, Nq, Nk, H, kv_shift, scale, stream);
+  int rc = attn_delta<__nv_bfloat16>(out, dout, delta, B, Nq, H, stream);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_DKV_SMEM);
+    LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_DQ_SMEM);
+    LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const float sl2 = scale * 1.4426950408889634f;
+  {
+    CUtensorMap tq, tk, tv, tdo;
+    if ((rc = make_qkv_tmap(&tq, q, B, Nq, H, FB_R))) return rc;
+    if ((rc = make_qkv_tmap(&tdo, dout, B, Nq, H, FB_R))) return rc;
+    if ((rc = make_qkv_tmap(&tk, k, B, Nk, H, FB_C))) return rc;
+    if ((rc = make_qkv_tmap(&tv, v, B, Nk, H, FB_C))) return rc;
+    dim3 grid((Nq + FB_R - 1) / FB_R, H, B);
+    attn_bwd_dq_tc_kernel<<<grid, 192, FB_DQ_SMEM, stream>>>(tq, tk, tv, tdo, lse, delta,
+                                                            static_cast<__nv_bfloat16*>(dq), B, Nq, Nk, H, kv_shift,
+                                                            scale, sl2);
+  }
+  {
+    CUtensorMap tq, tk, tv, tdo;
+    if ((rc = make_qkv_tmap(&tq, q, B, Nq, H, FB_C))) return rc;
+    if ((rc = make_qkv_tmap(&tdo, dout, B, Nq, H, FB_C))) return rc;
+    if ((rc = make_qkv_tmap(&tk, k, B, Nk, H, FB_R))) return rc;
+    if ((rc = make_qkv_tmap(&tv, v, B, Nk, H, FB_R))) return rc;
+    dim3 grid((Nk + FB_R - 1) / FB_R, H, B);
+    attn_bwd_dkv_tc_kernel<<<grid, 192, FB_DKV_SMEM, stream>>>(tq, tk, tv, tdo, lse, delta,
+                                                              static_cast<__nv_bfloat16*>(dk),
+                                                              static_cast<__nv_bfloat16*>(dv), B, Nq, Nk, H, kv_shift,
+                                                              scale, sl2);
+  }
+  return check_launch("attn_bwd_tc");
 }
 
 }  // namespace lgb
