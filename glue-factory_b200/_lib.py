@@ -38,7 +38,7 @@ SIGNATURES = {
     "lgb200_heads_ws_bytes": (_sz, [_i, _i, _i]),
     "lgb200_log_double_softmax": (_i, [_vp, _f, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_sinkhorn": (_i, [_vp, _f, _i, _vp, _vp, _i, _i, _i, _vp]),
-    "lgb200_adam_flat": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _i, _f, _vp]),
+    "lgb200_adam_flat": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _i, _vp, _f, _vp]),
     "lgb200_cast_bf16": (_i, [_vp, _vp, _i64, _vp]),
 }
 

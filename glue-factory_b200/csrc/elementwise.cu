@@ -284,9 +284,15 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                        const float* __restrict__ lr_per_elem_or_null, float lr,
                                                        float beta1, float beta2, float eps, float wd, float bc1,
-                                                       float bc2_sqrt, float grad_scale) {
+                                                       float bc2_sqrt, float grad_scale,
+                                                       const int* __restrict__ step_dev) {
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i0 >= n) return;
+  if (step_dev) {  // step count lives in device memory (CUDA-graph replay): bias corrections computed here
+    const float t = (float)(*step_dev);
+    bc1 = 1.f - powf(beta1, t);
+    bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+  }
   if (i0 + 4 <= n) {
     float4 pp = *reinterpret_cast<float4*>(p + i0), gg = *reinterpret_cast<const float4*>(g + i0);
     float4 mm = *reinterpret_cast<float4*>(m + i0), vv = *reinterpret_cast<float4*>(v + i0);
@@ -438,18 +444,18 @@ int lgb200_ln_gelu_bwd(const void* dy, const void* x, const float* gamma, const 
 }
 
 int lgb200_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_per_elem, float lr,
-                     float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                     cudaStream_t stream) {
+                     float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
+                     float grad_scale, cudaStream_t stream) {
   LGB_REQUIRE(p && g && m && v, kErrInvalid, "adam_flat: null pointer");
-  LGB_REQUIRE(n > 0 && step >= 1, kErrInvalid, "adam_flat: bad n/step");
+  LGB_REQUIRE(n > 0 && (step >= 1 || step_dev), kErrInvalid, "adam_flat: bad n/step");
   LGB_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                reinterpret_cast<uintptr_t>(v)) % 16 == 0,
               kErrInvalid, "adam_flat: buffers must be 16-byte aligned");
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  const float bc1 = step >= 1 ? 1.f - powf(beta1, (float)step) : 1.f;
+  const float bc2s = step >= 1 ? sqrtf(1.f - powf(beta2, (float)step)) : 1.f;
   const unsigned grid = (unsigned)(((n + 3) / 4 + 255) / 256);
   adam_flat_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n, lr_per_elem, lr, beta1, beta2, eps, weight_decay, bc1, bc2s,
-                                             grad_scale);
+                                             grad_scale, step_dev);
   return check_launch("adam_flat");
 }
 

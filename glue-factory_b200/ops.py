@@ -251,9 +251,11 @@ def log_optimal_transport(sim, alpha, iters):
     return out
 
 
-def adam_flat_(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0, lr_per_elem=None):
-    """In-place Adam on flat fp32 buffers (train.py:358-361, 513)."""
+def adam_flat_(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0, lr_per_elem=None,
+               step_dev=None):
+    """In-place Adam on flat fp32 buffers (train.py:358-361, 513).  `step_dev` (int32 device scalar) replaces
+    the host step count when the call is captured in a CUDA graph."""
     for t in (p, g, m, v):
         _chk(t, torch.float32)
     call("lgb200_adam_flat", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), ptr(lr_per_elem), float(lr), float(betas[0]),
-         float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale), stream_ptr())
+         float(betas[1]), float(eps), float(weight_decay), int(step), ptr(step_dev), float(grad_scale), stream_ptr())

@@ -69,17 +69,59 @@ class MatcherTrainer:
         if self.world > 1:
             dist.all_reduce(self.fp.grad, op=dist.ReduceOp.SUM, group=self.group)
 
+    # ---- CUDA-graph replay of the whole step (removes the ~2500 per-step launch calls from the host)
+    def capture(self, example, device, warmup=3):
+        """Capture forward + loss + backward + all-reduce + Adam into one CUDA graph.  `example` fixes the
+        shapes; later batches are copied into the captured static input buffers."""
+        self._static = to_device(example, device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_impl(self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        self._t_dev = torch.full((1,), self.t, device=device, dtype=torch.int32)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss, self._static_losses = self._step_impl(self._static, graphed=True)
+        return self
+
+    def step_graphed(self, data):
+        """Replay the captured step on a new batch (host or device tensors of the captured shapes)."""
+        _copy_into(self._static, data)
+        self._graph.replay()
+        self.t += 1
+        return self._static_loss, self._static_losses
+
     def step(self, data, device=None):
         """One optimiser step on one batch; `data` may live in (pinned) host memory."""
         if device is not None:
             data = to_device(data, device, non_blocking=True)
+        return self._step_impl(data)
+
+    def _step_impl(self, data, graphed=False):
         self.fp.zero_grad()
         pred = self.model(data)
         losses, _ = self.model.loss(pred, data)
         loss = losses["total"].mean()
         loss.backward()
         self.exchange_gradients()
-        self.t += 1
-        ops.adam_flat_(self.fp.flat, self.fp.grad, self.m, self.v, self.t, self.lr, self.betas, self.eps, self.wd,
-                       grad_scale=1.0 / self.world)
+        if graphed:
+            # the bias-correction terms depend on the step count, which must not be baked into the graph:
+            # the count lives in device memory and is incremented inside the graph.
+            self._t_dev.add_(1)
+            ops.adam_flat_(self.fp.flat, self.fp.grad, self.m, self.v, 0, self.lr, self.betas, self.eps, self.wd,
+                           grad_scale=1.0 / self.world, step_dev=self._t_dev)
+        else:
+            self.t += 1
+            ops.adam_flat_(self.fp.flat, self.fp.grad, self.m, self.v, self.t, self.lr, self.betas, self.eps, self.wd,
+                           grad_scale=1.0 / self.world)
         return loss.detach(), losses
+
+
+def _copy_into(dst, src):
+    for k, v in dst.items():
+        if isinstance(v, dict):
+            _copy_into(v, src[k])
+        elif torch.is_tensor(v):
+            v.copy_(src[k], non_blocking=True)

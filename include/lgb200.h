@@ -132,9 +132,11 @@ int lgb200_sinkhorn(const float* sim, float alpha, int iters, float* out, void* 
                     cudaStream_t stream);
 
 /* ---- flat-buffer optimiser (train.py:358-361, 513) and casts --------------------------------------- */
+/* step: 1-based step count for the bias correction; when step_dev != NULL the count is read from device
+ * memory instead (so a CUDA graph of the whole training step can be replayed).                       */
 int lgb200_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_per_elem, float lr,
-                     float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                     cudaStream_t stream);
+                     float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
+                     float grad_scale, cudaStream_t stream);
 int lgb200_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream);
 
 #ifdef __cplusplus

@@ -141,3 +141,25 @@ def test_nan_propagates_to_loss():
     pred = model(data)
     losses, _ = model.loss(pred, data)
     assert torch.isnan(losses["total"]).all()
+
+
+def test_cuda_graph_step_matches_eager_step():
+    """The captured-graph replay of the training step must produce the same parameters as eager steps."""
+    conf = dict(synthetic.DEFAULT_CONF, n_layers=2)
+    batches = [synthetic.to_device(synthetic.make_pairs(2, 256, seed=50 + i), DEV) for i in range(3)]
+
+    def run(graphed):
+        model = _build(conf, synthetic.make_weights(conf, seed=51), "bf16")
+        tr = MatcherTrainer(model, lr=1e-3)
+        if graphed:
+            tr.capture(batches[0], DEV, warmup=0)
+        losses = []
+        for b in batches:
+            loss, _ = tr.step_graphed(b) if graphed else tr.step(b)
+            losses.append(loss.item())
+        return tr.fp.flat.clone(), losses
+
+    p_eager, l_eager = run(False)
+    p_graph, l_graph = run(True)
+    np.testing.assert_allclose(l_graph, l_eager, rtol=1e-5)
+    assert rel_err(p_graph, p_eager) < 1e-5
