@@ -82,6 +82,20 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
+def host_threads():
+    """Threads the CPU leg may really use: affinity mask and cgroup CPU quota, capped at 32 (the oracle's
+    N=2048 GEMMs are small; more threads only add synchronisation on a many-core host)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return max(1, min(n, int(os.environ.get("LGB200_CPU_THREADS", "32"))))
+
+
 def pin(data):
     if isinstance(data, dict):
         return {k: pin(v) for k, v in data.items()}
@@ -105,7 +119,7 @@ def run_reference(args, rank, world):
     from gluefactory_b200 import synthetic
     from oracle import lightglue_oracle as O
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     conf = dict(synthetic.DEFAULT_CONF)
     w = {k: v.clone().requires_grad_(True) for k, v in synthetic.make_weights(conf, seed=0).items()}
     data = synthetic.make_pairs(1, N_KPTS, seed=1234)
@@ -129,6 +143,7 @@ def run_reference(args, rank, world):
         "config": {"workload": f"LightGlue train step N={N_KPTS} d={D_DESC} L={N_LAYERS} (configs[2]); one pair per step",
                    "pairs_per_step": 1},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "host_cpus": os.cpu_count(),
                          "sample": f"{steps} train steps of 1 pair (N={N_KPTS}, L={N_LAYERS}) after {warm + 1} warm-up"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -141,7 +156,7 @@ def cpu_baseline_sample(seconds=25.0):
     from gluefactory_b200 import synthetic
     from oracle import lightglue_oracle as O
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     conf = dict(synthetic.DEFAULT_CONF)
     w = {k: v.clone().requires_grad_(True) for k, v in synthetic.make_weights(conf, seed=0).items()}
     data = synthetic.make_pairs(1, N_KPTS, seed=1234)
@@ -153,7 +168,7 @@ def cpu_baseline_sample(seconds=25.0):
     for _ in range(steps):
         O.train_step_cpu(w, data, conf, adam_state=state)
     dt = (time.time() - t0) / steps
-    return {"value": 1.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "host_cpus": os.cpu_count(),
             "sample": f"{steps} train steps of 1 pair (N={N_KPTS}, L={N_LAYERS}, fp32, oracle port) after 1 warm-up"}
 
 

@@ -29,7 +29,7 @@ SIGNATURES = {
     "lgb200_ln_gelu_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _i, _vp]),
     "lgb200_ln_gelu_bwd_parts": (_i, [_i64]),
     "lgb200_ln_gelu_bwd": (_i, [_vp] * 9 + [_i64, _i, _i, _vp]),
-    "lgb200_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i, _vp]),
+    "lgb200_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i, _f, _vp]),
     "lgb200_assign_ws_bytes": (_sz, [_i, _i, _i]),
     "lgb200_assign_lse": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_assign_scores": (_i, [_vp] * 16 + [_i, _i, _i, _vp]),
@@ -40,6 +40,7 @@ SIGNATURES = {
     "lgb200_sinkhorn": (_i, [_vp, _f, _i, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_adam_flat": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _i, _vp, _f, _vp]),
     "lgb200_cast_bf16": (_i, [_vp, _vp, _i64, _vp]),
+    "lgb200_residual_add_cast": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
 }
 
 

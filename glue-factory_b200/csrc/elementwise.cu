@@ -338,11 +338,52 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
   }
 }
 
+// x_out = x + y (fp32 residual stream) and its compute-dtype copy for the next GEMM, in one pass
+template <typename T>
+__global__ void __launch_bounds__(256) residual_add_cast_kernel(const float* __restrict__ x, const T* __restrict__ y,
+                                                               float* __restrict__ xo, T* __restrict__ xc, int64_t n) {
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i0 >= n) return;
+  if (i0 + 8 <= n) {
+    Vec8<float> a = Vec8<float>::load(x + i0);
+    if (y) {
+      Vec8<T> b = Vec8<T>::load(y + i0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a.v[e] += b.v[e];
+    }
+    if (xo) a.store(xo + i0);
+    Vec8<T> c;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) c.v[e] = a.v[e];
+    if (xc) c.store(xc + i0);
+  } else {
+    for (int64_t i = i0; i < n; ++i) {
+      float v = x[i] + (y ? (float)y[i] : 0.f);
+      if (xo) xo[i] = v;
+      if (xc) xc[i] = (T)v;
+    }
+  }
+}
+
 }  // namespace lgb
 
 using namespace lgb;
 
 extern "C" {
+
+int lgb200_residual_add_cast(const float* x, const void* y, float* x_out, void* x_cast, int64_t n, int dtype,
+                             cudaStream_t stream) {
+  LGB_REQUIRE(x && (x_out || x_cast) && n > 0, kErrInvalid, "residual_add_cast: bad arguments");
+  const unsigned grid = (unsigned)(((n + 7) / 8 + 255) / 256);
+  if (dtype == LGB200_F32)
+    residual_add_cast_kernel<float><<<grid, 256, 0, stream>>>(x, (const float*)y, x_out, (float*)x_cast, n);
+  else if (dtype == LGB200_BF16)
+    residual_add_cast_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, (const __nv_bfloat16*)y, x_out,
+                                                                      (__nv_bfloat16*)x_cast, n);
+  else
+    LGB_REQUIRE(false, kErrInvalid, "residual_add_cast: bad dtype %d", dtype);
+  return check_launch("residual_add_cast");
+}
 
 int lgb200_rope_split_fwd(const void* qkv, const float* theta, void* q, void* k, void* v, int64_t ntok, int H,
                           int dtype, cudaStream_t stream) {

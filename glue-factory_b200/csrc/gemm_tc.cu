@@ -19,7 +19,7 @@ constexpr int G_SMEM = G_STAGES * 2 * G_TILE + 256;
 template <bool A_MN, bool B_MN, typename OutT>
 __global__ void __launch_bounds__(192, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     OutT* __restrict__ C, int M, int N, int K, int64_t ldc, int64_t strideC) {
+                     OutT* __restrict__ C, int M, int N, int K, int64_t ldc, int64_t strideC, float alpha) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + G_STAGES * G_TILE;
@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(192, 1)
       float v[32];
       tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
       tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] *= alpha;
       if (row < M) {
         const int col0 = n0 + c * 32;
         if (vec_ok && col0 + 32 <= N) {
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(192, 1)
 
 template <bool A_MN, bool B_MN, typename OutT>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int batch, int M, int N, int K,
-                       int64_t ldc, int64_t strideC, cudaStream_t stream) {
+                       int64_t ldc, int64_t strideC, float alpha, cudaStream_t stream) {
   auto kern = gemm_bf16_kernel<A_MN, B_MN, OutT>;
   static bool configured = false;
   if (!configured) {
@@ -149,7 +151,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, in
     configured = true;
   }
   dim3 grid((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M, batch);
-  kern<<<grid, 192, G_SMEM, stream>>>(ta, tb, static_cast<OutT*>(C), M, N, K, ldc, strideC);
+  kern<<<grid, 192, G_SMEM, stream>>>(ta, tb, static_cast<OutT*>(C), M, N, K, ldc, strideC, alpha);
   return check_launch("gemm_bf16");
 }
 
@@ -159,7 +161,7 @@ using namespace lgb;
 
 extern "C" int lgb200_gemm_bf16(const void* A, const void* B, void* C, int batch, int M, int N, int K, int a_mn_major,
                                 int b_mn_major, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA,
-                                int64_t strideB, int64_t strideC, int c_dtype, cudaStream_t stream) {
+                                int64_t strideB, int64_t strideC, int c_dtype, float alpha, cudaStream_t stream) {
   LGB_REQUIRE(A && B && C, kErrInvalid, "gemm_bf16: null pointer");
   LGB_REQUIRE(batch > 0 && M > 0 && N > 0 && K > 0, kErrInvalid, "gemm_bf16: empty problem %dx%dx%dx%d", batch, M, N, K);
   LGB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, kErrInvalid, "gemm_bf16: lda/ldb must be multiples of 8 elements");
@@ -185,9 +187,9 @@ extern "C" int lgb200_gemm_bf16(const void* A, const void* B, void* C, int batch
   }
 #define LGB_GEMM_CASE(AM, BMJ)                                                                              \
   if (a_mn_major == AM && b_mn_major == BMJ) {                                                              \
-    if (c_dtype == LGB200_F32) return launch_gemm<AM, BMJ, float>(ta, tb, C, batch, M, N, K, ldc, strideC, stream); \
+    if (c_dtype == LGB200_F32) return launch_gemm<AM, BMJ, float>(ta, tb, C, batch, M, N, K, ldc, strideC, alpha, stream); \
     if (c_dtype == LGB200_BF16)                                                                             \
-      return launch_gemm<AM, BMJ, __nv_bfloat16>(ta, tb, C, batch, M, N, K, ldc, strideC, stream);         \
+      return launch_gemm<AM, BMJ, __nv_bfloat16>(ta, tb, C, batch, M, N, K, ldc, strideC, alpha, stream);  \
   }
   LGB_GEMM_CASE(0, 0)
   LGB_GEMM_CASE(0, 1)

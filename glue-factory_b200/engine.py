@@ -1,0 +1,252 @@
+"""Hand-scheduled forward/backward of the matcher's two repeating units.
+
+`LayerFn`  : one LightGlue transformer layer (self block on both images + bidirectional cross block,
+             lightglue.py:224-245) as ONE autograd node.
+`HeadFn`   : one deep-supervision head (MatchAssignment + NLL terms + argmax, lightglue.py:271-290,
+             losses.py:6-73) as ONE autograd node.
+
+Compared with composing the same kernels through torch autograd op by op (the `engine: autograd`
+path kept in matchers/lightglue.py as the cross-check), the explicit schedule removes the per-op
+dtype casts, the cat/slice copies and ~2/3 of the launches: weights are read from a compute-dtype
+shadow refreshed once per step, weight gradients are produced in fp32 directly by the GEMM
+(`out_dtype`), the residual update emits the next GEMM's operand in the same pass, and nothing
+N x N is ever kept besides `sim`.
+
+All dense projections are plain cuBLAS GEMMs (`torch.mm/addmm`); everything else is an lgb200 kernel.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+_OUT_DTYPE_OK = True
+
+
+def _wgrad(dy, a):
+    """dW [out, in] fp32 = dy^T a for compute-dtype dy [T, out], a [T, in]."""
+    global _OUT_DTYPE_OK
+    if dy.dtype == torch.float32:
+        return torch.mm(dy.t(), a)
+    if _OUT_DTYPE_OK:
+        try:
+            return torch.mm(dy.t(), a, out_dtype=torch.float32)
+        except (TypeError, RuntimeError):
+            _OUT_DTYPE_OK = False
+    return torch.mm(dy.t(), a).float()
+
+
+def _bgrad(dy):
+    return dy.sum(0, dtype=torch.float32)
+
+
+def _attend_fwd(q, k, v, sizes, H, cross):
+    """q,k,v [T, H*64] over tokens [image0 (B*M); image1 (B*N)] -> (out [T, H*64], lse tuple)."""
+    B, M, N = sizes
+    scale = 0.125
+    if M == N:
+        shp = (2 * B, M, H, 64)
+        out, lse = ops.attn_fwd(q.view(shp), k.view(shp), v.view(shp), B if cross else 0, scale)
+        return out.view(q.shape), (lse,)
+    t0 = B * M
+    q0, q1 = q[:t0].view(B, M, H, 64), q[t0:].view(B, N, H, 64)
+    k0, k1 = k[:t0].view(B, M, H, 64), k[t0:].view(B, N, H, 64)
+    v0, v1 = v[:t0].view(B, M, H, 64), v[t0:].view(B, N, H, 64)
+    if cross:
+        o0, l0 = ops.attn_fwd(q0, k1, v1, 0, scale)
+        o1, l1 = ops.attn_fwd(q1, k0, v0, 0, scale)
+    else:
+        o0, l0 = ops.attn_fwd(q0, k0, v0, 0, scale)
+        o1, l1 = ops.attn_fwd(q1, k1, v1, 0, scale)
+    return torch.cat([o0.reshape(t0, -1), o1.reshape(B * N, -1)], 0), (l0, l1)
+
+
+def _attend_bwd(q, k, v, out, lses, dout, sizes, H, cross):
+    B, M, N = sizes
+    scale = 0.125
+    if M == N:
+        shp = (2 * B, M, H, 64)
+        dq, dk, dv = ops.attn_bwd(q.view(shp), k.view(shp), v.view(shp), out.view(shp), lses[0], dout.view(shp),
+                                  B if cross else 0, scale)
+        return dq.view(q.shape), dk.view(q.shape), dv.view(q.shape)
+    t0 = B * M
+    sp = lambda t: (t[:t0].view(B, M, H, 64), t[t0:].view(B, N, H, 64))  # noqa: E731
+    (q0, q1), (k0, k1), (v0, v1), (o0, o1), (g0, g1) = sp(q), sp(k), sp(v), sp(out), sp(dout.contiguous())
+    if cross:
+        dq0, dk1, dv1 = ops.attn_bwd(q0, k1, v1, o0, lses[0], g0, 0, scale)
+        dq1, dk0, dv0 = ops.attn_bwd(q1, k0, v0, o1, lses[1], g1, 0, scale)
+    else:
+        dq0, dk0, dv0 = ops.attn_bwd(q0, k0, v0, o0, lses[0], g0, 0, scale)
+        dq1, dk1, dv1 = ops.attn_bwd(q1, k1, v1, o1, lses[1], g1, 0, scale)
+    cat = lambda a, b: torch.cat([a.reshape(t0, -1), b.reshape(B * N, -1)], 0)  # noqa: E731
+    return cat(dq0, dq1), cat(dk0, dk1), cat(dv0, dv1)
+
+
+# order of the per-layer tensors (reference names, lightglue.py:139-148, 174-183)
+LAYER_PARAMS = [
+    "self_attn.Wqkv.weight", "self_attn.Wqkv.bias", "self_attn.out_proj.weight", "self_attn.out_proj.bias",
+    "self_attn.ffn.0.weight", "self_attn.ffn.0.bias", "self_attn.ffn.1.weight", "self_attn.ffn.1.bias",
+    "self_attn.ffn.3.weight", "self_attn.ffn.3.bias",
+    "cross_attn.to_qk.weight", "cross_attn.to_qk.bias", "cross_attn.to_v.weight", "cross_attn.to_v.bias",
+    "cross_attn.to_out.weight", "cross_attn.to_out.bias", "cross_attn.ffn.0.weight", "cross_attn.ffn.0.bias",
+    "cross_attn.ffn.1.weight", "cross_attn.ffn.1.bias", "cross_attn.ffn.3.weight", "cross_attn.ffn.3.bias",
+]
+_LN_SLOTS = (6, 7, 18, 19)  # LayerNorm affine stays fp32
+
+
+class LayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, theta, sizes, H, cdt, eps, w, *params):
+        (Wqkv, bqkv, Wo, bo, W0, b0, g1, be1, W3, b3,
+         Wqk, bqk, Wv, bv, Wout, bout, W0c, b0c, g2, be2, W3c, b3c) = w
+        D = x.shape[1]
+        x = x.contiguous()
+        # ---- self block (lightglue.py:150-163)
+        _, x16 = ops.residual_add_cast(x, None, cdt)
+        qkv = torch.addmm(bqkv, x16, Wqkv.t())
+        q, k, v = ops.rope_fwd(qkv, theta, H)
+        del qkv
+        att, lse1 = _attend_fwd(q, k, v, sizes, H, cross=False)
+        msg = torch.addmm(bo, att, Wo.t())
+        h = torch.addmm(b0, x16, W0[:, :D].t())
+        h.addmm_(msg, W0[:, D:].t())
+        g, mean1, rstd1 = ops.ln_gelu_fwd(h, g1, be1, eps)
+        y = torch.addmm(b3, g, W3.t())
+        x1, x1_16 = ops.residual_add_cast(x, y, cdt)
+        del y
+        # ---- cross block (lightglue.py:195-221)
+        qk = torch.addmm(bqk, x1_16, Wqk.t())
+        vv = torch.addmm(bv, x1_16, Wv.t())
+        m, lse2 = _attend_fwd(qk, qk, vv, sizes, H, cross=True)
+        msg2 = torch.addmm(bout, m, Wout.t())
+        h2 = torch.addmm(b0c, x1_16, W0c[:, :D].t())
+        h2.addmm_(msg2, W0c[:, D:].t())
+        gg, mean2, rstd2 = ops.ln_gelu_fwd(h2, g2, be2, eps)
+        y2 = torch.addmm(b3c, gg, W3c.t())
+        x2 = x1 + y2
+        ctx.save_for_backward(theta, x16, q, k, v, att, msg, h, mean1, rstd1, g, x1_16, qk, vv, m, msg2, h2, mean2,
+                              rstd2, gg, *lse1, *lse2, *w)
+        ctx.meta = (sizes, H, cdt, len(lse1), len(lse2), D)
+        return x2
+
+    @staticmethod
+    def backward(ctx, dx):
+        sizes, H, cdt, n1, n2, D = ctx.meta
+        sv = ctx.saved_tensors
+        (theta, x16, q, k, v, att, msg, h, mean1, rstd1, g, x1_16, qk, vv, m, msg2, h2, mean2, rstd2, gg) = sv[:20]
+        lse1, lse2 = sv[20:20 + n1], sv[20 + n1:20 + n1 + n2]
+        (Wqkv, bqkv, Wo, bo, W0, b0, g1, be1, W3, b3,
+         Wqk, bqk, Wv, bv, Wout, bout, W0c, b0c, g2, be2, W3c, b3c) = sv[20 + n1 + n2:]
+        dx = dx.contiguous()
+        # ---- cross block
+        dy2 = dx.to(cdt)
+        dW3c, db3c = _wgrad(dy2, gg), _bgrad(dy2)
+        dgg = torch.mm(dy2, W3c)
+        dh2, dg2, dbe2 = ops.ln_gelu_bwd(dgg, h2, g2, be2, mean2, rstd2)
+        del dgg
+        db0c = _bgrad(dh2)
+        dW0c = torch.cat([_wgrad(dh2, x1_16), _wgrad(dh2, msg2)], 1)
+        dmsg2 = torch.mm(dh2, W0c[:, D:])
+        dx1 = dx + torch.mm(dh2, W0c[:, :D])  # fp32 accumulation of the residual-stream gradient
+        del dh2
+        dWout, dbout = _wgrad(dmsg2, m), _bgrad(dmsg2)
+        dm = torch.mm(dmsg2, Wout)
+        dq_, dk_, dvv = _attend_bwd(qk, qk, vv, m, lse2, dm, sizes, H, cross=True)
+        dqk = dq_.add_(dk_)  # the shared to_qk projection is query in one direction and key in the other
+        dWqk, dbqk = _wgrad(dqk, x1_16), _bgrad(dqk)
+        dWv, dbv = _wgrad(dvv, x1_16), _bgrad(dvv)
+        dx1.add_(torch.mm(dqk, Wqk))
+        dx1.add_(torch.mm(dvv, Wv))
+        # ---- self block
+        dy = dx1.to(cdt)
+        dW3, db3 = _wgrad(dy, g), _bgrad(dy)
+        dg = torch.mm(dy, W3)
+        dh, dg1, dbe1 = ops.ln_gelu_bwd(dg, h, g1, be1, mean1, rstd1)
+        del dg
+        db0 = _bgrad(dh)
+        dW0 = torch.cat([_wgrad(dh, x16), _wgrad(dh, msg)], 1)
+        dmsg = torch.mm(dh, W0[:, D:])
+        dx0 = dx1.add_(torch.mm(dh, W0[:, :D]))
+        del dh
+        dWo, dbo = _wgrad(dmsg, att), _bgrad(dmsg)
+        datt = torch.mm(dmsg, Wo)
+        dq, dk, dv = _attend_bwd(q, k, v, att, lse1, datt, sizes, H, cross=False)
+        dqkv, dtheta = ops.rope_bwd(dq, dk, dv, q, k, theta, H)
+        dWqkv, dbqkv = _wgrad(dqkv, x16), _bgrad(dqkv)
+        dx0.add_(torch.mm(dqkv, Wqkv))
+        grads = (dWqkv, dbqkv, dWo, dbo, dW0, db0, dg1, dbe1, dW3, db3,
+                 dWqk, dbqk, dWv, dbv, dWout, dbout, dW0c, db0c, dg2, dbe2, dW3c, db3c)
+        return (dx0, dtheta, None, None, None, None, None) + grads
+
+
+class HeadFn(torch.autograd.Function):
+    """x [T, D] fp32 (tokens of both images) -> per-pair NLL of this layer's assignment
+    (+ detached nll_pos / nll_neg and the row / column argmax including the dustbin)."""
+
+    @staticmethod
+    def forward(ctx, x, sizes, cdt, gt, bal, wfp, bfp, Wfp_p, bfp_p, wm, bm):
+        B, M, N = sizes
+        D = x.shape[1]
+        t0 = B * M
+        x = x.contiguous()
+        _, x16 = ops.residual_add_cast(x, None, cdt)
+        md = torch.addmm(bfp, x16, wfp.t())  # final_proj, un-scaled; d^-1/2 is folded into sim
+        md0, md1 = md[:t0].view(B, M, D), md[t0:].view(B, N, D)
+        alpha = float(D) ** -0.5
+        if cdt == torch.bfloat16:
+            sim = ops.gemm_bf16(md0, md1, alpha=alpha)
+        else:
+            sim = torch.bmm(md0, md1.transpose(1, 2)).mul_(alpha)
+        z = torch.mv(x, wm.view(-1)).add_(bm)  # matchability logits (fp32)
+        ls = F.logsigmoid(z)
+        du = ls - z  # log sigmoid(-z)
+        ls0, ls1, du0, du1 = ls[:t0].view(B, M), ls[t0:].view(B, N), du[:t0].view(B, M), du[t0:].view(B, N)
+        st = ops.assign_stats(sim, ls0, ls1, du0, du1, gt_u8=gt["u8"], dense=False)
+        pos = st["pos_row_sum"].sum(1) + (gt["rowcnt"] * ls0).sum(1) + (gt["colcnt"] * ls1).sum(1)
+        nll_pos = -pos / gt["num_pos"]
+        nll_neg = -((gt["neg0"] * du0).sum(1) + (gt["neg1"] * du1).sum(1)) / gt["num_neg"]
+        nll = bal * nll_pos + (1 - bal) * nll_neg
+        arg0 = torch.where(du0 > st["rowmax"], torch.full_like(st["rowarg"], N), st["rowarg"])
+        arg1 = torch.where(du1 > st["colmax"], torch.full_like(st["colarg"], M), st["colarg"])
+        ctx.save_for_backward(x, x16, md, sim, st["lse_row"], st["lse_col"], z, wfp, wm, gt["u8"], gt["rowcnt"],
+                              gt["colcnt"], gt["neg0"], gt["neg1"], gt["num_pos"], gt["num_neg"])
+        ctx.meta = (sizes, cdt, bal, alpha)
+        for t in (nll_pos, nll_neg, arg0, arg1):
+            ctx.mark_non_differentiable(t)
+        return nll, nll_pos, nll_neg, arg0, arg1
+
+    @staticmethod
+    def backward(ctx, g, *_):
+        (x, x16, md, sim, lse_row, lse_col, z, wfp, wm, gt_u8, rowcnt, colcnt, neg0, neg1, num_pos,
+         num_neg) = ctx.saved_tensors
+        (B, M, N), cdt, bal, alpha = ctx.meta
+        D = x.shape[1]
+        t0 = B * M
+        g = g.float()
+        gpos = (-bal) * g / num_pos            # d nll / d (sum_P scores)
+        gneg = -(1 - bal) * g / num_neg        # d nll / d (sum of dustbin scores)
+        # matchability: d logsig(z) = sigmoid(-z), d logsig(-z) = -sigmoid(z)
+        s = torch.sigmoid(z)
+        s0, s1 = s[:t0].view(B, M), s[t0:].view(B, N)
+        dz = torch.cat([(gpos[:, None] * rowcnt * (1 - s0) - gneg[:, None] * neg0 * s0).reshape(-1),
+                        (gpos[:, None] * colcnt * (1 - s1) - gneg[:, None] * neg1 * s1).reshape(-1)])
+        # similarity: dsim = gc (2 gt - softmax_row * rowcnt - softmax_col * colcnt), gc includes d^-1/2
+        gc = (gpos * alpha).contiguous()
+        a_row, a_col = (gc[:, None] * rowcnt).contiguous(), (gc[:, None] * colcnt).contiguous()
+        tc = cdt == torch.bfloat16 and N % 8 == 0 and M % 8 == 0
+        dsim = torch.empty(B, M, N, device=x.device, dtype=torch.bfloat16 if tc else torch.float32)
+        ops.call("lgb200_assign_bwd", ops.ptr(sim), ops.ptr(lse_row), ops.ptr(lse_col), ops.ptr(gt_u8), ops.ptr(gc),
+                 ops.ptr(a_row), ops.ptr(a_col), ops.ptr(dsim), ops._code(dsim.dtype), B, M, N, ops.stream_ptr())
+        md0, md1 = md[:t0].view(B, M, D), md[t0:].view(B, N, D)
+        if tc:
+            dmd0 = ops.gemm_bf16(dsim, md1, a_mn_major=False, b_mn_major=True, out_dtype=cdt)  # dsim   md1
+            dmd1 = ops.gemm_bf16(dsim, md0, a_mn_major=True, b_mn_major=True, out_dtype=cdt)   # dsim^T md0
+        else:
+            dmd0 = torch.bmm(dsim, md1.float()).to(cdt)
+            dmd1 = torch.bmm(dsim.transpose(1, 2), md0.float()).to(cdt)
+        dmd = torch.cat([dmd0.reshape(t0, D), dmd1.reshape(B * N, D)], 0)
+        dWfp, dbfp = _wgrad(dmd, x16), _bgrad(dmd)
+        dx = torch.mm(dmd, wfp).float()
+        dx.addr_(dz, wm.view(-1))
+        dwm = torch.mv(x.t(), dz).view(1, -1)
+        dbm = dz.sum().view(1)
+        return dx, None, None, None, None, None, None, dWfp, dbfp, dwm, dbm

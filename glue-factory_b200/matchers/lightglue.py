@@ -31,7 +31,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .. import _lib, ops
+from .. import _lib, engine, ops
 
 
 class _Conf(dict):
@@ -151,6 +151,7 @@ class LightGlue(nn.Module):
         "weights_from_version": "v0.1_arxiv",
         "loss": {"gamma": 1.0, "fn": "nll", "nll_balancing": 0.5},
         "precision": "bf16",
+        "engine": "fused",  # "fused": hand-scheduled layer/head nodes (engine.py); "autograd": op-by-op cross-check
     }
     required_data_keys = ["keypoints0", "keypoints1", "descriptors0", "descriptors1"]
 
@@ -158,6 +159,7 @@ class LightGlue(nn.Module):
         super().__init__()
         self.conf = conf = _Conf(_merge(self.default_conf, _to_plain(conf)))
         assert conf.precision in ("bf16", "fp32"), conf.precision
+        assert conf.engine in ("fused", "autograd"), conf.engine
         d, h, n = conf.descriptor_dim, conf.num_heads, conf.n_layers
         assert d % h == 0 and d // h == 64, "the lgb200 kernels are built for head_dim 64"
         if conf.add_scale_ori:
@@ -181,6 +183,32 @@ class LightGlue(nn.Module):
     @property
     def _bf16(self):
         return self.conf.precision == "bf16"
+
+    @property
+    def _cdt(self):
+        return torch.bfloat16 if self._bf16 else torch.float32
+
+    def _refresh_shadow(self):
+        """Compute-dtype copies of the weights, refreshed once per forward.  With a flat parameter buffer
+        (trainer.FlatParams) this is ONE cast kernel over the whole buffer; otherwise one cast per tensor."""
+        if not self._bf16:
+            self._shadow = {n: p.detach() for n, p in self.named_parameters()}
+            return
+        fp = getattr(self, "_b200_flat", None)
+        if fp is not None:
+            self._shadow = fp.shadow_bf16()
+        else:
+            self._shadow = {n: p.detach().to(torch.bfloat16) for n, p in self.named_parameters()}
+
+    def _layer_weights(self, i):
+        pre = f"transformers.{i}."
+        w, params = [], []
+        named = dict(self.transformers[i].named_parameters())
+        for slot, name in enumerate(engine.LAYER_PARAMS):
+            p = named[name]
+            params.append(p)
+            w.append(p.detach() if slot in engine._LN_SLOTS else self._shadow[pre + name])
+        return w, params
 
     def _lin(self, x, layer):
         """nn.Linear through cuBLAS; bf16 operands in bf16 mode (fp32 accumulate inside cuBLAS)."""
@@ -265,11 +293,20 @@ class LightGlue(nn.Module):
         kp = torch.cat([kpts0.reshape(B * M, 2), kpts1.reshape(B * N, 2)], 0)
         theta = F.linear(kp, self.posenc.Wr.weight.float()).contiguous()
         sizes = (B, M, N)
-        all0, all1 = [], []
+        all0, all1, layers_x = [], [], []
         L = conf.n_layers
+        fused = conf.engine == "fused"
+        if fused:
+            self._refresh_shadow()
         for i in range(L):
-            x = self._layer(x, theta, self.transformers[i], sizes)
+            if fused:
+                w, params = self._layer_weights(i)
+                x = engine.LayerFn.apply(x, theta, sizes, conf.num_heads, self._cdt, self.transformers[i].self_attn.ffn[1].eps,
+                                         w, *params)
+            else:
+                x = self._layer(x, theta, self.transformers[i], sizes)
             if self.training or i == L - 1:
+                layers_x.append(x)
                 all0.append(x[: B * M].view(B, M, D))
                 all1.append(x[B * M:].view(B, N, D))
         d0, d1 = all0[-1], all1[-1]
@@ -290,6 +327,11 @@ class LightGlue(nn.Module):
             "prune0": torch.ones_like(ms0) * L,
             "prune1": torch.ones_like(ms1) * L,
         }
+        if fused:
+            # private side channel for loss(): the per-layer token tensors (both images, [T, D]); avoids
+            # slicing the stacked ref_descriptors (whose backward would scatter into 9 zero-filled stacks)
+            pred["_b200_layers"] = layers_x
+            pred["_b200_sizes"] = sizes
         return pred
 
     # ------------------------------------------------------------------------------------------
@@ -327,6 +369,18 @@ class LightGlue(nn.Module):
             arg0 = self._argmax_with_dustbin(rmax, rarg, du0.detach(), N)
             arg1 = self._argmax_with_dustbin(cmax, carg, du1.detach(), M)
             return nll, nll_pos, nll_neg, arg0, arg1
+
+        layers_x = pred.get("_b200_layers") if conf.engine == "fused" else None
+        if layers_x is not None and len(layers_x) == L:
+            gtd = {"u8": gt_u8, "rowcnt": rowcnt, "colcnt": colcnt, "neg0": neg0, "neg1": neg1, "num_pos": num_pos,
+                   "num_neg": num_neg0 + num_neg1}
+
+            def head(i):  # noqa: F811  (hand-scheduled head, engine.HeadFn)
+                la_i = self.log_assignment[i]
+                pre = f"log_assignment.{i}.final_proj."
+                return engine.HeadFn.apply(layers_x[i], (B, M, N), self._cdt, gtd, bal, self._shadow[pre + "weight"],
+                                           self._shadow[pre + "bias"], la_i.final_proj.weight, la_i.final_proj.bias,
+                                           la_i.matchability.weight, la_i.matchability.bias)
 
         nll, nll_pos, nll_neg, _, _ = head(L - 1)
         losses = {

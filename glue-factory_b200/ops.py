@@ -32,17 +32,34 @@ def _chk(t, dtype=None):
 # ------------------------------------------------------------------------------------------------
 # rotary split (lightglue.py:157-160)
 # ------------------------------------------------------------------------------------------------
+def rope_fwd(qkv, theta, H):
+    _chk(qkv)
+    _chk(theta, torch.float32)
+    T = qkv.shape[0]
+    q = torch.empty(T, H * 64, device=qkv.device, dtype=qkv.dtype)
+    k, v = torch.empty_like(q), torch.empty_like(q)
+    call("lgb200_rope_split_fwd", ptr(qkv), ptr(theta), ptr(q), ptr(k), ptr(v), T, H, _code(qkv.dtype), stream_ptr())
+    return q, k, v
+
+
+def rope_bwd(dq, dk, dv, q, k, theta, H, dtheta=None):
+    """Returns dqkv; ACCUMULATES into dtheta (allocated zeroed when None)."""
+    T = q.shape[0]
+    dq, dk, dv = (g.contiguous() for g in (dq, dk, dv))
+    dqkv = torch.empty(T, H * 192, device=q.device, dtype=q.dtype)
+    if dtheta is None:
+        dtheta = torch.zeros_like(theta)
+    call("lgb200_rope_split_bwd", ptr(dq), ptr(dk), ptr(dv), ptr(q), ptr(k), ptr(theta), ptr(dqkv), ptr(dtheta),
+         T, H, _code(q.dtype), stream_ptr())
+    return dqkv, dtheta
+
+
 class RopeSplit(torch.autograd.Function):
     """qkv [T, H*192] (interleaved) , theta [T, 32] -> rotated q, rotated k, v  each [T, H*64]."""
 
     @staticmethod
     def forward(ctx, qkv, theta, H):
-        _chk(qkv)
-        _chk(theta, torch.float32)
-        T = qkv.shape[0]
-        q = torch.empty(T, H * 64, device=qkv.device, dtype=qkv.dtype)
-        k, v = torch.empty_like(q), torch.empty_like(q)
-        call("lgb200_rope_split_fwd", ptr(qkv), ptr(theta), ptr(q), ptr(k), ptr(v), T, H, _code(qkv.dtype), stream_ptr())
+        q, k, v = rope_fwd(qkv, theta, H)
         ctx.save_for_backward(q, k, theta)
         ctx.H = H
         return q, k, v
@@ -50,32 +67,43 @@ class RopeSplit(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dq, dk, dv):
         q, k, theta = ctx.saved_tensors
-        T, H = q.shape[0], ctx.H
-        dq, dk, dv = (g.contiguous() for g in (dq, dk, dv))
-        dqkv = torch.empty(T, H * 192, device=q.device, dtype=q.dtype)
-        dtheta = torch.zeros_like(theta)
-        call("lgb200_rope_split_bwd", ptr(dq), ptr(dk), ptr(dv), ptr(q), ptr(k), ptr(theta), ptr(dqkv), ptr(dtheta),
-             T, H, _code(q.dtype), stream_ptr())
+        dqkv, dtheta = rope_bwd(dq, dk, dv, q, k, theta, ctx.H)
         return dqkv, dtheta, None
 
 
 # ------------------------------------------------------------------------------------------------
 # attention (lightglue.py:118-121, 207-216)
 # ------------------------------------------------------------------------------------------------
+def attn_fwd(q, k, v, kv_shift, scale):
+    _chk(q), _chk(k), _chk(v)
+    B, Nq, H, D = q.shape
+    Nk = k.shape[1]
+    assert D == 64, "head_dim must be 64"
+    out = torch.empty_like(q)
+    lse = torch.empty(B, H, Nq, device=q.device, dtype=torch.float32)
+    call("lgb200_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, Nq, Nk, H, kv_shift, float(scale),
+         _code(q.dtype), stream_ptr())
+    return out, lse
+
+
+def attn_bwd(q, k, v, out, lse, dout, kv_shift, scale):
+    B, Nq, H, _ = q.shape
+    Nk = k.shape[1]
+    dout = dout.contiguous()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    delta = torch.empty(B, H, Nq, device=q.device, dtype=torch.float32)
+    call("lgb200_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(dout), ptr(dq), ptr(dk), ptr(dv),
+         ptr(delta), B, Nq, Nk, H, kv_shift, float(scale), _code(q.dtype), stream_ptr())
+    return dq, dk, dv
+
+
 class Attention(torch.autograd.Function):
     """q [B,Nq,H,64], k,v [B,Nk,H,64] -> softmax(q k^T / 8) v, keys of batch b taken from batch
     (b + kv_shift) % B."""
 
     @staticmethod
     def forward(ctx, q, k, v, kv_shift, scale):
-        _chk(q), _chk(k), _chk(v)
-        B, Nq, H, D = q.shape
-        Nk = k.shape[1]
-        assert D == 64, "head_dim must be 64"
-        out = torch.empty_like(q)
-        lse = torch.empty(B, H, Nq, device=q.device, dtype=torch.float32)
-        call("lgb200_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, Nq, Nk, H, kv_shift, float(scale),
-             _code(q.dtype), stream_ptr())
+        out, lse = attn_fwd(q, k, v, kv_shift, scale)
         ctx.save_for_backward(q, k, v, out, lse)
         ctx.meta = (kv_shift, float(scale))
         return out
@@ -84,51 +112,64 @@ class Attention(torch.autograd.Function):
     def backward(ctx, dout):
         q, k, v, out, lse = ctx.saved_tensors
         kv_shift, scale = ctx.meta
-        B, Nq, H, _ = q.shape
-        Nk = k.shape[1]
-        dout = dout.contiguous()
-        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        delta = torch.empty(B, H, Nq, device=q.device, dtype=torch.float32)
-        call("lgb200_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(dout), ptr(dq), ptr(dk), ptr(dv),
-             ptr(delta), B, Nq, Nk, H, kv_shift, scale, _code(q.dtype), stream_ptr())
+        dq, dk, dv = attn_bwd(q, k, v, out, lse, dout, kv_shift, scale)
         return dq, dk, dv, None, None
 
 
 # ------------------------------------------------------------------------------------------------
 # LayerNorm + GELU (lightglue.py:143-148)
 # ------------------------------------------------------------------------------------------------
+def ln_gelu_fwd(x, g, b, eps):
+    """g, b fp32 contiguous. Returns y, mean, rstd."""
+    _chk(x)
+    T, W = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(T, device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    call("lgb200_ln_gelu_fwd", ptr(x), ptr(g), ptr(b), ptr(y), ptr(mean), ptr(rstd), T, W, float(eps),
+         _code(x.dtype), stream_ptr())
+    return y, mean, rstd
+
+
+def ln_gelu_bwd(dy, x, g, b, mean, rstd):
+    T, W = x.shape
+    dy = dy.contiguous()
+    dx = torch.empty_like(x)
+    parts = _lib.load().lgb200_ln_gelu_bwd_parts(T)
+    dg = torch.empty(parts, W, device=x.device, dtype=torch.float32)
+    db = torch.empty_like(dg)
+    call("lgb200_ln_gelu_bwd", ptr(dy), ptr(x), ptr(g), ptr(b), ptr(mean), ptr(rstd), ptr(dx), ptr(dg), ptr(db),
+         T, W, _code(x.dtype), stream_ptr())
+    return dx, dg.sum(0), db.sum(0)
+
+
 class LnGelu(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps):
-        _chk(x)
         g, b = gamma.float().contiguous(), beta.float().contiguous()
-        T, W = x.shape
-        y = torch.empty_like(x)
-        mean = torch.empty(T, device=x.device, dtype=torch.float32)
-        rstd = torch.empty_like(mean)
-        call("lgb200_ln_gelu_fwd", ptr(x), ptr(g), ptr(b), ptr(y), ptr(mean), ptr(rstd), T, W, float(eps),
-             _code(x.dtype), stream_ptr())
+        y, mean, rstd = ln_gelu_fwd(x, g, b, eps)
         ctx.save_for_backward(x, g, b, mean, rstd)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, g, b, mean, rstd = ctx.saved_tensors
-        T, W = x.shape
-        dy = dy.contiguous()
-        dx = torch.empty_like(x)
-        parts = _lib.load().lgb200_ln_gelu_bwd_parts(T)
-        dg = torch.empty(parts, W, device=x.device, dtype=torch.float32)
-        db = torch.empty_like(dg)
-        call("lgb200_ln_gelu_bwd", ptr(dy), ptr(x), ptr(g), ptr(b), ptr(mean), ptr(rstd), ptr(dx), ptr(dg), ptr(db),
-             T, W, _code(x.dtype), stream_ptr())
-        return dx, dg.sum(0), db.sum(0), None
+        dx, dg, db = ln_gelu_bwd(dy, *ctx.saved_tensors)
+        return dx, dg, db, None
+
+
+def residual_add_cast(x, y, cdt, want_sum=True):
+    """x fp32 [.., D] + y (compute dtype or None) -> (x_new fp32 or None, cast(x_new) in cdt)."""
+    _chk(x, torch.float32)
+    xo = torch.empty_like(x) if (want_sum and y is not None) else None
+    xc = torch.empty(x.shape, device=x.device, dtype=cdt)
+    call("lgb200_residual_add_cast", ptr(x), ptr(y), ptr(xo), ptr(xc), x.numel(), _code(cdt), stream_ptr())
+    return (xo if xo is not None else x), xc
 
 
 # ------------------------------------------------------------------------------------------------
 # batched GEMM on tcgen05 (lightglue.py:283)
 # ------------------------------------------------------------------------------------------------
-def gemm_bf16(a, b, a_mn_major=False, b_mn_major=False, out_dtype=torch.float32):
+def gemm_bf16(a, b, a_mn_major=False, b_mn_major=False, out_dtype=torch.float32, alpha=1.0):
     """C[i] = opA(a[i]) @ opB(b[i])^T-style contraction on the tensor cores (see lgb200.h).
     a: [batch, M, K] (or [batch, K, M] when a_mn_major); b: [batch, N, K] (or [batch, K, N])."""
     _chk(a, torch.bfloat16), _chk(b, torch.bfloat16)
@@ -139,7 +180,7 @@ def gemm_bf16(a, b, a_mn_major=False, b_mn_major=False, out_dtype=torch.float32)
     c = torch.empty(batch, M, N, device=a.device, dtype=out_dtype)
     call("lgb200_gemm_bf16", ptr(a), ptr(b), ptr(c), batch, M, N, K, int(a_mn_major), int(b_mn_major),
          a.shape[2], b.shape[2], N, a.shape[1] * a.shape[2], b.shape[1] * b.shape[2], M * N, _code(out_dtype),
-         stream_ptr())
+         float(alpha), stream_ptr())
     return c
 
 

@@ -43,6 +43,20 @@ class FlatParams:
             self.flat[off:off + p.numel()].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + p.numel()].view_as(p)
             p.grad = self.grad[off:off + p.numel()].view_as(p)
+        # bf16 shadow of the whole buffer (one cast kernel per step) for the tensor-core GEMMs
+        self._names = {id(p): n for n, p in module.named_parameters()}
+        self.flat16 = None
+        self._views16 = None
+        module._b200_flat = self
+
+    def shadow_bf16(self):
+        """name -> bf16 view of the parameter, refreshed from the fp32 master copy by ONE cast kernel."""
+        if self.flat16 is None:
+            self.flat16 = torch.empty(self.numel, device=self.flat.device, dtype=torch.bfloat16)
+            self._views16 = {self._names[id(p)]: self.flat16[off:off + p.numel()].view_as(p)
+                             for p, off in zip(self.params, self.offsets)}
+        ops.call("lgb200_cast_bf16", ops.ptr(self.flat), ops.ptr(self.flat16), self.numel, ops.stream_ptr())
+        return self._views16
 
     def zero_grad(self):
         self.grad.zero_()

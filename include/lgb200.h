@@ -90,10 +90,11 @@ int lgb200_ln_gelu_bwd(const void* dy, const void* x, const float* gamma, const 
  * contractions.  C[b] (M x N) = opA(A[b]) * opB(B[b]):
  *   a_mn_major = 0: A is [M,K] row-major (lda);  1: A is stored [K,M] row-major (lda)
  *   b_mn_major = 0: B is [N,K] row-major (ldb);  1: B is stored [K,N] row-major (ldb)
- * lda/ldb in elements, multiples of 8; base pointers 16-byte aligned; C row-major with ldc.      */
+ * lda/ldb in elements, multiples of 8; base pointers 16-byte aligned; C row-major with ldc;
+ * the result is scaled by alpha in the epilogue (the d^-1/2 of lightglue.py:282).                  */
 int lgb200_gemm_bf16(const void* A, const void* B, void* C, int batch, int M, int N, int K, int a_mn_major,
                      int b_mn_major, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
-                     int64_t strideC, int c_dtype, cudaStream_t stream);
+                     int64_t strideC, int c_dtype, float alpha, cudaStream_t stream);
 
 /* ---- assignment head: sigmoid_log_double_softmax + NLL terms + argmax --------------------------------
  * replaces lightglue.py:256-268 (two log_softmax, transposed copy, slice assignment),
@@ -138,6 +139,10 @@ int lgb200_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, co
                      float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
                      float grad_scale, cudaStream_t stream);
 int lgb200_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream);
+/* residual update of the fp32 stream fused with the cast for the next GEMM (lightglue.py:163, 219-220):
+ * x_out = x + y (y in `dtype`, may be NULL), x_cast = (dtype) x_out; either output may be NULL.   */
+int lgb200_residual_add_cast(const float* x, const void* y, float* x_out, void* x_cast, int64_t n, int dtype,
+                             cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -21,8 +21,8 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _build(conf, weights, precision):
-    model = LightGlue(dict(conf, precision=precision))
+def _build(conf, weights, precision, engine="fused"):
+    model = LightGlue(dict(conf, precision=precision, engine=engine))
     missing, unexpected = model.load_state_dict({k: v.float() for k, v in weights.items()}, strict=False)
     assert not unexpected and missing in ([], ["confidence_thresholds"])
     return model.to(DEV).train()
@@ -33,10 +33,11 @@ def _f32(data):
                                     (v.float() if v.is_floating_point() else v)) for k, v in data.items()}, DEV)
 
 
+@pytest.mark.parametrize("engine", ["fused", "autograd"])
 @pytest.mark.parametrize("name", CASES[:4])
-def test_fp32_path_matches_reference_golden(name):
+def test_fp32_path_matches_reference_golden(name, engine):
     g, conf, w, data = load_case(name)
-    model = _build(conf, w, "fp32")
+    model = _build(conf, w, "fp32", engine)
     d = _f32(data)
     pred = model(d)
     losses, _ = model.loss(pred, d)
@@ -163,3 +164,28 @@ def test_cuda_graph_step_matches_eager_step():
     p_graph, l_graph = run(True)
     np.testing.assert_allclose(l_graph, l_eager, rtol=1e-5)
     assert rel_err(p_graph, p_eager) < 1e-5
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("M,N", [(192, 192), (150, 203)])
+def test_fused_engine_matches_autograd_engine(precision, tol, M, N):
+    """The hand-scheduled layer/head nodes (engine.py) and the op-by-op autograd composition are two
+    independent implementations of the same backward; they must agree."""
+    conf = dict(synthetic.DEFAULT_CONF, n_layers=2)
+    w = synthetic.make_weights(conf, seed=61)
+    d = synthetic.to_device(synthetic.make_pairs(2, N, seed=62, M=M), DEV)
+    out = {}
+    for engine in ("fused", "autograd"):
+        model = _build(conf, w, precision, engine)
+        pred = model(d)
+        losses, _ = model.loss(pred, d)
+        losses["total"].mean().backward()
+        out[engine] = (pred, losses, {k: p.grad.clone() for k, p in model.named_parameters()})
+    pa, la, ga = out["autograd"]
+    pf, lf, gf = out["fused"]
+    assert rel_err(pf["log_assignment"], pa["log_assignment"]) < tol
+    for k in la:
+        if torch.is_tensor(la[k]):
+            assert rel_err(lf[k], la[k]) < tol, k
+    for k in ga:
+        assert rel_err(gf[k], ga[k]) < (tol if precision == "fp32" else 0.1), k
