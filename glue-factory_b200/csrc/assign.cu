@@ -133,12 +133,21 @@ __global__ void assign_col_lse_merge_kernel(const float* __restrict__ colpart_m,
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N) return;
-  float m = kNegInf, s = 0.f;
-  for (int st = 0; st < nstrips; ++st) {
-    const int64_t o = ((int64_t)b * nstrips + st) * N + j;
-    lse_merge(m, s, colpart_m[o], colpart_s[o]);
+  const float* pm = colpart_m + (int64_t)b * nstrips * N + j;
+  const float* ps = colpart_s + (int64_t)b * nstrips * N + j;
+  float m = kNegInf;
+  for (int st = 0; st < nstrips; ++st) m = fmaxf(m, pm[(int64_t)st * N]);
+  const float ref = (m == kNegInf) ? 0.f : m;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int st = 0;
+  for (; st + 4 <= nstrips; st += 4) {
+    s0 += ps[(int64_t)(st + 0) * N] * __expf(pm[(int64_t)(st + 0) * N] - ref);
+    s1 += ps[(int64_t)(st + 1) * N] * __expf(pm[(int64_t)(st + 1) * N] - ref);
+    s2 += ps[(int64_t)(st + 2) * N] * __expf(pm[(int64_t)(st + 2) * N] - ref);
+    s3 += ps[(int64_t)(st + 3) * N] * __expf(pm[(int64_t)(st + 3) * N] - ref);
   }
-  lse_col[(int64_t)b * N + j] = m + logf(s);
+  for (; st < nstrips; ++st) s0 += ps[(int64_t)st * N] * __expf(pm[(int64_t)st * N] - ref);
+  lse_col[(int64_t)b * N + j] = m + logf((s0 + s1) + (s2 + s3));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -412,7 +421,7 @@ int lgb200_assign_lse(const float* sim, float* lse_row, float* lse_col, void* ws
   float* pm = static_cast<float*>(ws);
   float* ps = pm + (size_t)B * nstrips * N;
   assign_lse_kernel<<<dim3(nstrips, B), 256, 0, stream>>>(sim, lse_row, pm, ps, M, N, nstrips);
-  assign_col_lse_merge_kernel<<<dim3((N + 127) / 128, B), 128, 0, stream>>>(pm, ps, lse_col, N, nstrips);
+  assign_col_lse_merge_kernel<<<dim3((N + 63) / 64, B), 64, 0, stream>>>(pm, ps, lse_col, N, nstrips);
   return check_launch("assign_lse");
 }
 

@@ -338,6 +338,44 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// column sums of a tall [rows, cols] matrix (bias gradients): block = 32 row-lanes x 8 column-vectors
+// (8 elements = one 128-bit load for bf16), row slabs across blockIdx.y, deterministic two-stage sum.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ a, float* __restrict__ part,
+                                                            int64_t rows, int cols, int rows_per_slab) {
+  __shared__ float s_red[32][65];
+  const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
+  const int col0 = blockIdx.x * 64 + cx * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab;
+  const int64_t r1 = min(rows, r0 + rows_per_slab);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col0 < cols) {
+    for (int64_t r = r0 + ry; r < r1; r += 32) {
+      Vec8<T> v = Vec8<T>::load(a + r * cols + col0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v.v[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s_red[ry][cx * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += s_red[r][threadIdx.x];
+    part[(int64_t)blockIdx.y * cols + blockIdx.x * 64 + threadIdx.x] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int cols, int nslabs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float t = 0.f;
+  for (int sidx = 0; sidx < nslabs; ++sidx) t += part[(int64_t)sidx * cols + c];
+  out[c] = t;
+}
+
 // x_out = x + y (fp32 residual stream) and its compute-dtype copy for the next GEMM, in one pass
 template <typename T>
 __global__ void __launch_bounds__(256) residual_add_cast_kernel(const float* __restrict__ x, const T* __restrict__ y,
@@ -370,6 +408,30 @@ __global__ void __launch_bounds__(256) residual_add_cast_kernel(const float* __r
 using namespace lgb;
 
 extern "C" {
+
+int lgb200_colsum_slabs(int64_t rows, int cols) {
+  const int cb = (cols + 63) / 64;
+  int64_t want = (2 * 148 + cb - 1) / cb;           // ~2 CTAs per SM in total
+  int64_t maxs = (rows + 255) / 256;                // at least 256 rows per slab
+  int64_t n = want < maxs ? want : maxs;
+  return (int)(n < 1 ? 1 : n);
+}
+
+int lgb200_colsum(const void* a, float* out, float* ws, int64_t rows, int cols, int dtype, cudaStream_t stream) {
+  LGB_REQUIRE(a && out && ws && rows > 0 && cols > 0, kErrInvalid, "colsum: bad arguments");
+  LGB_REQUIRE(cols % 8 == 0, kErrInvalid, "colsum: cols must be a multiple of 8");
+  const int nslabs = lgb200_colsum_slabs(rows, cols);
+  const int rps = (int)((rows + nslabs - 1) / nslabs);
+  dim3 grid((cols + 63) / 64, nslabs);
+  if (dtype == LGB200_F32)
+    colsum_partial_kernel<float><<<grid, 256, 0, stream>>>((const float*)a, ws, rows, cols, rps);
+  else if (dtype == LGB200_BF16)
+    colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)a, ws, rows, cols, rps);
+  else
+    LGB_REQUIRE(false, kErrInvalid, "colsum: bad dtype %d", dtype);
+  colsum_final_kernel<<<(cols + 127) / 128, 128, 0, stream>>>(ws, out, cols, nslabs);
+  return check_launch("colsum");
+}
 
 int lgb200_residual_add_cast(const float* x, const void* y, float* x_out, void* x_cast, int64_t n, int dtype,
                              cudaStream_t stream) {

@@ -36,7 +36,7 @@ def _wgrad(dy, a):
 
 
 def _bgrad(dy):
-    return dy.sum(0, dtype=torch.float32)
+    return ops.colsum(dy)
 
 
 def _attend_fwd(q, k, v, sizes, H, cross):

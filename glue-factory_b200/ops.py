@@ -157,6 +157,18 @@ class LnGelu(torch.autograd.Function):
         return dx, dg, db, None
 
 
+def colsum(a):
+    """[rows, cols] (fp32 / bf16) -> fp32 [cols] column sums (bias gradients)."""
+    _chk(a)
+    rows, cols = a.shape
+    if cols % 8:
+        return a.sum(0, dtype=torch.float32)
+    out = torch.empty(cols, device=a.device, dtype=torch.float32)
+    ws = torch.empty(_lib.load().lgb200_colsum_slabs(rows, cols) * cols, device=a.device, dtype=torch.float32)
+    call("lgb200_colsum", ptr(a), ptr(out), ptr(ws), rows, cols, _code(a.dtype), stream_ptr())
+    return out
+
+
 def residual_add_cast(x, y, cdt, want_sum=True):
     """x fp32 [.., D] + y (compute dtype or None) -> (x_new fp32 or None, cast(x_new) in cdt)."""
     _chk(x, torch.float32)

@@ -47,6 +47,7 @@ class FlatParams:
         self._names = {id(p): n for n, p in module.named_parameters()}
         self.flat16 = None
         self._views16 = None
+        self.grad_views = [self.grad[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
         module._b200_flat = self
 
     def shadow_bf16(self):
@@ -59,10 +60,20 @@ class FlatParams:
         return self._views16
 
     def zero_grad(self):
-        self.grad.zero_()
-        for p, off in zip(self.params, self.offsets):  # re-attach in case something detached the views
-            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + off * 4:
-                p.grad = self.grad[off:off + p.numel()].view_as(p)
+        """Detach the .grad views: autograd then hands each freshly computed gradient over by reference
+        (no per-parameter accumulate kernel); `gather_grads` packs them into the flat buffer."""
+        for p in self.params:
+            p.grad = None
+
+    def gather_grads(self):
+        have = [(v, p.grad) for v, p in zip(self.grad_views, self.params) if p.grad is not None]
+        missing = [v for v, p in zip(self.grad_views, self.params) if p.grad is None]
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        if missing:
+            torch._foreach_zero_(missing)
+        for p, v in zip(self.params, self.grad_views):
+            p.grad = v
 
 
 class MatcherTrainer:
@@ -119,6 +130,7 @@ class MatcherTrainer:
         losses, _ = self.model.loss(pred, data)
         loss = losses["total"].mean()
         loss.backward()
+        self.fp.gather_grads()
         self.exchange_gradients()
         if graphed:
             # the bias-correction terms depend on the step count, which must not be baked into the graph:

@@ -132,6 +132,11 @@ int lgb200_log_double_softmax(const float* sim, float bin_score, float* scores, 
 int lgb200_sinkhorn(const float* sim, float alpha, int iters, float* out, void* ws, int B, int M, int N,
                     cudaStream_t stream);
 
+/* column sums of a tall [rows, cols] matrix = bias gradient of an nn.Linear (autograd of lightglue.py:156 etc.).
+ * ws: lgb200_colsum_slabs(rows, cols) * cols floats of scratch; cols % 8 == 0.                       */
+int lgb200_colsum_slabs(int64_t rows, int cols);
+int lgb200_colsum(const void* a, float* out, float* ws, int64_t rows, int cols, int dtype, cudaStream_t stream);
+
 /* ---- flat-buffer optimiser (train.py:358-361, 513) and casts --------------------------------------- */
 /* step: 1-based step count for the bias correction; when step_dev != NULL the count is read from device
  * memory instead (so a CUDA graph of the whole training step can be replayed).                       */

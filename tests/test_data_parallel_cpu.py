@@ -1,7 +1,7 @@
 """CPU, world_size 2 over gloo: the flat-buffer gradient exchange (the path's one collective).
-The optimiser kernel itself is CUDA-only; here we check the host logic: parameters and gradients are
-views of the flat buffers, autograd accumulates into them in place, and one all_reduce leaves every
-rank with the sum of the per-rank gradients."""
+The optimiser kernel itself is CUDA-only; here we check the host logic: parameters are views of the flat
+buffer, the gradients autograd hands over are packed into the flat gradient buffer, and one all_reduce
+leaves every rank with the sum of the per-rank gradients."""
 import os
 
 import torch
@@ -24,8 +24,11 @@ def _worker(rank, world, port, out):
     x = torch.full((4, 8), float(rank + 1))
     tr.fp.zero_grad()
     net(x).sum().backward()
+    assert all(p.grad is not None and p.grad.data_ptr() != tr.fp.grad.data_ptr() + off * 4
+               for p, off in zip(tr.fp.params, tr.fp.offsets))  # handed over by reference, not accumulated
+    tr.fp.gather_grads()
     local = tr.fp.grad.clone()
-    # gradients landed in the flat buffer through the parameter views
+    # gradients were packed into the flat buffer and the .grad views re-attached
     for p, off in zip(tr.fp.params, tr.fp.offsets):
         assert p.grad.data_ptr() == tr.fp.grad.data_ptr() + off * 4
         assert torch.equal(p.grad.reshape(-1), tr.fp.grad[off:off + p.numel()])

@@ -200,6 +200,20 @@ def test_other_heads_match_golden():
         np.testing.assert_allclose(ops.log_optimal_transport(sim, 0.7, 50).cpu().numpy(), g[f"{tag}|lot"], atol=1e-4)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,cols", [(16384, 256), (1000, 768), (37, 8), (4096, 512)])
+def test_colsum_and_residual(dtype, rows, cols):
+    a = _rand(rows, cols, seed=1, dtype=dtype)
+    ref = a.double().sum(0)
+    assert rel_err(ops.colsum(a), ref) < 1e-5
+    x = _rand(rows, cols, seed=2)
+    xo, xc = ops.residual_add_cast(x, a, dtype)
+    assert torch.equal(xo, x + a.float())
+    assert torch.equal(xc, (x + a.float()).to(dtype))
+    _, xc2 = ops.residual_add_cast(x, None, dtype)
+    assert torch.equal(xc2, x.to(dtype))
+
+
 def test_adam_flat_matches_torch():
     n = 100_003
     p = _rand(n, seed=1)
