@@ -5,14 +5,13 @@
 // FORWARD.  One CTA = one (batch, head, 128-query tile).  Q/K/V tiles are brought in by TMA
 // (4-D tensor map over the token-major [B,N,H,64] layout, 128-byte swizzle) and consumed straight
 // from shared memory by tcgen05.mma:
-//     S (128 x 128 fp32, TMEM cols [0,128))   = Q K_j^T        4 MMAs  (M128 N128 K16)
-//     O_j (128 x 64 fp32, TMEM cols [128,192)) = P_j V_j        8 MMAs  (M128 N64  K16)
-// Warps 0-3 are the softmax warpgroup (thread == query row == TMEM lane): two sweeps over S with
-// tcgen05.ld (row max, then exp2 / row sum / bf16 pack), P_j written to shared memory in the
+//     S_j (128 x 64 fp32, TMEM, double-buffered) = Q K_j^T      4 MMAs  (M128 N64 K16)
+//     O_j (128 x 64 fp32, TMEM, double-buffered) = P_j V_j      4 MMAs  (M128 N64 K16)
+// Warps 0-3 are the softmax warpgroup (thread == query row == TMEM lane): one sweep over S_j with
+// tcgen05.ld (row max, exp2 / row sum / bf16 pack), P_j written to shared memory in the
 // K-major 128B-swizzled layout the MMA expects, O_j folded into a register accumulator with the
 // usual online-softmax rescale.  Warp 4 = TMA producer, warp 5 = MMA issuer + TMEM owner.
-// Two CTAs fit per SM (112 KiB smem, 256 TMEM columns each), so one CTA's MMAs overlap the
-// other's softmax.
+// Two CTAs fit per SM (96 KiB smem, 256 TMEM columns each).
 #include <math.h>
 
 #include "common.cuh"
@@ -21,17 +20,33 @@
 
 namespace lgb {
 
+// 32 consecutive columns [c*32, c*32+32) of a 64-column bf16 row (128 B, swizzled 16-byte chunks)
+__device__ __forceinline__ void store_row_chunk32_fwd(uint8_t* row_base, int sw, int c, const float* v) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 u;
+    u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+    u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+    const int chunk = c * 4 + g;
+    *reinterpret_cast<uint4*>(row_base + ((chunk ^ sw) << 4)) = u;
+  }
+}
+
 constexpr int FA_BM = 128;     // queries per CTA
-constexpr int FA_BN = 128;     // keys per iteration
+constexpr int FA_BN = 64;      // keys per iteration
 constexpr int FA_D = 64;
-constexpr int FA_STAGES = 2;
+constexpr int FA_STAGES = 3;
 constexpr int FA_QBYTES = FA_BM * FA_D * 2;   // 16 KiB
-constexpr int FA_KBYTES = FA_BN * FA_D * 2;   // 16 KiB
-constexpr int FA_PBYTES = FA_BM * FA_BN * 2;  // 32 KiB
-constexpr int FA_SMEM = FA_QBYTES + FA_STAGES * 2 * FA_KBYTES + FA_PBYTES + 256;
-constexpr int FA_TMEM_COLS = 256;
+constexpr int FA_KBYTES = FA_BN * FA_D * 2;   // 8 KiB
+constexpr int FA_PBYTES = FA_BM * FA_BN * 2;  // 16 KiB (one 128-byte swizzle row per query)
+constexpr int FA_SMEM = FA_QBYTES + FA_STAGES * 2 * FA_KBYTES + 2 * FA_PBYTES + 256;
+constexpr int FA_TMEM_COLS = 256;             // S0 [0,64) S1 [64,128) O0 [128,192) O1 [192,256)
 constexpr int FA_S_COL = 0, FA_O_COL = 128;
 
+// Software pipeline (per CTA):  the MMA thread keeps TWO S tiles in flight (double-buffered in TMEM) so the
+// softmax warps never wait for Q K^T; P and the per-tile O = P V are double-buffered as well, so the P V of
+// tile j runs while the softmax of tile j+1 is being computed and is folded into the register accumulator
+// one iteration later.
 __global__ void __launch_bounds__(192, 2)
     attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out,
@@ -40,15 +55,15 @@ __global__ void __launch_bounds__(192, 2)
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + FA_QBYTES;
   uint8_t* sV = sK + FA_STAGES * FA_KBYTES;
-  uint8_t* sP = sV + FA_STAGES * FA_KBYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FA_PBYTES);
+  uint8_t* sP = sV + FA_STAGES * FA_KBYTES;  // [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_PBYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;               // [FA_STAGES]
   uint64_t* kv_empty = kv_full + FA_STAGES;   // [FA_STAGES]
-  uint64_t* s_full = kv_empty + FA_STAGES;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_full = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* s_full = kv_empty + FA_STAGES;    // [2]
+  uint64_t* p_full = s_full + 2;              // [2]
+  uint64_t* o_full = p_full + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
@@ -62,9 +77,11 @@ __global__ void __launch_bounds__(192, 2)
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 4);
+      mbar_init(&o_full[s], 1);
+    }
     mbar_fence_init();
   }
   if (warp == 4 && lane == 0) {
@@ -85,8 +102,7 @@ __global__ void __launch_bounds__(192, 2)
       tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
       for (int j = 0; j < ntiles; ++j) {
         const int s = j % FA_STAGES;
-        const uint32_t ph = (j / FA_STAGES) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_wait(&kv_empty[s], ((j / FA_STAGES) & 1) ^ 1);
         mbar_expect_tx(&kv_full[s], 2 * FA_KBYTES);
         tma_load_4d(sK + s * FA_KBYTES, &tmK, &kv_full[s], 0, h, j * FA_BN, kb);
         tma_load_4d(sV + s * FA_KBYTES, &tmV, &kv_full[s], 0, h, j * FA_BN, kb);
@@ -95,8 +111,8 @@ __global__ void __launch_bounds__(192, 2)
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(FA_BM, FA_BN, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = make_idesc_bf16(FA_BM, FA_D, 0, 1);   // P (K-major) x V (MN-major)
+      constexpr uint32_t idesc_s = make_idesc_bf16(FA_BM, FA_BN, 0, 0);  // Q (K-major) x K_j (K-major)
+      constexpr uint32_t idesc_o = make_idesc_bf16(FA_BM, FA_D, 0, 1);   // P (K-major) x V_j (MN-major)
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
       auto issue_s = [&](int j) {
         const int s = j % FA_STAGES;
@@ -104,23 +120,24 @@ __global__ void __launch_bounds__(192, 2)
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16(tmem_base + FA_S_COL, make_smem_desc(aQ + kk * 32, 16, 1024),
+          umma_bf16(tmem_base + FA_S_COL + (j & 1) * FA_BN, make_smem_desc(aQ + kk * 32, 16, 1024),
                     make_smem_desc(aK + s * FA_KBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(s_full);
+        umma_commit(&s_full[j & 1]);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
+      if (ntiles > 1) issue_s(1);
       for (int j = 0; j < ntiles; ++j) {
         const int s = j % FA_STAGES;
-        mbar_wait(p_full, j & 1);
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < FA_BN / 16; ++kk)
-          umma_bf16(tmem_base + FA_O_COL, make_smem_desc(aP + (kk >> 2) * (FA_BM * 128) + (kk & 3) * 32, 16, 1024),
+          umma_bf16(tmem_base + FA_O_COL + (j & 1) * FA_D, make_smem_desc(aP + (j & 1) * FA_PBYTES + kk * 32, 16, 1024),
                     make_smem_desc(aV + s * FA_KBYTES + kk * 2048, 8192, 1024), idesc_o, kk != 0 ? 1u : 0u);
         umma_commit(&kv_empty[s]);
-        umma_commit(o_full);
-        if (j + 1 < ntiles) issue_s(j + 1);
+        umma_commit(&o_full[j & 1]);
+        if (j + 2 < ntiles) issue_s(j + 2);
       }
     }
   } else {
@@ -131,87 +148,57 @@ __global__ void __launch_bounds__(192, 2)
 #pragma unroll
     for (int d = 0; d < FA_D; ++d) o_acc[d] = 0.f;
     float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    uint8_t* prow = sP + r * 128;
     const int sw = r & 7;
+    auto fold_o = [&](int jj, float a) {  // o_acc = o_acc * a + O_jj
+      mbar_wait(&o_full[jj & 1], (jj >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < FA_D / 32; ++c) {
+        float v[32];
+        tmem_ld32(t_lane + FA_O_COL + (jj & 1) * FA_D + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o_acc[c * 32 + e] = fmaf(o_acc[c * 32 + e], a, v[e]);
+      }
+    };
     for (int j = 0; j < ntiles; ++j) {
       const int kbase = j * FA_BN;
       const bool tail = kbase + FA_BN > Nk;
-      mbar_wait(s_full, j & 1);
+      uint8_t* prow = sP + (j & 1) * FA_PBYTES + r * 128;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      // sweep 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < FA_BN / 32; ++c) {
-        float v[32];
-        tmem_ld32(t_lane + FA_S_COL + c * 32, v);
-        tmem_ld_wait();
-        if (tail) {
+      float sv[FA_BN];
+      tmem_ld32(t_lane + FA_S_COL + (j & 1) * FA_BN, sv);
+      tmem_ld32(t_lane + FA_S_COL + (j & 1) * FA_BN + 32, sv + 32);
+      tmem_ld_wait();
+      if (tail) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (kbase + c * 32 + e >= Nk) v[e] = -INFINITY;
-        }
-#pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, v[e]);
+        for (int e = 0; e < FA_BN; ++e)
+          if (kbase + e >= Nk) sv[e] = -INFINITY;
       }
+      float mx = sv[0];
+#pragma unroll
+      for (int e = 1; e < FA_BN; ++e) mx = fmaxf(mx, sv[e]);
       const float m_new = fmaxf(m, mx * scale_log2);
       const float alpha = fast_exp2(m - m_new);  // first tile: exp2(-inf) = 0
-      // fold the previous tile's P V into the register accumulator
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < FA_D / 32; ++c) {
-          float v[32];
-          tmem_ld32(t_lane + FA_O_COL + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o_acc[c * 32 + e] = fmaf(o_acc[c * 32 + e], alpha_prev, v[e]);
-        }
-      }
-      // sweep 2: p = exp2(s*scale - m_new), row sum, bf16 pack, swizzled store
       float lsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < FA_BN / 32; ++c) {
-        float v[32];
-        tmem_ld32(t_lane + FA_S_COL + c * 32, v);
-        tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float p = fast_exp2(fmaf(v[e], scale_log2, -m_new));
-          if (tail && kbase + c * 32 + e >= Nk) p = 0.f;
-          v[e] = p;
-          lsum += p;
-        }
-        // columns [c*32, c*32+32) -> k-block (c>>1), 16-byte chunks (c&1)*4 .. +3
-        uint8_t* pblk = prow + (c >> 1) * (FA_BM * 128);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-          u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-          const int chunk = (c & 1) * 4 + g;
-          *reinterpret_cast<uint4*>(pblk + ((chunk ^ sw) << 4)) = u;
-        }
+      for (int e = 0; e < FA_BN; ++e) {
+        sv[e] = fast_exp2(fmaf(sv[e], scale_log2, -m_new));  // masked keys: exp2(-inf) = 0
+        lsum += sv[e];
       }
-      l = l * alpha + lsum;
-      m = m_new;
-      alpha_prev = alpha;
+      store_row_chunk32_fwd(prow, sw, 0, sv);
+      store_row_chunk32_fwd(prow, sw, 1, sv + 32);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+      if (j > 0) fold_o(j - 1, alpha_prev);  // the P V of the previous tile ran under this tile's softmax
+      l = l * alpha + lsum;
+      m = m_new;
+      alpha_prev = alpha;
     }
-    // last tile's P V
-    mbar_wait(o_full, (ntiles - 1) & 1);
-    tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < FA_D / 32; ++c) {
-      float v[32];
-      tmem_ld32(t_lane + FA_O_COL + c * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) o_acc[c * 32 + e] = fmaf(o_acc[c * 32 + e], alpha_prev, v[e]);
-    }
+    fold_o(ntiles - 1, alpha_prev);
     const int row = q0 + r;
     if (row < Nq) {
       const float inv = 1.f / l;
@@ -245,7 +232,7 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* l
                 int kv_shift, float scale, cudaStream_t stream) {
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = make_qkv_tmap(&tq, q, B, Nq, H, FA_BM))) return rc;
+  if ((rc = make_qkv_tmap(&tq, q, B, Nq, H, FA_BM))) return rc;  // K/V boxes: FA_BN rows
   if ((rc = make_qkv_tmap(&tk, k, B, Nk, H, FA_BN))) return rc;
   if ((rc = make_qkv_tmap(&tv, v, B, Nk, H, FA_BN))) return rc;
   static bool configured = false;
@@ -277,18 +264,21 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* l
 // race-free dQ.  P^T / dS^T / dS are rounded to bf16 and handed to the second MMA through shared
 // memory in the K-major 128B-swizzled layout; the 64-row operand tiles (Q_i, dO_i, K_j) are used both
 // as K-major B operands (first GEMMs) and as MN-major B operands (accumulating GEMMs) of the same
-// shared-memory bytes.  256 TMEM columns and < 100 KiB smem per CTA -> two CTAs per SM.
+// shared-memory bytes.  One CTA per SM: S / dP are double-buffered in TMEM (the MMA thread runs one
+// tile ahead of the softmax warps), two softmax warpgroups split the 64 columns of a tile.
 // ---------------------------------------------------------------------------------------------
 constexpr int FB_R = 128;            // rows owned by the CTA
 constexpr int FB_C = 64;             // inner tile
 constexpr int FB_RBYTES = FB_R * FA_D * 2;  // 16 KiB
 constexpr int FB_CBYTES = FB_C * FA_D * 2;  // 8 KiB
 constexpr int FB_PBYTES = FB_R * FB_C * 2;  // 16 KiB (128 rows x 64 bf16 = one swizzle block per row)
-constexpr int FB_STAGES = 2;
-constexpr int FB_TMEM_COLS = 256;
-constexpr int FB_S_COL = 0, FB_DP_COL = 64, FB_ACC0_COL = 128, FB_ACC1_COL = 192;
-constexpr int FB_DKV_SMEM = 2 * FB_RBYTES + FB_STAGES * 2 * FB_CBYTES + 2 * FB_PBYTES + 2 * 2 * FB_C * 4 + 256;
-constexpr int FB_DQ_SMEM = 2 * FB_RBYTES + FB_STAGES * 2 * FB_CBYTES + FB_PBYTES + 256;
+constexpr int FB_STAGES = 3;
+constexpr int FB_THREADS = 320;      // warps 0-7 softmax (two warpgroups, 32 columns each), 8 TMA, 9 MMA
+constexpr int FB_TMEM_COLS = 512;
+// TMEM columns: S/dP double-buffered at [b*128, b*128+64) / [b*128+64, b*128+128), accumulators behind
+constexpr int FB_ACC0_COL = 256, FB_ACC1_COL = 320;
+constexpr int FB_DKV_SMEM = 2 * FB_RBYTES + FB_STAGES * 2 * FB_CBYTES + 4 * FB_PBYTES + 2 * 2 * FB_C * 4 + 256;
+constexpr int FB_DQ_SMEM = 2 * FB_RBYTES + FB_STAGES * 2 * FB_CBYTES + 2 * FB_PBYTES + 256;
 
 __device__ __forceinline__ void store_row_chunk32(uint8_t* row_base, int sw, int c, const float* v) {
   // 32 consecutive columns [c*32, c*32+32) of a 64-column bf16 row (128 B, swizzled 16-byte chunks)
@@ -302,26 +292,23 @@ __device__ __forceinline__ void store_row_chunk32(uint8_t* row_base, int sw, int
   }
 }
 
-__device__ __forceinline__ void store_out_row64(__nv_bfloat16* dst, uint32_t taddr, bool valid) {
-  // 64 fp32 TMEM columns of this thread's lane -> 64 bf16 (128 contiguous bytes) in global memory.
-  // The TMEM loads are warp-collective: every lane executes them, only valid rows store.
+__device__ __forceinline__ void store_out_cols32(__nv_bfloat16* dst, uint32_t taddr, bool valid) {
+  // 32 fp32 TMEM columns of this thread's lane -> 32 bf16 (64 contiguous bytes) in global memory.
+  // The TMEM load is warp-collective: every lane executes it, only valid rows store.
+  float v[32];
+  tmem_ld32(taddr, v);
+  tmem_ld_wait();
+  if (!valid) return;
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    float v[32];
-    tmem_ld32(taddr + c * 32, v);
-    tmem_ld_wait();
-    if (!valid) continue;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint4 u;
-      u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-      u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-      *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = u;
-    }
+  for (int g = 0; g < 4; ++g) {
+    uint4 u;
+    u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+    u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+    *reinterpret_cast<uint4*>(dst + g * 8) = u;
   }
 }
 
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(FB_THREADS, 1)
     attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                            const float* __restrict__ lse, const float* __restrict__ delta,
@@ -332,17 +319,17 @@ __global__ void __launch_bounds__(192, 2)
   uint8_t* sV = sK + FB_RBYTES;
   uint8_t* sQ = sV + FB_RBYTES;                      // [FB_STAGES]
   uint8_t* sDO = sQ + FB_STAGES * FB_CBYTES;         // [FB_STAGES]
-  uint8_t* sP = sDO + FB_STAGES * FB_CBYTES;
-  uint8_t* sDS = sP + FB_PBYTES;
-  float* sLse = reinterpret_cast<float*>(sDS + FB_PBYTES);  // [2][64]
-  float* sDel = sLse + 2 * FB_C;                            // [2][64]
+  uint8_t* sP = sDO + FB_STAGES * FB_CBYTES;         // [2]
+  uint8_t* sDS = sP + 2 * FB_PBYTES;                 // [2]
+  float* sLse = reinterpret_cast<float*>(sDS + 2 * FB_PBYTES);  // [2][64]
+  float* sDel = sLse + 2 * FB_C;                                // [2][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDel + 2 * FB_C);
   uint64_t* kv_full = bars;
   uint64_t* in_full = bars + 1;               // [FB_STAGES]
   uint64_t* in_empty = in_full + FB_STAGES;   // [FB_STAGES]
-  uint64_t* sp_full = in_empty + FB_STAGES;
-  uint64_t* pds_full = sp_full + 1;
-  uint64_t* acc_done = pds_full + 1;
+  uint64_t* sp_full = in_empty + FB_STAGES;   // [2]
+  uint64_t* pds_full = sp_full + 2;           // [2]
+  uint64_t* acc_done = pds_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -357,21 +344,23 @@ __global__ void __launch_bounds__(192, 2)
       mbar_init(&in_full[s], 1);
       mbar_init(&in_empty[s], 1);
     }
-    mbar_init(sp_full, 1);
-    mbar_init(pds_full, 4);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sp_full[s], 1);
+      mbar_init(&pds_full[s], 8);
+    }
     mbar_init(acc_done, 1);
     mbar_fence_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
   }
-  if (warp == 5) tmem_alloc(tmem_slot, FB_TMEM_COLS);
+  if (warp == 9) tmem_alloc(tmem_slot, FB_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(kv_full, 2 * FB_RBYTES);
       tma_load_4d(sK, &tmK, kv_full, 0, h, k0, kb);
@@ -384,94 +373,94 @@ __global__ void __launch_bounds__(192, 2)
         tma_load_4d(sDO + s * FB_CBYTES, &tmDO, &in_full[s], 0, h, i * FB_C, qb);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (K|V) K-major x (Q|dO) K-major
       constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // (P^T|dS^T) K-major x (dO|Q) MN-major
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aDO = smem_u32(sDO);
       const uint32_t aP = smem_u32(sP), aDS = smem_u32(sDS);
-      mbar_wait(kv_full, 0);
-      for (int i = 0; i < ntiles; ++i) {
+      auto issue_sp = [&](int i) {  // S^T and dP^T of query tile i into TMEM buffer i&1
         const int s = i % FB_STAGES;
+        const uint32_t tb = tmem_base + (i & 1) * 128;
         mbar_wait(&in_full[s], (i / FB_STAGES) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk) {
-          umma_bf16(tmem_base + FB_S_COL, make_smem_desc(aK + kk * 32, 16, 1024),
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16(tb, make_smem_desc(aK + kk * 32, 16, 1024),
                     make_smem_desc(aQ + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
-        }
 #pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk) {
-          umma_bf16(tmem_base + FB_DP_COL, make_smem_desc(aV + kk * 32, 16, 1024),
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16(tb + 64, make_smem_desc(aV + kk * 32, 16, 1024),
                     make_smem_desc(aDO + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
-        }
-        umma_commit(sp_full);
-        mbar_wait(pds_full, i & 1);
+        umma_commit(&sp_full[i & 1]);
+      };
+      mbar_wait(kv_full, 0);
+      issue_sp(0);
+      if (ntiles > 1) issue_sp(1);
+      for (int i = 0; i < ntiles; ++i) {
+        const int s = i % FB_STAGES;
+        mbar_wait(&pds_full[i & 1], (i >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < FB_C / 16; ++kk) {  // contraction over the 64 queries of this tile
-          umma_bf16(tmem_base + FB_ACC0_COL, make_smem_desc(aP + kk * 32, 16, 1024),
+        for (int kk = 0; kk < FB_C / 16; ++kk)  // contraction over the 64 queries of this tile
+          umma_bf16(tmem_base + FB_ACC0_COL, make_smem_desc(aP + (i & 1) * FB_PBYTES + kk * 32, 16, 1024),
                     make_smem_desc(aDO + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (i | kk) != 0 ? 1u : 0u);
-        }
 #pragma unroll
-        for (int kk = 0; kk < FB_C / 16; ++kk) {
-          umma_bf16(tmem_base + FB_ACC1_COL, make_smem_desc(aDS + kk * 32, 16, 1024),
+        for (int kk = 0; kk < FB_C / 16; ++kk)
+          umma_bf16(tmem_base + FB_ACC1_COL, make_smem_desc(aDS + (i & 1) * FB_PBYTES + kk * 32, 16, 1024),
                     make_smem_desc(aQ + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (i | kk) != 0 ? 1u : 0u);
-        }
         umma_commit(&in_empty[s]);
+        if (i + 2 < ntiles) issue_sp(i + 2);
       }
       umma_commit(acc_done);
     }
   } else {
-    const int r = warp * 32 + lane;  // key row within the tile
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    uint8_t* prow = sP + r * 128;
-    uint8_t* dsrow = sDS + r * 128;
+    const int c = warp >> 2;                 // column half handled by this warpgroup
+    const int r = (warp & 3) * 32 + lane;    // key row within the tile == TMEM lane
+    const int tid = threadIdx.x;             // 0..255
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int sw = r & 7;
     for (int i = 0; i < ntiles; ++i) {
       const int buf = i & 1;
       {  // stage lse (pre-multiplied by log2 e) and delta of the 64 queries of this tile
-        const int qi = i * FB_C + (r & 63);
+        const int qi = i * FB_C + (tid & 63);
         const int64_t o = ((int64_t)qb * H + h) * Nq + qi;
-        if (r < 64) sLse[buf * FB_C + r] = qi < Nq ? lse[o] * 1.4426950408889634f : INFINITY;
-        else sDel[buf * FB_C + (r - 64)] = qi < Nq ? delta[o] : 0.f;
+        if (tid < 64) sLse[buf * FB_C + tid] = qi < Nq ? lse[o] * 1.4426950408889634f : INFINITY;
+        else if (tid < 128) sDel[buf * FB_C + (tid - 64)] = qi < Nq ? delta[o] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(sp_full, i & 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(&sp_full[buf], (i >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < FB_C / 32; ++c) {
-        float sv[32], dp[32];
-        tmem_ld32(t_lane + FB_S_COL + c * 32, sv);
-        tmem_ld32(t_lane + FB_DP_COL + c * 32, dp);
-        tmem_ld_wait();
+      float sv[32], dp[32];
+      tmem_ld32(t_lane + buf * 128 + c * 32, sv);
+      tmem_ld32(t_lane + buf * 128 + 64 + c * 32, dp);
+      tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float p = fast_exp2(fmaf(sv[e], scale_log2, -sLse[buf * FB_C + c * 32 + e]));
-          dp[e] = p * (dp[e] - sDel[buf * FB_C + c * 32 + e]) * scale;
-          sv[e] = p;
-        }
-        store_row_chunk32(prow, sw, c, sv);
-        store_row_chunk32(dsrow, sw, c, dp);
+      for (int e = 0; e < 32; ++e) {
+        const float p = fast_exp2(fmaf(sv[e], scale_log2, -sLse[buf * FB_C + c * 32 + e]));
+        dp[e] = p * (dp[e] - sDel[buf * FB_C + c * 32 + e]) * scale;
+        sv[e] = p;
       }
+      store_row_chunk32(sP + buf * FB_PBYTES + r * 128, sw, c, sv);
+      store_row_chunk32(sDS + buf * FB_PBYTES + r * 128, sw, c, dp);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
+      if (lane == 0) mbar_arrive(&pds_full[buf]);
     }
     mbar_wait(acc_done, 0);
     tc_fence_after();
     const int row = k0 + r;
-    const int64_t o = (((int64_t)kb * Nk + (row < Nk ? row : 0)) * H + h) * FA_D;
-    store_out_row64(dv + o, t_lane + FB_ACC0_COL, row < Nk);
-    store_out_row64(dk + o, t_lane + FB_ACC1_COL, row < Nk);
+    const int64_t o = (((int64_t)kb * Nk + (row < Nk ? row : 0)) * H + h) * FA_D + c * 32;
+    store_out_cols32(dv + o, t_lane + FB_ACC0_COL + c * 32, row < Nk);
+    store_out_cols32(dk + o, t_lane + FB_ACC1_COL + c * 32, row < Nk);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, FB_TMEM_COLS);
+  if (warp == 9) tmem_dealloc(tmem_base, FB_TMEM_COLS);
 }
 
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(FB_THREADS, 1)
     attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                           const float* __restrict__ lse, const float* __restrict__ delta,
@@ -482,14 +471,14 @@ __global__ void __launch_bounds__(192, 2)
   uint8_t* sDO = sQ + FB_RBYTES;
   uint8_t* sK = sDO + FB_RBYTES;                  // [FB_STAGES]
   uint8_t* sV = sK + FB_STAGES * FB_CBYTES;       // [FB_STAGES]
-  uint8_t* sDS = sV + FB_STAGES * FB_CBYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + FB_PBYTES);
+  uint8_t* sDS = sV + FB_STAGES * FB_CBYTES;      // [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * FB_PBYTES);
   uint64_t* q_full = bars;
   uint64_t* in_full = bars + 1;
   uint64_t* in_empty = in_full + FB_STAGES;
-  uint64_t* sp_full = in_empty + FB_STAGES;
-  uint64_t* ds_full = sp_full + 1;
-  uint64_t* acc_done = ds_full + 1;
+  uint64_t* sp_full = in_empty + FB_STAGES;   // [2]
+  uint64_t* ds_full = sp_full + 2;            // [2]
+  uint64_t* acc_done = ds_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -504,21 +493,23 @@ __global__ void __launch_bounds__(192, 2)
       mbar_init(&in_full[s], 1);
       mbar_init(&in_empty[s], 1);
     }
-    mbar_init(sp_full, 1);
-    mbar_init(ds_full, 4);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sp_full[s], 1);
+      mbar_init(&ds_full[s], 8);
+    }
     mbar_init(acc_done, 1);
     mbar_fence_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
   }
-  if (warp == 5) tmem_alloc(tmem_slot, FB_TMEM_COLS);
+  if (warp == 9) tmem_alloc(tmem_slot, FB_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(q_full, 2 * FB_RBYTES);
       tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
@@ -531,76 +522,79 @@ __global__ void __launch_bounds__(192, 2)
         tma_load_4d(sV + s * FB_CBYTES, &tmV, &in_full[s], 0, h, j * FB_C, kb);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (Q|dO) K-major x (K|V) K-major
       constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // dS K-major x K_j MN-major
       const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV);
       const uint32_t aDS = smem_u32(sDS);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < ntiles; ++j) {
+      auto issue_sp = [&](int j) {
         const int s = j % FB_STAGES;
+        const uint32_t tb = tmem_base + (j & 1) * 128;
         mbar_wait(&in_full[s], (j / FB_STAGES) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk) {
-          umma_bf16(tmem_base + FB_S_COL, make_smem_desc(aQ + kk * 32, 16, 1024),
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16(tb, make_smem_desc(aQ + kk * 32, 16, 1024),
                     make_smem_desc(aK + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
-        }
 #pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk) {
-          umma_bf16(tmem_base + FB_DP_COL, make_smem_desc(aDO + kk * 32, 16, 1024),
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16(tb + 64, make_smem_desc(aDO + kk * 32, 16, 1024),
                     make_smem_desc(aV + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
-        }
-        umma_commit(sp_full);
-        mbar_wait(ds_full, j & 1);
+        umma_commit(&sp_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_sp(0);
+      if (ntiles > 1) issue_sp(1);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % FB_STAGES;
+        mbar_wait(&ds_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < FB_C / 16; ++kk) {  // contraction over the 64 keys of this tile
-          umma_bf16(tmem_base + FB_ACC0_COL, make_smem_desc(aDS + kk * 32, 16, 1024),
+        for (int kk = 0; kk < FB_C / 16; ++kk)  // contraction over the 64 keys of this tile
+          umma_bf16(tmem_base + FB_ACC0_COL, make_smem_desc(aDS + (j & 1) * FB_PBYTES + kk * 32, 16, 1024),
                     make_smem_desc(aK + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0 ? 1u : 0u);
-        }
         umma_commit(&in_empty[s]);
+        if (j + 2 < ntiles) issue_sp(j + 2);
       }
       umma_commit(acc_done);
     }
   } else {
-    const int r = warp * 32 + lane;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    uint8_t* dsrow = sDS + r * 128;
+    const int c = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int sw = r & 7;
     const int row = q0 + r;
-    const int64_t lo = ((int64_t)b * H + h) * Nq + row;
+    const int64_t lo = ((int64_t)b * H + h) * Nq + (row < Nq ? row : 0);
     const float lse2 = row < Nq ? lse[lo] * 1.4426950408889634f : INFINITY;
     const float dl = row < Nq ? delta[lo] : 0.f;
     for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(sp_full, j & 1);
+      const int buf = j & 1;
+      mbar_wait(&sp_full[buf], (j >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < FB_C / 32; ++c) {
-        float sv[32], dp[32];
-        tmem_ld32(t_lane + FB_S_COL + c * 32, sv);
-        tmem_ld32(t_lane + FB_DP_COL + c * 32, dp);
-        tmem_ld_wait();
+      float sv[32], dp[32];
+      tmem_ld32(t_lane + buf * 128 + c * 32, sv);
+      tmem_ld32(t_lane + buf * 128 + 64 + c * 32, dp);
+      tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float p = fast_exp2(fmaf(sv[e], scale_log2, -lse2));
-          dp[e] = p * (dp[e] - dl) * scale;
-        }
-        store_row_chunk32(dsrow, sw, c, dp);
+      for (int e = 0; e < 32; ++e) {
+        const float p = fast_exp2(fmaf(sv[e], scale_log2, -lse2));
+        dp[e] = p * (dp[e] - dl) * scale;
       }
+      store_row_chunk32(sDS + buf * FB_PBYTES + r * 128, sw, c, dp);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
+      if (lane == 0) mbar_arrive(&ds_full[buf]);
     }
     mbar_wait(acc_done, 0);
     tc_fence_after();
-    store_out_row64(dq + (((int64_t)b * Nq + (row < Nq ? row : 0)) * H + h) * FA_D, t_lane + FB_ACC0_COL, row < Nq);
+    store_out_cols32(dq + (((int64_t)b * Nq + (row < Nq ? row : 0)) * H + h) * FA_D + c * 32,
+                     t_lane + FB_ACC0_COL + c * 32, row < Nq);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, FB_TMEM_COLS);
+  if (warp == 9) tmem_dealloc(tmem_base, FB_TMEM_COLS);
 }
 
 int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
@@ -624,7 +618,7 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, co
     if ((rc = make_qkv_tmap(&tk, k, B, Nk, H, FB_C))) return rc;
     if ((rc = make_qkv_tmap(&tv, v, B, Nk, H, FB_C))) return rc;
     dim3 grid((Nq + FB_R - 1) / FB_R, H, B);
-    attn_bwd_dq_tc_kernel<<<grid, 192, FB_DQ_SMEM, stream>>>(tq, tk, tv, tdo, lse, delta,
+    attn_bwd_dq_tc_kernel<<<grid, FB_THREADS, FB_DQ_SMEM, stream>>>(tq, tk, tv, tdo, lse, delta,
                                                             static_cast<__nv_bfloat16*>(dq), B, Nq, Nk, H, kv_shift,
                                                             scale, sl2);
   }
@@ -635,7 +629,7 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, co
     if ((rc = make_qkv_tmap(&tk, k, B, Nk, H, FB_R))) return rc;
     if ((rc = make_qkv_tmap(&tv, v, B, Nk, H, FB_R))) return rc;
     dim3 grid((Nk + FB_R - 1) / FB_R, H, B);
-    attn_bwd_dkv_tc_kernel<<<grid, 192, FB_DKV_SMEM, stream>>>(tq, tk, tv, tdo, lse, delta,
+    attn_bwd_dkv_tc_kernel<<<grid, FB_THREADS, FB_DKV_SMEM, stream>>>(tq, tk, tv, tdo, lse, delta,
                                                               static_cast<__nv_bfloat16*>(dk),
                                                               static_cast<__nv_bfloat16*>(dv), B, Nq, Nk, H, kv_shift,
                                                               scale, sl2);
