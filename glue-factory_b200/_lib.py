@@ -35,6 +35,9 @@ SIGNATURES = {
     "lgb200_assign_scores": (_i, [_vp] * 16 + [_i, _i, _i, _vp]),
     "lgb200_assign_bwd": (_i, [_vp] * 8 + [_i, _i, _i, _i, _vp]),
     "lgb200_filter_matches": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lgb200_head_logsig": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "lgb200_head_terms_fwd": (_i, [_vp] * 14 + [_f] + [_vp] * 4 + [_i, _i, _i, _vp]),
+    "lgb200_head_terms_bwd": (_i, [_vp] * 13 + [_f] + [_vp] * 3 + [_i, _i, _i, _vp]),
     "lgb200_heads_ws_bytes": (_sz, [_i, _i, _i]),
     "lgb200_log_double_softmax": (_i, [_vp, _f, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_sinkhorn": (_i, [_vp, _f, _i, _vp, _vp, _i, _i, _i, _vp]),

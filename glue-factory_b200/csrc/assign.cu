@@ -310,7 +310,8 @@ __global__ void assign_col_arg_merge_kernel(const float* __restrict__ colpart_v,
 // ---------------------------------------------------------------------------------------------
 // backward of S_pos(sim) = sum_ij gt_ij (2 sim_ij - lse_row_i - lse_col_j):
 //   dsim_ij = 2 c_b gt_ij - exp(sim_ij - lse_row_i) a_row_i - exp(sim_ij - lse_col_j) a_col_j
-// (a_row = c_b * rowcount(gt), a_col = c_b * colcount(gt))
+// (here a_row_i = c_b * rowcount_i(gt), a_col_j = c_b * colcount_j(gt): the
+//  kernel takes the counts and applies c_b itself)
 // ---------------------------------------------------------------------------------------------
 template <typename OutT>
 __global__ void __launch_bounds__(256) assign_bwd_kernel(const float* __restrict__ sim,
@@ -325,9 +326,10 @@ __global__ void __launch_bounds__(256) assign_bwd_kernel(const float* __restrict
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const bool vec = (N & 3) == 0;
-  const float c2 = 2.f * gcoef[b];
+  const float gc = gcoef[b];
+  const float c2 = 2.f * gc;
   const float lr = lse_row[(int64_t)b * M + row];
-  const float ar = a_row[(int64_t)b * M + row];
+  const float ar = gc * a_row[(int64_t)b * M + row];
   const int64_t roff = ((int64_t)b * M + row) * N;
   for (int col = lane * 4; col < N; col += 128) {
     const int valid = min(4, N - col);
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(256) assign_bwd_kernel(const float* __restrict
     for (int e = 0; e < 4; ++e) {
       d[e] = 0.f;
       if (e < valid) {
-        const float ac = a_col[(int64_t)b * N + col + e];
+        const float ac = gc * a_col[(int64_t)b * N + col + e];
         float v = ((g >> (8 * e)) & 0xffu) ? c2 : 0.f;
         if (ar != 0.f) v -= __expf(x[e] - lr) * ar;
         if (ac != 0.f) v -= __expf(x[e] - lse_col[(int64_t)b * N + col + e]) * ac;
@@ -402,11 +404,179 @@ __global__ void filter_matches_kernel(const float* __restrict__ rowmax, const in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// O(M+N) terms of one supervised layer, fused: matchability log-sigmoids, the NLL of losses.py:6-25
+// (given the similarity part sum_j gt_ij(2 sim - lse_r - lse_c) per row from pass 2), and the
+// TokenConfidence BCE of lightglue.py:81-94.  zt holds [matchability logit, token logit] per token,
+// tokens ordered [image0 (B*M); image1 (B*N)].  One CTA per pair; deterministic block reduction.
+// ---------------------------------------------------------------------------------------------
+struct HeadArgs {
+  const float* zt;           // [T, 2]
+  const float* pos_row_sum;  // [B,M]
+  const float* rowcnt; const float* colcnt; const float* neg0; const float* neg1;
+  const float* rowmax; const int* rowarg; const float* colmax; const int* colarg;
+  const int* fin0; const int* fin1;  // final-layer argmax incl. dustbin, or null (no confidence term)
+  const float* num_pos; const float* num_neg;  // [B]
+  float bal;
+  int B, M, N;
+  float* nll; float* nll_pos; float* nll_neg; float* conf;  // [B]
+};
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) head_terms_fwd_kernel(HeadArgs a) {
+  __shared__ float red[8];
+  const int b = blockIdx.x, M = a.M, N = a.N;
+  const int64_t t0 = (int64_t)a.B * M;
+  float pos = 0.f, neg = 0.f, c0 = 0.f, c1 = 0.f;
+  for (int i = threadIdx.x; i < M; i += 256) {
+    const int64_t r = (int64_t)b * M + i;
+    const float2 z = *reinterpret_cast<const float2*>(a.zt + 2 * r);
+    const float ls = log_sigmoid(z.x), du = ls - z.x;
+    pos += a.pos_row_sum[r] + a.rowcnt[r] * ls;
+    neg += a.neg0[r] * du;
+    if (a.fin0) {
+      const int arg = du > a.rowmax[r] ? N : a.rowarg[r];
+      const float y = (a.fin0[r] == arg) ? 1.f : 0.f;
+      c0 += fmaxf(z.y, 0.f) - z.y * y + log1pf(expf(-fabsf(z.y)));
+    }
+  }
+  for (int j = threadIdx.x; j < N; j += 256) {
+    const int64_t r = (int64_t)b * N + j;
+    const float2 z = *reinterpret_cast<const float2*>(a.zt + 2 * (t0 + r));
+    const float ls = log_sigmoid(z.x), du = ls - z.x;
+    pos += a.colcnt[r] * ls;
+    neg += a.neg1[r] * du;
+    if (a.fin1) {
+      const int arg = du > a.colmax[r] ? M : a.colarg[r];
+      const float y = (a.fin1[r] == arg) ? 1.f : 0.f;
+      c1 += fmaxf(z.y, 0.f) - z.y * y + log1pf(expf(-fabsf(z.y)));
+    }
+  }
+  pos = block_sum_256(pos, red);
+  neg = block_sum_256(neg, red);
+  c0 = block_sum_256(c0, red);
+  c1 = block_sum_256(c1, red);
+  if (threadIdx.x == 0) {
+    const float np = -pos / a.num_pos[b], nn = -neg / a.num_neg[b];
+    a.nll_pos[b] = np;
+    a.nll_neg[b] = nn;
+    a.nll[b] = a.bal * np + (1.f - a.bal) * nn;
+    a.conf[b] = a.fin0 ? 0.5f * (c0 / M + c1 / N) : 0.f;
+  }
+}
+
+// d(zt) for upstream gradients g_nll[b], g_conf[b]
+__global__ void __launch_bounds__(256) head_terms_bwd_kernel(HeadArgs a, const float* __restrict__ g_nll,
+                                                            const float* __restrict__ g_conf,
+                                                            float* __restrict__ dzt) {
+  const int M = a.M, N = a.N;
+  const int64_t t0 = (int64_t)a.B * M, T = t0 + (int64_t)a.B * N;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const bool side1 = t >= t0;
+  const int64_t r = side1 ? t - t0 : t;
+  const int L = side1 ? N : M;
+  const int b = (int)(r / L);
+  const float2 z = *reinterpret_cast<const float2*>(a.zt + 2 * t);
+  const float g = g_nll[b];
+  const float gpos = -a.bal * g / a.num_pos[b];
+  const float gneg = -(1.f - a.bal) * g / a.num_neg[b];
+  const float sg = 1.f / (1.f + expf(-z.x));
+  const float cnt = side1 ? a.colcnt[r] : a.rowcnt[r];
+  const float ng = side1 ? a.neg1[r] : a.neg0[r];
+  float2 d;
+  d.x = gpos * cnt * (1.f - sg) - gneg * ng * sg;
+  d.y = 0.f;
+  const int* fin = side1 ? a.fin1 : a.fin0;
+  if (fin) {
+    const float ls = log_sigmoid(z.x), du = ls - z.x;
+    const float mx = side1 ? a.colmax[r] : a.rowmax[r];
+    const int ag = side1 ? a.colarg[r] : a.rowarg[r];
+    const int arg = du > mx ? (side1 ? M : N) : ag;
+    const float y = (fin[r] == arg) ? 1.f : 0.f;
+    d.y = g_conf[b] * (0.5f / L) * (1.f / (1.f + expf(-z.y)) - y);
+  }
+  *reinterpret_cast<float2*>(dzt + 2 * t) = d;
+}
+
+// ls = log sigmoid(z), du = log sigmoid(-z) from the strided logits (feeds pass 2)
+__global__ void __launch_bounds__(256) logsig_kernel(const float* __restrict__ zt, float* __restrict__ ls,
+                                                    float* __restrict__ du, int64_t T) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float z = zt[2 * t];
+  const float l = log_sigmoid(z);
+  ls[t] = l;
+  du[t] = l - z;
+}
+
 }  // namespace lgb
 
 using namespace lgb;
 
 extern "C" {
+
+int lgb200_head_logsig(const float* zt, float* ls, float* du, int64_t T, cudaStream_t stream) {
+  LGB_REQUIRE(zt && ls && du && T > 0, kErrInvalid, "head_logsig: bad arguments");
+  logsig_kernel<<<(unsigned)((T + 255) / 256), 256, 0, stream>>>(zt, ls, du, T);
+  return check_launch("head_logsig");
+}
+
+static int fill_head_args(HeadArgs& a, const float* zt, const float* pos_row_sum, const float* rowcnt,
+                          const float* colcnt, const float* neg0, const float* neg1, const float* rowmax,
+                          const int* rowarg, const float* colmax, const int* colarg, const int* fin0, const int* fin1,
+                          const float* num_pos, const float* num_neg, float bal, int B, int M, int N) {
+  LGB_REQUIRE(zt && pos_row_sum && rowcnt && colcnt && neg0 && neg1 && rowmax && rowarg && colmax && colarg &&
+                  num_pos && num_neg,
+              kErrInvalid, "head_terms: null pointer");
+  LGB_REQUIRE((fin0 == nullptr) == (fin1 == nullptr), kErrInvalid, "head_terms: fin0/fin1 must both be set or null");
+  LGB_REQUIRE(B > 0 && M > 0 && N > 0, kErrInvalid, "head_terms: empty input");
+  a.zt = zt; a.pos_row_sum = pos_row_sum; a.rowcnt = rowcnt; a.colcnt = colcnt; a.neg0 = neg0; a.neg1 = neg1;
+  a.rowmax = rowmax; a.rowarg = rowarg; a.colmax = colmax; a.colarg = colarg; a.fin0 = fin0; a.fin1 = fin1;
+  a.num_pos = num_pos; a.num_neg = num_neg; a.bal = bal; a.B = B; a.M = M; a.N = N;
+  a.nll = a.nll_pos = a.nll_neg = a.conf = nullptr;
+  return 0;
+}
+
+int lgb200_head_terms_fwd(const float* zt, const float* pos_row_sum, const float* rowcnt, const float* colcnt,
+                          const float* neg0, const float* neg1, const float* rowmax, const int* rowarg,
+                          const float* colmax, const int* colarg, const int* fin0, const int* fin1,
+                          const float* num_pos, const float* num_neg, float bal, float* nll, float* nll_pos,
+                          float* nll_neg, float* conf, int B, int M, int N, cudaStream_t stream) {
+  HeadArgs a;
+  int rc = fill_head_args(a, zt, pos_row_sum, rowcnt, colcnt, neg0, neg1, rowmax, rowarg, colmax, colarg, fin0, fin1,
+                          num_pos, num_neg, bal, B, M, N);
+  if (rc) return rc;
+  LGB_REQUIRE(nll && nll_pos && nll_neg && conf, kErrInvalid, "head_terms_fwd: null output");
+  a.nll = nll; a.nll_pos = nll_pos; a.nll_neg = nll_neg; a.conf = conf;
+  head_terms_fwd_kernel<<<B, 256, 0, stream>>>(a);
+  return check_launch("head_terms_fwd");
+}
+
+int lgb200_head_terms_bwd(const float* zt, const float* rowcnt, const float* colcnt, const float* neg0,
+                          const float* neg1, const float* rowmax, const int* rowarg, const float* colmax,
+                          const int* colarg, const int* fin0, const int* fin1, const float* num_pos,
+                          const float* num_neg, float bal, const float* g_nll, const float* g_conf, float* dzt, int B,
+                          int M, int N, cudaStream_t stream) {
+  HeadArgs a;
+  int rc = fill_head_args(a, zt, rowcnt /*unused*/, rowcnt, colcnt, neg0, neg1, rowmax, rowarg, colmax, colarg, fin0,
+                          fin1, num_pos, num_neg, bal, B, M, N);
+  if (rc) return rc;
+  LGB_REQUIRE(g_nll && g_conf && dzt, kErrInvalid, "head_terms_bwd: null pointer");
+  const int64_t T = (int64_t)B * (M + N);
+  head_terms_bwd_kernel<<<(unsigned)((T + 255) / 256), 256, 0, stream>>>(a, g_nll, g_conf, dzt);
+  return check_launch("head_terms_bwd");
+}
 
 size_t lgb200_assign_ws_bytes(int B, int M, int N) {
   const int nstrips = (M + kStripRows - 1) / kStripRows;

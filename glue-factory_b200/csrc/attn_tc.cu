@@ -11,7 +11,7 @@
 // tcgen05.ld (row max, exp2 / row sum / bf16 pack), P_j written to shared memory in the
 // K-major 128B-swizzled layout the MMA expects, O_j folded into a register accumulator with the
 // usual online-softmax rescale.  Warp 4 = TMA producer, warp 5 = MMA issuer + TMEM owner.
-// Two CTAs fit per SM (96 KiB smem, 256 TMEM columns each).
+// Two CTAs fit per SM (112 KiB smem, 256 TMEM columns each); 4 K/V stages keep the TMA loads ~2 tiles ahead.
 #include <math.h>
 
 #include "common.cuh"
@@ -35,7 +35,7 @@ __device__ __forceinline__ void store_row_chunk32_fwd(uint8_t* row_base, int sw,
 constexpr int FA_BM = 128;     // queries per CTA
 constexpr int FA_BN = 64;      // keys per iteration
 constexpr int FA_D = 64;
-constexpr int FA_STAGES = 3;
+constexpr int FA_STAGES = 4;
 constexpr int FA_QBYTES = FA_BM * FA_D * 2;   // 16 KiB
 constexpr int FA_KBYTES = FA_BN * FA_D * 2;   // 8 KiB
 constexpr int FA_PBYTES = FA_BM * FA_BN * 2;  // 16 KiB (one 128-byte swizzle row per query)
@@ -272,7 +272,7 @@ constexpr int FB_C = 64;             // inner tile
 constexpr int FB_RBYTES = FB_R * FA_D * 2;  // 16 KiB
 constexpr int FB_CBYTES = FB_C * FA_D * 2;  // 8 KiB
 constexpr int FB_PBYTES = FB_R * FB_C * 2;  // 16 KiB (128 rows x 64 bf16 = one swizzle block per row)
-constexpr int FB_STAGES = 3;
+constexpr int FB_STAGES = 5;
 constexpr int FB_THREADS = 320;      // warps 0-7 softmax (two warpgroups, 32 columns each), 8 TMA, 9 MMA
 constexpr int FB_TMEM_COLS = 512;
 // TMEM columns: S/dP double-buffered at [b*128, b*128+64) / [b*128+64, b*128+128), accumulators behind

@@ -179,14 +179,16 @@ class LayerFn(torch.autograd.Function):
 
 
 class HeadFn(torch.autograd.Function):
-    """x [T, D] fp32 (tokens of both images) -> per-pair NLL of this layer's assignment
-    (+ detached nll_pos / nll_neg and the row / column argmax including the dustbin)."""
+    """x [T, D] fp32 (tokens of both images) -> (nll [B], conf [B]) of this layer: the NLL of its assignment
+    and the token-confidence BCE against the final layer's argmax (`fin`; None for the last layer),
+    plus the detached nll_pos / nll_neg for logging."""
 
     @staticmethod
-    def forward(ctx, x, sizes, cdt, gt, bal, wfp, bfp, Wfp_p, bfp_p, wm, bm):
+    def forward(ctx, x, sizes, cdt, gt, bal, fin, wfp, bfp, Wfp_p, bfp_p, wm, bm, wt, bt):
         B, M, N = sizes
         D = x.shape[1]
         t0 = B * M
+        dev = x.device
         x = x.contiguous()
         _, x16 = ops.residual_add_cast(x, None, cdt)
         md = torch.addmm(bfp, x16, wfp.t())  # final_proj, un-scaled; d^-1/2 is folded into sim
@@ -196,46 +198,54 @@ class HeadFn(torch.autograd.Function):
             sim = ops.gemm_bf16(md0, md1, alpha=alpha)
         else:
             sim = torch.bmm(md0, md1.transpose(1, 2)).mul_(alpha)
-        z = torch.mv(x, wm.view(-1)).add_(bm)  # matchability logits (fp32)
-        ls = F.logsigmoid(z)
-        du = ls - z  # log sigmoid(-z)
+        # [matchability logit, token-confidence logit] per token in one skinny GEMM (fp32)
+        has_tok = wt is not None
+        W2 = torch.cat([wm, wt if has_tok else wm], 0)
+        b2 = torch.cat([bm, bt if has_tok else bm], 0)
+        zt = torch.addmm(b2, x, W2.t())
+        ls, du = ops.head_logsig(zt)
         ls0, ls1, du0, du1 = ls[:t0].view(B, M), ls[t0:].view(B, N), du[:t0].view(B, M), du[t0:].view(B, N)
         st = ops.assign_stats(sim, ls0, ls1, du0, du1, gt_u8=gt["u8"], dense=False)
-        pos = st["pos_row_sum"].sum(1) + (gt["rowcnt"] * ls0).sum(1) + (gt["colcnt"] * ls1).sum(1)
-        nll_pos = -pos / gt["num_pos"]
-        nll_neg = -((gt["neg0"] * du0).sum(1) + (gt["neg1"] * du1).sum(1)) / gt["num_neg"]
-        nll = bal * nll_pos + (1 - bal) * nll_neg
-        arg0 = torch.where(du0 > st["rowmax"], torch.full_like(st["rowarg"], N), st["rowarg"])
-        arg1 = torch.where(du1 > st["colmax"], torch.full_like(st["colarg"], M), st["colarg"])
-        ctx.save_for_backward(x, x16, md, sim, st["lse_row"], st["lse_col"], z, wfp, wm, gt["u8"], gt["rowcnt"],
-                              gt["colcnt"], gt["neg0"], gt["neg1"], gt["num_pos"], gt["num_neg"])
-        ctx.meta = (sizes, cdt, bal, alpha)
-        for t in (nll_pos, nll_neg, arg0, arg1):
-            ctx.mark_non_differentiable(t)
-        return nll, nll_pos, nll_neg, arg0, arg1
+        out = torch.empty(4, B, device=dev, dtype=torch.float32)
+        f0, f1 = (fin if (fin is not None and has_tok) else (None, None))
+        ops.call("lgb200_head_terms_fwd", ops.ptr(zt), ops.ptr(st["pos_row_sum"]), ops.ptr(gt["rowcnt"]),
+                 ops.ptr(gt["colcnt"]), ops.ptr(gt["neg0"]), ops.ptr(gt["neg1"]), ops.ptr(st["rowmax"]),
+                 ops.ptr(st["rowarg"]), ops.ptr(st["colmax"]), ops.ptr(st["colarg"]), ops.ptr(f0), ops.ptr(f1),
+                 ops.ptr(gt["num_pos"]), ops.ptr(gt["num_neg"]), float(bal), ops.ptr(out[0]), ops.ptr(out[1]),
+                 ops.ptr(out[2]), ops.ptr(out[3]), B, M, N, ops.stream_ptr())
+        nll, nll_pos, nll_neg, conf = out[0], out[1], out[2], out[3]
+        saved = [x, x16, md, sim, st["lse_row"], st["lse_col"], zt, st["rowmax"], st["rowarg"], st["colmax"],
+                 st["colarg"], wfp, wm, gt["u8"], gt["rowcnt"], gt["colcnt"], gt["neg0"], gt["neg1"], gt["num_pos"],
+                 gt["num_neg"]]
+        if f0 is not None:
+            saved += [f0, f1]
+        ctx.save_for_backward(*saved)
+        ctx.meta = (sizes, cdt, bal, alpha, has_tok, f0 is not None)
+        ctx.mark_non_differentiable(nll_pos, nll_neg)
+        return nll, conf, nll_pos, nll_neg
 
     @staticmethod
-    def backward(ctx, g, *_):
-        (x, x16, md, sim, lse_row, lse_col, z, wfp, wm, gt_u8, rowcnt, colcnt, neg0, neg1, num_pos,
-         num_neg) = ctx.saved_tensors
-        (B, M, N), cdt, bal, alpha = ctx.meta
+    def backward(ctx, g_nll, g_conf, *_):
+        sv = ctx.saved_tensors
+        (x, x16, md, sim, lse_row, lse_col, zt, rowmax, rowarg, colmax, colarg, wfp, wm, gt_u8, rowcnt, colcnt, neg0,
+         neg1, num_pos, num_neg) = sv[:20]
+        (B, M, N), cdt, bal, alpha, has_tok, has_fin = ctx.meta
+        f0, f1 = (sv[20], sv[21]) if has_fin else (None, None)
         D = x.shape[1]
         t0 = B * M
-        g = g.float()
-        gpos = (-bal) * g / num_pos            # d nll / d (sum_P scores)
-        gneg = -(1 - bal) * g / num_neg        # d nll / d (sum of dustbin scores)
-        # matchability: d logsig(z) = sigmoid(-z), d logsig(-z) = -sigmoid(z)
-        s = torch.sigmoid(z)
-        s0, s1 = s[:t0].view(B, M), s[t0:].view(B, N)
-        dz = torch.cat([(gpos[:, None] * rowcnt * (1 - s0) - gneg[:, None] * neg0 * s0).reshape(-1),
-                        (gpos[:, None] * colcnt * (1 - s1) - gneg[:, None] * neg1 * s1).reshape(-1)])
+        g_nll = g_nll.float().contiguous()
+        g_conf = g_conf.float().contiguous() if g_conf is not None else torch.zeros_like(g_nll)
+        dzt = torch.empty_like(zt)
+        ops.call("lgb200_head_terms_bwd", ops.ptr(zt), ops.ptr(rowcnt), ops.ptr(colcnt), ops.ptr(neg0), ops.ptr(neg1),
+                 ops.ptr(rowmax), ops.ptr(rowarg), ops.ptr(colmax), ops.ptr(colarg), ops.ptr(f0), ops.ptr(f1),
+                 ops.ptr(num_pos), ops.ptr(num_neg), float(bal), ops.ptr(g_nll), ops.ptr(g_conf), ops.ptr(dzt), B, M, N,
+                 ops.stream_ptr())
         # similarity: dsim = gc (2 gt - softmax_row * rowcnt - softmax_col * colcnt), gc includes d^-1/2
-        gc = (gpos * alpha).contiguous()
-        a_row, a_col = (gc[:, None] * rowcnt).contiguous(), (gc[:, None] * colcnt).contiguous()
+        gc = (g_nll * (-bal * alpha) / num_pos).contiguous()
         tc = cdt == torch.bfloat16 and N % 8 == 0 and M % 8 == 0
         dsim = torch.empty(B, M, N, device=x.device, dtype=torch.bfloat16 if tc else torch.float32)
         ops.call("lgb200_assign_bwd", ops.ptr(sim), ops.ptr(lse_row), ops.ptr(lse_col), ops.ptr(gt_u8), ops.ptr(gc),
-                 ops.ptr(a_row), ops.ptr(a_col), ops.ptr(dsim), ops._code(dsim.dtype), B, M, N, ops.stream_ptr())
+                 ops.ptr(rowcnt), ops.ptr(colcnt), ops.ptr(dsim), ops._code(dsim.dtype), B, M, N, ops.stream_ptr())
         md0, md1 = md[:t0].view(B, M, D), md[t0:].view(B, N, D)
         if tc:
             dmd0 = ops.gemm_bf16(dsim, md1, a_mn_major=False, b_mn_major=True, out_dtype=cdt)  # dsim   md1
@@ -246,7 +256,8 @@ class HeadFn(torch.autograd.Function):
         dmd = torch.cat([dmd0.reshape(t0, D), dmd1.reshape(B * N, D)], 0)
         dWfp, dbfp = _wgrad(dmd, x16), _bgrad(dmd)
         dx = torch.mm(dmd, wfp).float()
-        dx.addr_(dz, wm.view(-1))
-        dwm = torch.mv(x.t(), dz).view(1, -1)
-        dbm = dz.sum().view(1)
-        return dx, None, None, None, None, None, None, dWfp, dbfp, dwm, dbm
+        dx.addr_(dzt[:, 0], wm.view(-1))  # the token-confidence head reads a detached x (lightglue.py:82-83)
+        dW2 = torch.mm(dzt.t(), x)
+        db2 = dzt.sum(0)
+        dwt, dbt = (dW2[1:2], db2[1:2]) if has_tok else (None, None)
+        return dx, None, None, None, None, None, None, None, dWfp, dbfp, dW2[0:1], db2[0:1], dwt, dbt

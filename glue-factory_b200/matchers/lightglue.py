@@ -329,12 +329,71 @@ class LightGlue(nn.Module):
         }
         if fused:
             # private side channel for loss(): the per-layer token tensors (both images, [T, D]); avoids
-            # slicing the stacked ref_descriptors (whose backward would scatter into 9 zero-filled stacks)
+            # slicing the stacked ref_descriptors (whose backward would scatter into 9 zero-filled stacks).
+            # Also the final layer's argmax including the dustbin (labels of TokenConfidence.loss) and the
+            # row_norm monitor, both by-products of the dense pass.
             pred["_b200_layers"] = layers_x
             pred["_b200_sizes"] = sizes
+            du0, du1 = F.logsigmoid(-z0), F.logsigmoid(-z1)
+            pred["_b200_final_arg"] = (
+                self._argmax_with_dustbin(st["rowmax"], st["rowarg"], du0, N).contiguous(),
+                self._argmax_with_dustbin(st["colmax"], st["colarg"], du1, M).contiguous())
+            pred["_b200_row_expsum"] = st["row_expsum"]
         return pred
 
     # ------------------------------------------------------------------------------------------
+    def _loss_fused(self, pred, data, layers_x, gt_u8, rowcnt, colcnt, neg0, neg1, num_pos, num_neg0, num_neg1):
+        """lightglue.py:578-627 on the hand-scheduled heads (engine.HeadFn): per layer one autograd node that
+        yields the NLL and the token-confidence BCE; the O(M+N) terms are two small fused kernels."""
+        conf = self.conf
+        B, M, N = pred["_b200_sizes"]
+        L = len(layers_x)
+        gtd = {"u8": gt_u8, "rowcnt": rowcnt.contiguous(), "colcnt": colcnt.contiguous(), "neg0": neg0.contiguous(),
+               "neg1": neg1.contiguous(), "num_pos": num_pos.contiguous(), "num_neg": (num_neg0 + num_neg1).contiguous()}
+        la = pred["log_assignment"].detach()
+        fin = pred.get("_b200_final_arg")
+        if fin is None and L > 1:
+            fin = (la[:, :-1, :].max(-1).indices.to(torch.int32).contiguous(),
+                   la[:, :, :-1].max(-2).indices.to(torch.int32).contiguous())
+
+        def head(i):
+            la_i = self.log_assignment[i]
+            pre = f"log_assignment.{i}.final_proj."
+            tok = self.token_confidence[i].token[0] if (i < L - 1 and self.training) else None
+            return engine.HeadFn.apply(layers_x[i], (B, M, N), self._cdt, gtd, conf.loss.nll_balancing, fin,
+                                       self._shadow[pre + "weight"], self._shadow[pre + "bias"],
+                                       la_i.final_proj.weight, la_i.final_proj.bias, la_i.matchability.weight,
+                                       la_i.matchability.bias, tok.weight if tok is not None else None,
+                                       tok.bias if tok is not None else None)
+
+        nll, _, nll_pos, nll_neg = head(L - 1)
+        losses = {
+            "total": nll,
+            "last": nll.clone().detach(),
+            "assignment_nll": nll,
+            "nll_pos": nll_pos,
+            "nll_neg": nll_neg,
+            "num_matchable": num_pos,
+            "num_unmatchable": (num_neg0 + num_neg1) / 2.0,
+        }
+        if self.training:
+            losses["confidence"] = 0.0
+        rn = pred.get("_b200_row_expsum")
+        losses["row_norm"] = rn.mean(1) if rn is not None else la.exp()[:, :-1].sum(2).mean(1)
+        sum_weights = 1.0
+        for i in range(L - 1):
+            nll_i, conf_i, _, _ = head(i)
+            weight = conf.loss.gamma ** (L - i - 1) if conf.loss.gamma > 0.0 else i + 1
+            sum_weights += weight
+            losses["total"] = losses["total"] + nll_i * weight
+            if self.training:
+                losses["confidence"] = losses["confidence"] + conf_i / (L - 1)
+        losses["total"] = losses["total"] / sum_weights
+        if self.training:
+            losses["total"] = losses["total"] + losses["confidence"]
+        metrics = {} if self.training else matcher_metrics(pred, data)
+        return losses, metrics
+
     @staticmethod
     def _argmax_with_dustbin(val, arg, dust, width):
         """argmax over [inner scores | dustbin]: the dustbin (highest index) wins only when strictly larger."""
@@ -372,15 +431,7 @@ class LightGlue(nn.Module):
 
         layers_x = pred.get("_b200_layers") if conf.engine == "fused" else None
         if layers_x is not None and len(layers_x) == L:
-            gtd = {"u8": gt_u8, "rowcnt": rowcnt, "colcnt": colcnt, "neg0": neg0, "neg1": neg1, "num_pos": num_pos,
-                   "num_neg": num_neg0 + num_neg1}
-
-            def head(i):  # noqa: F811  (hand-scheduled head, engine.HeadFn)
-                la_i = self.log_assignment[i]
-                pre = f"log_assignment.{i}.final_proj."
-                return engine.HeadFn.apply(layers_x[i], (B, M, N), self._cdt, gtd, bal, self._shadow[pre + "weight"],
-                                           self._shadow[pre + "bias"], la_i.final_proj.weight, la_i.final_proj.bias,
-                                           la_i.matchability.weight, la_i.matchability.bias)
+            return self._loss_fused(pred, data, layers_x, gt_u8, rowcnt, colcnt, neg0, neg1, num_pos, num_neg0, num_neg1)
 
         nll, nll_pos, nll_neg, _, _ = head(L - 1)
         losses = {

@@ -253,11 +253,9 @@ class AssignPositives(torch.autograd.Function):
         md0, md1, sim, lse_row, lse_col, gt_u8, rowcnt, colcnt = ctx.saved_tensors
         B, M, N = sim.shape
         g = g.float().contiguous()
-        a_row = (g[:, None] * rowcnt).contiguous()
-        a_col = (g[:, None] * colcnt).contiguous()
         tc = ctx.bf16 and N % 8 == 0 and M % 8 == 0
         dsim = torch.empty(B, M, N, device=sim.device, dtype=torch.bfloat16 if tc else torch.float32)
-        call("lgb200_assign_bwd", ptr(sim), ptr(lse_row), ptr(lse_col), ptr(gt_u8), ptr(g), ptr(a_row), ptr(a_col),
+        call("lgb200_assign_bwd", ptr(sim), ptr(lse_row), ptr(lse_col), ptr(gt_u8), ptr(g), ptr(rowcnt), ptr(colcnt),
              ptr(dsim), _code(dsim.dtype), B, M, N, stream_ptr())
         if tc:
             b0 = md0.to(torch.bfloat16).contiguous()
@@ -268,6 +266,14 @@ class AssignPositives(torch.autograd.Function):
             dmd0 = torch.bmm(dsim, md1.float())
             dmd1 = torch.bmm(dsim.transpose(1, 2), md0.float())
         return dmd0.to(md0.dtype), dmd1.to(md1.dtype), None, None, None, None, None, None, None, None
+
+
+def head_logsig(zt):
+    T = zt.shape[0]
+    ls = torch.empty(T, device=zt.device, dtype=torch.float32)
+    du = torch.empty_like(ls)
+    call("lgb200_head_logsig", ptr(zt), ptr(ls), ptr(du), T, stream_ptr())
+    return ls, du
 
 
 def filter_matches(rowmax, rowarg, colarg, th):

@@ -113,14 +113,35 @@ int lgb200_assign_scores(const float* sim, const float* lse_row, const float* ls
                          const float* ls1, const float* dust0, const float* dust1, const uint8_t* gt, float* scores,
                          float* rowmax, int* rowarg, float* colmax, int* colarg, float* pos_row_sum,
                          float* row_expsum, void* ws, int B, int M, int N, cudaStream_t stream);
-/* backward of sum_ij gt_ij (2 sim_ij - lse_row_i - lse_col_j) scaled by gcoef[b]:
- *   dsim_ij = 2 gcoef_b gt_ij - exp(sim_ij-lse_row_i) a_row_i - exp(sim_ij-lse_col_j) a_col_j          */
+/* backward of sum_ij gt_ij (2 sim_ij - lse_row_i - lse_col_j) scaled by gcoef[b]
+ * (rowcnt_i = sum_j gt_ij, colcnt_j = sum_i gt_ij, as floats):
+ *   dsim_ij = gcoef_b (2 gt_ij - exp(sim_ij-lse_row_i) rowcnt_i - exp(sim_ij-lse_col_j) colcnt_j)     */
 int lgb200_assign_bwd(const float* sim, const float* lse_row, const float* lse_col, const uint8_t* gt,
-                      const float* gcoef, const float* a_row, const float* a_col, void* dsim, int out_dtype, int B,
+                      const float* gcoef, const float* rowcnt, const float* colcnt, void* dsim, int out_dtype, int B,
                       int M, int N, cudaStream_t stream);
 /* filter_matches (lightglue.py:293-309): mutual check + threshold; m0,m1 int64, -1 = no match       */
 int lgb200_filter_matches(const float* rowmax, const int* rowarg, const int* colarg, float th, int64_t* m0,
                           int64_t* m1, float* ms0, float* ms1, int B, int M, int N, cudaStream_t stream);
+
+/* O(M+N) terms of one supervised layer (replaces the logsigmoid / weighted-sum / clamp / BCE tensor ops of
+ * lightglue.py:264-267, losses.py:13-25, lightglue.py:81-94).  zt [T,2] = per token (matchability logit,
+ * token-confidence logit), tokens ordered [image0 (B*M); image1 (B*N)].
+ *   head_logsig   : ls = log sigmoid(z), du = log sigmoid(-z)                      [T] each
+ *   head_terms_fwd: nll_pos = -(sum pos_row_sum + sum rowcnt ls0 + sum colcnt ls1)/num_pos,
+ *                   nll_neg = -(sum neg0 du0 + sum neg1 du1)/num_neg, nll = bal nll_pos + (1-bal) nll_neg,
+ *                   conf = token-confidence BCE against [argmax incl. dustbin == fin] (0 when fin* NULL)
+ *   head_terms_bwd: d zt for upstream g_nll[B], g_conf[B]                                           */
+int lgb200_head_logsig(const float* zt, float* ls, float* du, int64_t T, cudaStream_t stream);
+int lgb200_head_terms_fwd(const float* zt, const float* pos_row_sum, const float* rowcnt, const float* colcnt,
+                          const float* neg0, const float* neg1, const float* rowmax, const int* rowarg,
+                          const float* colmax, const int* colarg, const int* fin0, const int* fin1,
+                          const float* num_pos, const float* num_neg, float bal, float* nll, float* nll_pos,
+                          float* nll_neg, float* conf, int B, int M, int N, cudaStream_t stream);
+int lgb200_head_terms_bwd(const float* zt, const float* rowcnt, const float* colcnt, const float* neg0,
+                          const float* neg1, const float* rowmax, const int* rowarg, const float* colmax,
+                          const int* colarg, const int* fin0, const int* fin1, const float* num_pos,
+                          const float* num_neg, float bal, const float* g_nll, const float* g_conf, float* dzt, int B,
+                          int M, int N, cudaStream_t stream);
 
 /* ---- other assignment heads on the path ----------------------------------------------------------
  * log_double_softmax with a learned bin (gluestick.py:772-783) and log-domain Sinkhorn optimal
