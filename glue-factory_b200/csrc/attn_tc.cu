@@ -420,15 +420,25 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
     const int tid = threadIdx.x;             // 0..255
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int sw = r & 7;
+    // lse (pre-multiplied by log2 e) / delta of the 64 queries of a tile are staged through smem one tile
+    // ahead: threads 0-63 carry lse, 64-127 delta; the global load of tile i+1 is issued at the top of
+    // iteration i and lands in smem at its end, so no load latency sits between two tiles.
+    auto fetch = [&](int i) -> float {
+      const int qi = i * FB_C + (tid & 63);
+      const int64_t o = ((int64_t)qb * H + h) * Nq + (qi < Nq ? qi : 0);
+      if (tid < 64) return (i < ntiles && qi < Nq) ? lse[o] * 1.4426950408889634f : INFINITY;
+      return (i < ntiles && qi < Nq) ? delta[o] : 0.f;
+    };
+    auto stage = [&](int i, float val) {
+      if (tid < 64) sLse[(i & 1) * FB_C + tid] = val;
+      else if (tid < 128) sDel[(i & 1) * FB_C + (tid - 64)] = val;
+    };
+    float pre = 0.f;
+    if (tid < 128) stage(0, fetch(0));
     for (int i = 0; i < ntiles; ++i) {
       const int buf = i & 1;
-      {  // stage lse (pre-multiplied by log2 e) and delta of the 64 queries of this tile
-        const int qi = i * FB_C + (tid & 63);
-        const int64_t o = ((int64_t)qb * H + h) * Nq + qi;
-        if (tid < 64) sLse[buf * FB_C + tid] = qi < Nq ? lse[o] * 1.4426950408889634f : INFINITY;
-        else if (tid < 128) sDel[buf * FB_C + (tid - 64)] = qi < Nq ? delta[o] : 0.f;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid < 128) pre = fetch(i + 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // smem[buf] written at the end of the previous iteration
       mbar_wait(&sp_full[buf], (i >> 1) & 1);
       tc_fence_after();
       float sv[32], dp[32];
@@ -447,6 +457,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[buf]);
+      if (tid < 128 && i + 1 < ntiles) stage(i + 1, pre);
     }
     mbar_wait(acc_done, 0);
     tc_fence_after();
@@ -597,6 +608,370 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   if (warp == 9) tmem_dealloc(tmem_base, FB_TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// BACKWARD v3: every A operand lives in tensor memory.
+//   * the CTA's resident 128-row operands (K,V for dKV; Q,dO for dQ) are written once into TMEM
+//     (bf16, two K-elements per 32-bit column) and feed the S / dP MMAs as TMEM A operands;
+//   * P^T / dS^T (dKV) and dS (dQ) are written by the softmax warps with tcgen05.st IN PLACE over
+//     the S / dP columns they were computed from (each warpgroup over its own 32-column half), and
+//     feed the accumulating MMAs as TMEM A operands.
+// Shared memory then carries only the streamed 64-row B tiles: ~3x less smem traffic per tile than
+// v2 (the v2 kernels were shared-memory-bandwidth bound: 6 KB of operand reads per 32-cycle MMA),
+// and the generic->async proxy fence of the P hand-off disappears.
+// TMEM columns: A0 [0,32) A1 [32,64) | buffer b: S at 64+b*128, dP at 128+b*128 | accumulators at 320, 384.
+// ---------------------------------------------------------------------------------------------
+constexpr int F3_A0 = 0, F3_A1 = 32, F3_BUF0 = 64, F3_ACC0 = 320, F3_ACC1 = 384;
+constexpr int F3_NWG = 4;                    // softmax warpgroups; each owns 64 / F3_NWG columns of a tile
+constexpr int F3_CW = FB_C / F3_NWG;         // 16 columns per warpgroup
+constexpr int F3_SWARPS = 4 * F3_NWG;        // 16 softmax warps: latency hiding for the exp / pack chain
+constexpr int F3_THREADS = (F3_SWARPS + 2) * 32;
+constexpr int F3_STAGES = 8;  // 128 KiB of staging: deep TMA prefetch, and forces one CTA per SM (TMEM = 512 columns)
+constexpr int F3_SMEM = F3_STAGES * 2 * FB_CBYTES + 2 * 2 * FB_C * 4 + 256;
+
+__device__ __forceinline__ void store_out_cols16(__nv_bfloat16* dst, uint32_t taddr, bool valid) {
+  float v[16];
+  tmem_ld16(taddr, v);
+  tmem_ld_wait();
+  if (!valid) return;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    uint4 u;
+    u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+    u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+    *reinterpret_cast<uint4*>(dst + g * 8) = u;
+  }
+}
+
+__device__ __forceinline__ void load_row_part_to_tmem(const __nv_bfloat16* row_ptr, bool valid, uint32_t taddr) {
+  // 16 bf16 (32 B) of this thread's row -> 8 packed TMEM columns
+  uint32_t w[8];
+  if (valid) {
+    const uint4* src = reinterpret_cast<const uint4*>(row_ptr);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const uint4 u = src[g];
+      w[g * 4 + 0] = u.x; w[g * 4 + 1] = u.y; w[g * 4 + 2] = u.z; w[g * 4 + 3] = u.w;
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) w[g] = 0u;
+  }
+  tmem_st8(taddr, w);
+}
+static_assert(F3_NWG == 4, "the v3 backward kernels are written for 4 softmax warpgroups of 16 columns");
+
+__global__ void __launch_bounds__(F3_THREADS, 1)
+    attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                           const __nv_bfloat16* __restrict__ kg, const __nv_bfloat16* __restrict__ vg,
+                           const float* __restrict__ lse, const float* __restrict__ delta,
+                           __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int B, int Nq, int Nk,
+                           int H, int kv_shift, float scale, float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;                                // [F3_STAGES]
+  uint8_t* sDO = sQ + F3_STAGES * FB_CBYTES;         // [F3_STAGES]
+  float* sLse = reinterpret_cast<float*>(sDO + F3_STAGES * FB_CBYTES);  // [2][64]
+  float* sDel = sLse + 2 * FB_C;                                        // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDel + 2 * FB_C);
+  uint64_t* a_ready = bars;
+  uint64_t* in_full = bars + 1;               // [F3_STAGES]
+  uint64_t* in_empty = in_full + F3_STAGES;   // [F3_STAGES]
+  uint64_t* sp_full = in_empty + F3_STAGES;   // [2]
+  uint64_t* pds_full = sp_full + 2;           // [2]
+  uint64_t* acc_done = pds_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * FB_R, h = blockIdx.y, kb = blockIdx.z;
+  const int qb = ((kb - kv_shift) % B + B) % B;
+  const int ntiles = (Nq + FB_C - 1) / FB_C;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(a_ready, F3_SWARPS);
+    for (int s = 0; s < F3_STAGES; ++s) {
+      mbar_init(&in_full[s], 1);
+      mbar_init(&in_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sp_full[s], 1);
+      mbar_init(&pds_full[s], F3_SWARPS);
+    }
+    mbar_init(acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == F3_SWARPS && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+  }
+  if (warp == F3_SWARPS + 1) tmem_alloc(tmem_slot, FB_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == F3_SWARPS) {
+    if (lane == 0) {
+      for (int i = 0; i < ntiles; ++i) {
+        const int s = i % F3_STAGES;
+        mbar_wait(&in_empty[s], ((i / F3_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&in_full[s], 2 * FB_CBYTES);
+        tma_load_4d(sQ + s * FB_CBYTES, &tmQ, &in_full[s], 0, h, i * FB_C, qb);
+        tma_load_4d(sDO + s * FB_CBYTES, &tmDO, &in_full[s], 0, h, i * FB_C, qb);
+      }
+    }
+  } else if (warp == F3_SWARPS + 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (K|V) in TMEM x (Q|dO) K-major
+      constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // (P^T|dS^T) in TMEM x (dO|Q) MN-major
+      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO);
+      auto issue_sp = [&](int i) {
+        const int s = i % F3_STAGES;
+        const uint32_t tb = tmem_base + F3_BUF0 + (i & 1) * 128;
+        mbar_wait(&in_full[s], (i / F3_STAGES) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16_ts(tb, tmem_base + F3_A0 + kk * 8, make_smem_desc(aQ + s * FB_CBYTES + kk * 32, 16, 1024),
+                       idesc_s, kk != 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16_ts(tb + 64, tmem_base + F3_A1 + kk * 8, make_smem_desc(aDO + s * FB_CBYTES + kk * 32, 16, 1024),
+                       idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(&sp_full[i & 1]);
+      };
+      mbar_wait(a_ready, 0);
+      tc_fence_after();
+      issue_sp(0);
+      if (ntiles > 1) issue_sp(1);
+      for (int i = 0; i < ntiles; ++i) {
+        const int s = i % F3_STAGES;
+        const uint32_t tb = tmem_base + F3_BUF0 + (i & 1) * 128;
+        mbar_wait(&pds_full[i & 1], (i >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < FB_C / 16; ++kk)  // P^T of queries [kk*16, kk*16+16): half kk/2, 8 columns each
+          umma_bf16_ts(tmem_base + F3_ACC0, tb + ((kk * 16) / F3_CW) * F3_CW + ((kk * 16) % F3_CW) / 2,
+                       make_smem_desc(aDO + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (i | kk) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < FB_C / 16; ++kk)
+          umma_bf16_ts(tmem_base + F3_ACC1, tb + 64 + ((kk * 16) / F3_CW) * F3_CW + ((kk * 16) % F3_CW) / 2,
+                       make_smem_desc(aQ + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (i | kk) != 0 ? 1u : 0u);
+        umma_commit(&in_empty[s]);
+        if (i + 2 < ntiles) issue_sp(i + 2);
+      }
+      umma_commit(acc_done);
+    }
+  } else {
+    const int c = warp >> 2;                 // column half handled by this warpgroup
+    const int r = (warp & 3) * 32 + lane;    // key row within the tile == TMEM lane
+    const int tid = threadIdx.x;             // 0..511
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const int row = k0 + r;
+    {  // resident A operands: this thread's half row of K and V -> TMEM
+      const int64_t o = (((int64_t)kb * Nk + (row < Nk ? row : 0)) * H + h) * FA_D + c * F3_CW;
+      load_row_part_to_tmem(kg + o, row < Nk, t_lane + F3_A0 + c * (F3_CW / 2));
+      load_row_part_to_tmem(vg + o, row < Nk, t_lane + F3_A1 + c * (F3_CW / 2));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    }
+    auto fetch = [&](int i) -> float {
+      const int qi = i * FB_C + (tid & 63);
+      const int64_t o = ((int64_t)qb * H + h) * Nq + (qi < Nq ? qi : 0);
+      if (tid < 64) return (i < ntiles && qi < Nq) ? lse[o] * 1.4426950408889634f : INFINITY;
+      return (i < ntiles && qi < Nq) ? delta[o] : 0.f;
+    };
+    auto stage = [&](int i, float val) {
+      if (tid < 64) sLse[(i & 1) * FB_C + tid] = val;
+      else if (tid < 128) sDel[(i & 1) * FB_C + (tid - 64)] = val;
+    };
+    float pre = 0.f;
+    if (tid < 128) stage(0, fetch(0));
+    for (int i = 0; i < ntiles; ++i) {
+      const int buf = i & 1;
+      const uint32_t tb = t_lane + F3_BUF0 + buf * 128;
+      if (tid < 128) pre = fetch(i + 1);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      mbar_wait(&sp_full[buf], (i >> 1) & 1);
+      tc_fence_after();
+      float sv[F3_CW], dp[F3_CW];
+      tmem_ld16(tb + c * F3_CW, sv);
+      tmem_ld16(tb + 64 + c * F3_CW, dp);
+      tmem_ld_wait();
+      uint32_t pw[F3_CW / 2], dw[F3_CW / 2];
+#pragma unroll
+      for (int e = 0; e < F3_CW; e += 2) {
+        const float p0 = fast_exp2(fmaf(sv[e], scale_log2, -sLse[buf * FB_C + c * F3_CW + e]));
+        const float p1 = fast_exp2(fmaf(sv[e + 1], scale_log2, -sLse[buf * FB_C + c * F3_CW + e + 1]));
+        const float d0 = p0 * (dp[e] - sDel[buf * FB_C + c * F3_CW + e]) * scale;
+        const float d1 = p1 * (dp[e + 1] - sDel[buf * FB_C + c * F3_CW + e + 1]) * scale;
+        pw[e >> 1] = pack_bf16(p0, p1);
+        dw[e >> 1] = pack_bf16(d0, d1);
+      }
+      tmem_st8(tb + c * F3_CW, pw);        // P^T over the S columns this warpgroup just consumed
+      tmem_st8(tb + 64 + c * F3_CW, dw);   // dS^T over the dP columns
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pds_full[buf]);
+      if (tid < 128 && i + 1 < ntiles) stage(i + 1, pre);
+    }
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    const int64_t o = (((int64_t)kb * Nk + (row < Nk ? row : 0)) * H + h) * FA_D + c * F3_CW;
+    store_out_cols16(dv + o, t_lane + F3_ACC0 + c * F3_CW, row < Nk);
+    store_out_cols16(dk + o, t_lane + F3_ACC1 + c * F3_CW, row < Nk);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == F3_SWARPS + 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
+}
+
+__global__ void __launch_bounds__(F3_THREADS, 1)
+    attn_bwd_dq_v3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                          const __nv_bfloat16* __restrict__ qg, const __nv_bfloat16* __restrict__ dog,
+                          const float* __restrict__ lse, const float* __restrict__ delta,
+                          __nv_bfloat16* __restrict__ dq, int B, int Nq, int Nk, int H, int kv_shift, float scale,
+                          float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;                                // [F3_STAGES]
+  uint8_t* sV = sK + F3_STAGES * FB_CBYTES;          // [F3_STAGES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + F3_STAGES * FB_CBYTES + 1024);
+  uint64_t* a_ready = bars;
+  uint64_t* in_full = bars + 1;
+  uint64_t* in_empty = in_full + F3_STAGES;
+  uint64_t* sp_full = in_empty + F3_STAGES;   // [2]
+  uint64_t* ds_full = sp_full + 2;            // [2]
+  uint64_t* acc_done = ds_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * FB_R, h = blockIdx.y, b = blockIdx.z;
+  const int kb = (b + kv_shift) % B;
+  const int ntiles = (Nk + FB_C - 1) / FB_C;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(a_ready, F3_SWARPS);
+    for (int s = 0; s < F3_STAGES; ++s) {
+      mbar_init(&in_full[s], 1);
+      mbar_init(&in_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sp_full[s], 1);
+      mbar_init(&ds_full[s], F3_SWARPS);
+    }
+    mbar_init(acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == F3_SWARPS && lane == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == F3_SWARPS + 1) tmem_alloc(tmem_slot, FB_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == F3_SWARPS) {
+    if (lane == 0) {
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % F3_STAGES;
+        mbar_wait(&in_empty[s], ((j / F3_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&in_full[s], 2 * FB_CBYTES);
+        tma_load_4d(sK + s * FB_CBYTES, &tmK, &in_full[s], 0, h, j * FB_C, kb);
+        tma_load_4d(sV + s * FB_CBYTES, &tmV, &in_full[s], 0, h, j * FB_C, kb);
+      }
+    }
+  } else if (warp == F3_SWARPS + 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (Q|dO) in TMEM x (K|V) K-major
+      constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // dS in TMEM x K_j MN-major
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+      auto issue_sp = [&](int j) {
+        const int s = j % F3_STAGES;
+        const uint32_t tb = tmem_base + F3_BUF0 + (j & 1) * 128;
+        mbar_wait(&in_full[s], (j / F3_STAGES) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16_ts(tb, tmem_base + F3_A0 + kk * 8, make_smem_desc(aK + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s,
+                       kk != 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16_ts(tb + 64, tmem_base + F3_A1 + kk * 8, make_smem_desc(aV + s * FB_CBYTES + kk * 32, 16, 1024),
+                       idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(&sp_full[j & 1]);
+      };
+      mbar_wait(a_ready, 0);
+      tc_fence_after();
+      issue_sp(0);
+      if (ntiles > 1) issue_sp(1);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % F3_STAGES;
+        const uint32_t tb = tmem_base + F3_BUF0 + (j & 1) * 128;
+        mbar_wait(&ds_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < FB_C / 16; ++kk)  // dS of keys [kk*16, kk*16+16) sits in the dP columns
+          umma_bf16_ts(tmem_base + F3_ACC0, tb + 64 + ((kk * 16) / F3_CW) * F3_CW + ((kk * 16) % F3_CW) / 2,
+                       make_smem_desc(aK + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0 ? 1u : 0u);
+        umma_commit(&in_empty[s]);
+        if (j + 2 < ntiles) issue_sp(j + 2);
+      }
+      umma_commit(acc_done);
+    }
+  } else {
+    const int c = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const int row = q0 + r;
+    {
+      const int64_t o = (((int64_t)b * Nq + (row < Nq ? row : 0)) * H + h) * FA_D + c * F3_CW;
+      load_row_part_to_tmem(qg + o, row < Nq, t_lane + F3_A0 + c * (F3_CW / 2));
+      load_row_part_to_tmem(dog + o, row < Nq, t_lane + F3_A1 + c * (F3_CW / 2));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    }
+    const int64_t lo = ((int64_t)b * H + h) * Nq + (row < Nq ? row : 0);
+    const float lse2 = row < Nq ? lse[lo] * 1.4426950408889634f : INFINITY;
+    const float dl = row < Nq ? delta[lo] : 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      const int buf = j & 1;
+      const uint32_t tb = t_lane + F3_BUF0 + buf * 128;
+      mbar_wait(&sp_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      float sv[F3_CW], dp[F3_CW];
+      tmem_ld16(tb + c * F3_CW, sv);
+      tmem_ld16(tb + 64 + c * F3_CW, dp);
+      tmem_ld_wait();
+      uint32_t dw[F3_CW / 2];
+#pragma unroll
+      for (int e = 0; e < F3_CW; e += 2) {
+        const float p0 = fast_exp2(fmaf(sv[e], scale_log2, -lse2));
+        const float p1 = fast_exp2(fmaf(sv[e + 1], scale_log2, -lse2));
+        dw[e >> 1] = pack_bf16(p0 * (dp[e] - dl) * scale, p1 * (dp[e + 1] - dl) * scale);
+      }
+      tmem_st8(tb + 64 + c * F3_CW, dw);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ds_full[buf]);
+    }
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    store_out_cols16(dq + (((int64_t)b * Nq + (row < Nq ? row : 0)) * H + h) * FA_D + c * F3_CW,
+                     t_lane + F3_ACC0 + c * F3_CW, row < Nq);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == F3_SWARPS + 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
+}
+
 int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
                 void* dq, void* dk, void* dv, float* delta, int B, int Nq, int Nk, int H, int kv_shift, float scale,
                 cudaStream_t stream) {
@@ -611,6 +986,28 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, co
     configured = true;
   }
   const float sl2 = scale * 1.4426950408889634f;
+  if (!env_flag("LGB200_ATTN_BWD_V2")) {
+    static bool configured3 = false;
+    if (!configured3) {
+      cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
+      LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      e = cudaFuncSetAttribute(attn_bwd_dq_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
+      LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      configured3 = true;
+    }
+    CUtensorMap tq, tk, tv, tdo;
+    if ((rc = make_qkv_tmap(&tk, k, B, Nk, H, FB_C))) return rc;
+    if ((rc = make_qkv_tmap(&tv, v, B, Nk, H, FB_C))) return rc;
+    attn_bwd_dq_v3_kernel<<<dim3((Nq + FB_R - 1) / FB_R, H, B), F3_THREADS, F3_SMEM, stream>>>(
+        tk, tv, static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(dout), lse, delta,
+        static_cast<__nv_bfloat16*>(dq), B, Nq, Nk, H, kv_shift, scale, sl2);
+    if ((rc = make_qkv_tmap(&tq, q, B, Nq, H, FB_C))) return rc;
+    if ((rc = make_qkv_tmap(&tdo, dout, B, Nq, H, FB_C))) return rc;
+    attn_bwd_dkv_v3_kernel<<<dim3((Nk + FB_R - 1) / FB_R, H, B), F3_THREADS, F3_SMEM, stream>>>(
+        tq, tdo, static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v), lse, delta,
+        static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv), B, Nq, Nk, H, kv_shift, scale, sl2);
+    return check_launch("attn_bwd_tc(v3)");
+  }
   {
     CUtensorMap tq, tk, tv, tdo;
     if ((rc = make_qkv_tmap(&tq, q, B, Nq, H, FB_R))) return rc;
