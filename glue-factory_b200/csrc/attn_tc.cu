@@ -110,35 +110,46 @@ __global__ void __launch_bounds__(192, 2)
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(FA_BM, FA_BN, 0, 0);  // Q (K-major) x K_j (K-major)
-      constexpr uint32_t idesc_o = make_idesc_bf16(FA_BM, FA_D, 0, 1);   // P (K-major) x V_j (MN-major)
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
-      auto issue_s = [&](int j) {
-        const int s = j % FA_STAGES;
-        mbar_wait(&kv_full[s], (j / FA_STAGES) & 1);
-        tc_fence_after();
+    // The whole warp runs the loop (waits, descriptor arithmetic stay warp-uniform -> uniform registers);
+    // one elected lane issues the tcgen05 instructions.
+    constexpr uint32_t idesc_s = make_idesc_bf16(FA_BM, FA_BN, 0, 0);  // Q (K-major) x K_j (K-major)
+    constexpr uint32_t idesc_o = make_idesc_bf16(FA_BM, FA_D, 0, 1);   // P (K-major) x V_j (MN-major)
+    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+    const uint64_t dQ0 = make_smem_desc(aQ, 16, 1024), dK0 = make_smem_desc(aK, 16, 1024);
+    const uint64_t dP0 = make_smem_desc(aP, 16, 1024), dV0 = make_smem_desc(aV, 8192, 1024);
+    const bool leader = elect_one();
+    auto issue_s = [&](int j) {
+      const int s = j % FA_STAGES;
+      mbar_wait(&kv_full[s], (j / FA_STAGES) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint64_t dk = dK0 + (uint64_t)((s * FA_KBYTES) >> 4);
+        const uint32_t d = tmem_base + FA_S_COL + (j & 1) * FA_BN;
 #pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16(tmem_base + FA_S_COL + (j & 1) * FA_BN, make_smem_desc(aQ + kk * 32, 16, 1024),
-                    make_smem_desc(aK + s * FA_KBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
+        for (int kk = 0; kk < FA_D / 16; ++kk) umma_bf16(d, dQ0 + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
         umma_commit(&s_full[j & 1]);
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      if (ntiles > 1) issue_s(1);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % FA_STAGES;
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    if (ntiles > 1) issue_s(1);
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = j % FA_STAGES;
+      mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint64_t dp = dP0 + (uint64_t)(((j & 1) * FA_PBYTES) >> 4);
+        const uint64_t dv = dV0 + (uint64_t)((s * FA_KBYTES) >> 4);
+        const uint32_t d = tmem_base + FA_O_COL + (j & 1) * FA_D;
 #pragma unroll
         for (int kk = 0; kk < FA_BN / 16; ++kk)
-          umma_bf16(tmem_base + FA_O_COL + (j & 1) * FA_D, make_smem_desc(aP + (j & 1) * FA_PBYTES + kk * 32, 16, 1024),
-                    make_smem_desc(aV + s * FA_KBYTES + kk * 2048, 8192, 1024), idesc_o, kk != 0 ? 1u : 0u);
+          umma_bf16(d, dp + (uint64_t)(kk * 2), dv + (uint64_t)(kk * 128), idesc_o, kk != 0 ? 1u : 0u);
         umma_commit(&kv_empty[s]);
         umma_commit(&o_full[j & 1]);
-        if (j + 2 < ntiles) issue_s(j + 2);
       }
+      __syncwarp();
+      if (j + 2 < ntiles) issue_s(j + 2);
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroup
@@ -249,7 +260,7 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* l
 
 // ---------------------------------------------------------------------------------------------
 // BACKWARD.  Two kernels, both deterministic (no atomics), both with the forward's structure
-// (TMA producer warp, single-thread MMA issuer, 4 softmax warps with thread == TMEM lane == row):
+// (TMA producer warp, MMA issuer warp, softmax warps with thread == TMEM lane == row):
 //
 //   dKV kernel: CTA owns 128 keys (rows), walks the queries in tiles of 64:
 //       S^T  = K  Q_i^T   (128 x 64)      dP^T = V dO_i^T   (128 x 64)
@@ -269,344 +280,8 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* l
 // ---------------------------------------------------------------------------------------------
 constexpr int FB_R = 128;            // rows owned by the CTA
 constexpr int FB_C = 64;             // inner tile
-constexpr int FB_RBYTES = FB_R * FA_D * 2;  // 16 KiB
 constexpr int FB_CBYTES = FB_C * FA_D * 2;  // 8 KiB
-constexpr int FB_PBYTES = FB_R * FB_C * 2;  // 16 KiB (128 rows x 64 bf16 = one swizzle block per row)
-constexpr int FB_STAGES = 5;
-constexpr int FB_THREADS = 320;      // warps 0-7 softmax (two warpgroups, 32 columns each), 8 TMA, 9 MMA
 constexpr int FB_TMEM_COLS = 512;
-// TMEM columns: S/dP double-buffered at [b*128, b*128+64) / [b*128+64, b*128+128), accumulators behind
-constexpr int FB_ACC0_COL = 256, FB_ACC1_COL = 320;
-constexpr int FB_DKV_SMEM = 2 * FB_RBYTES + FB_STAGES * 2 * FB_CBYTES + 4 * FB_PBYTES + 2 * 2 * FB_C * 4 + 256;
-constexpr int FB_DQ_SMEM = 2 * FB_RBYTES + FB_STAGES * 2 * FB_CBYTES + 2 * FB_PBYTES + 256;
-
-__device__ __forceinline__ void store_row_chunk32(uint8_t* row_base, int sw, int c, const float* v) {
-  // 32 consecutive columns [c*32, c*32+32) of a 64-column bf16 row (128 B, swizzled 16-byte chunks)
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    uint4 u;
-    u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-    u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-    const int chunk = c * 4 + g;
-    *reinterpret_cast<uint4*>(row_base + ((chunk ^ sw) << 4)) = u;
-  }
-}
-
-__device__ __forceinline__ void store_out_cols32(__nv_bfloat16* dst, uint32_t taddr, bool valid) {
-  // 32 fp32 TMEM columns of this thread's lane -> 32 bf16 (64 contiguous bytes) in global memory.
-  // The TMEM load is warp-collective: every lane executes it, only valid rows store.
-  float v[32];
-  tmem_ld32(taddr, v);
-  tmem_ld_wait();
-  if (!valid) return;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    uint4 u;
-    u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-    u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-    *reinterpret_cast<uint4*>(dst + g * 8) = u;
-  }
-}
-
-__global__ void __launch_bounds__(FB_THREADS, 1)
-    attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-                           const float* __restrict__ lse, const float* __restrict__ delta,
-                           __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int B, int Nq, int Nk,
-                           int H, int kv_shift, float scale, float scale_log2) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sK = smem;
-  uint8_t* sV = sK + FB_RBYTES;
-  uint8_t* sQ = sV + FB_RBYTES;                      // [FB_STAGES]
-  uint8_t* sDO = sQ + FB_STAGES * FB_CBYTES;         // [FB_STAGES]
-  uint8_t* sP = sDO + FB_STAGES * FB_CBYTES;         // [2]
-  uint8_t* sDS = sP + 2 * FB_PBYTES;                 // [2]
-  float* sLse = reinterpret_cast<float*>(sDS + 2 * FB_PBYTES);  // [2][64]
-  float* sDel = sLse + 2 * FB_C;                                // [2][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDel + 2 * FB_C);
-  uint64_t* kv_full = bars;
-  uint64_t* in_full = bars + 1;               // [FB_STAGES]
-  uint64_t* in_empty = in_full + FB_STAGES;   // [FB_STAGES]
-  uint64_t* sp_full = in_empty + FB_STAGES;   // [2]
-  uint64_t* pds_full = sp_full + 2;           // [2]
-  uint64_t* acc_done = pds_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k0 = blockIdx.x * FB_R, h = blockIdx.y, kb = blockIdx.z;
-  const int qb = ((kb - kv_shift) % B + B) % B;
-  const int ntiles = (Nq + FB_C - 1) / FB_C;
-
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(kv_full, 1);
-    for (int s = 0; s < FB_STAGES; ++s) {
-      mbar_init(&in_full[s], 1);
-      mbar_init(&in_empty[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&sp_full[s], 1);
-      mbar_init(&pds_full[s], 8);
-    }
-    mbar_init(acc_done, 1);
-    mbar_fence_init();
-  }
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
-  }
-  if (warp == 9) tmem_alloc(tmem_slot, FB_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 8) {
-    if (lane == 0) {
-      mbar_expect_tx(kv_full, 2 * FB_RBYTES);
-      tma_load_4d(sK, &tmK, kv_full, 0, h, k0, kb);
-      tma_load_4d(sV, &tmV, kv_full, 0, h, k0, kb);
-      for (int i = 0; i < ntiles; ++i) {
-        const int s = i % FB_STAGES;
-        mbar_wait(&in_empty[s], ((i / FB_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&in_full[s], 2 * FB_CBYTES);
-        tma_load_4d(sQ + s * FB_CBYTES, &tmQ, &in_full[s], 0, h, i * FB_C, qb);
-        tma_load_4d(sDO + s * FB_CBYTES, &tmDO, &in_full[s], 0, h, i * FB_C, qb);
-      }
-    }
-  } else if (warp == 9) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (K|V) K-major x (Q|dO) K-major
-      constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // (P^T|dS^T) K-major x (dO|Q) MN-major
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aDO = smem_u32(sDO);
-      const uint32_t aP = smem_u32(sP), aDS = smem_u32(sDS);
-      auto issue_sp = [&](int i) {  // S^T and dP^T of query tile i into TMEM buffer i&1
-        const int s = i % FB_STAGES;
-        const uint32_t tb = tmem_base + (i & 1) * 128;
-        mbar_wait(&in_full[s], (i / FB_STAGES) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16(tb, make_smem_desc(aK + kk * 32, 16, 1024),
-                    make_smem_desc(aQ + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16(tb + 64, make_smem_desc(aV + kk * 32, 16, 1024),
-                    make_smem_desc(aDO + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(&sp_full[i & 1]);
-      };
-      mbar_wait(kv_full, 0);
-      issue_sp(0);
-      if (ntiles > 1) issue_sp(1);
-      for (int i = 0; i < ntiles; ++i) {
-        const int s = i % FB_STAGES;
-        mbar_wait(&pds_full[i & 1], (i >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < FB_C / 16; ++kk)  // contraction over the 64 queries of this tile
-          umma_bf16(tmem_base + FB_ACC0_COL, make_smem_desc(aP + (i & 1) * FB_PBYTES + kk * 32, 16, 1024),
-                    make_smem_desc(aDO + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (i | kk) != 0 ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < FB_C / 16; ++kk)
-          umma_bf16(tmem_base + FB_ACC1_COL, make_smem_desc(aDS + (i & 1) * FB_PBYTES + kk * 32, 16, 1024),
-                    make_smem_desc(aQ + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (i | kk) != 0 ? 1u : 0u);
-        umma_commit(&in_empty[s]);
-        if (i + 2 < ntiles) issue_sp(i + 2);
-      }
-      umma_commit(acc_done);
-    }
-  } else {
-    const int c = warp >> 2;                 // column half handled by this warpgroup
-    const int r = (warp & 3) * 32 + lane;    // key row within the tile == TMEM lane
-    const int tid = threadIdx.x;             // 0..255
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const int sw = r & 7;
-    // lse (pre-multiplied by log2 e) / delta of the 64 queries of a tile are staged through smem one tile
-    // ahead: threads 0-63 carry lse, 64-127 delta; the global load of tile i+1 is issued at the top of
-    // iteration i and lands in smem at its end, so no load latency sits between two tiles.
-    auto fetch = [&](int i) -> float {
-      const int qi = i * FB_C + (tid & 63);
-      const int64_t o = ((int64_t)qb * H + h) * Nq + (qi < Nq ? qi : 0);
-      if (tid < 64) return (i < ntiles && qi < Nq) ? lse[o] * 1.4426950408889634f : INFINITY;
-      return (i < ntiles && qi < Nq) ? delta[o] : 0.f;
-    };
-    auto stage = [&](int i, float val) {
-      if (tid < 64) sLse[(i & 1) * FB_C + tid] = val;
-      else if (tid < 128) sDel[(i & 1) * FB_C + (tid - 64)] = val;
-    };
-    float pre = 0.f;
-    if (tid < 128) stage(0, fetch(0));
-    for (int i = 0; i < ntiles; ++i) {
-      const int buf = i & 1;
-      if (tid < 128) pre = fetch(i + 1);
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // smem[buf] written at the end of the previous iteration
-      mbar_wait(&sp_full[buf], (i >> 1) & 1);
-      tc_fence_after();
-      float sv[32], dp[32];
-      tmem_ld32(t_lane + buf * 128 + c * 32, sv);
-      tmem_ld32(t_lane + buf * 128 + 64 + c * 32, dp);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const float p = fast_exp2(fmaf(sv[e], scale_log2, -sLse[buf * FB_C + c * 32 + e]));
-        dp[e] = p * (dp[e] - sDel[buf * FB_C + c * 32 + e]) * scale;
-        sv[e] = p;
-      }
-      store_row_chunk32(sP + buf * FB_PBYTES + r * 128, sw, c, sv);
-      store_row_chunk32(sDS + buf * FB_PBYTES + r * 128, sw, c, dp);
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&pds_full[buf]);
-      if (tid < 128 && i + 1 < ntiles) stage(i + 1, pre);
-    }
-    mbar_wait(acc_done, 0);
-    tc_fence_after();
-    const int row = k0 + r;
-    const int64_t o = (((int64_t)kb * Nk + (row < Nk ? row : 0)) * H + h) * FA_D + c * 32;
-    store_out_cols32(dv + o, t_lane + FB_ACC0_COL + c * 32, row < Nk);
-    store_out_cols32(dk + o, t_lane + FB_ACC1_COL + c * 32, row < Nk);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, FB_TMEM_COLS);
-}
-
-__global__ void __launch_bounds__(FB_THREADS, 1)
-    attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-                          const float* __restrict__ lse, const float* __restrict__ delta,
-                          __nv_bfloat16* __restrict__ dq, int B, int Nq, int Nk, int H, int kv_shift, float scale,
-                          float scale_log2) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sDO = sQ + FB_RBYTES;
-  uint8_t* sK = sDO + FB_RBYTES;                  // [FB_STAGES]
-  uint8_t* sV = sK + FB_STAGES * FB_CBYTES;       // [FB_STAGES]
-  uint8_t* sDS = sV + FB_STAGES * FB_CBYTES;      // [2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * FB_PBYTES);
-  uint64_t* q_full = bars;
-  uint64_t* in_full = bars + 1;
-  uint64_t* in_empty = in_full + FB_STAGES;
-  uint64_t* sp_full = in_empty + FB_STAGES;   // [2]
-  uint64_t* ds_full = sp_full + 2;            // [2]
-  uint64_t* acc_done = ds_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * FB_R, h = blockIdx.y, b = blockIdx.z;
-  const int kb = (b + kv_shift) % B;
-  const int ntiles = (Nk + FB_C - 1) / FB_C;
-
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(q_full, 1);
-    for (int s = 0; s < FB_STAGES; ++s) {
-      mbar_init(&in_full[s], 1);
-      mbar_init(&in_empty[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&sp_full[s], 1);
-      mbar_init(&ds_full[s], 8);
-    }
-    mbar_init(acc_done, 1);
-    mbar_fence_init();
-  }
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
-  }
-  if (warp == 9) tmem_alloc(tmem_slot, FB_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 8) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * FB_RBYTES);
-      tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
-      tma_load_4d(sDO, &tmDO, q_full, 0, h, q0, b);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % FB_STAGES;
-        mbar_wait(&in_empty[s], ((j / FB_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&in_full[s], 2 * FB_CBYTES);
-        tma_load_4d(sK + s * FB_CBYTES, &tmK, &in_full[s], 0, h, j * FB_C, kb);
-        tma_load_4d(sV + s * FB_CBYTES, &tmV, &in_full[s], 0, h, j * FB_C, kb);
-      }
-    }
-  } else if (warp == 9) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (Q|dO) K-major x (K|V) K-major
-      constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // dS K-major x K_j MN-major
-      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV);
-      const uint32_t aDS = smem_u32(sDS);
-      auto issue_sp = [&](int j) {
-        const int s = j % FB_STAGES;
-        const uint32_t tb = tmem_base + (j & 1) * 128;
-        mbar_wait(&in_full[s], (j / FB_STAGES) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16(tb, make_smem_desc(aQ + kk * 32, 16, 1024),
-                    make_smem_desc(aK + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16(tb + 64, make_smem_desc(aDO + kk * 32, 16, 1024),
-                    make_smem_desc(aV + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(&sp_full[j & 1]);
-      };
-      mbar_wait(q_full, 0);
-      issue_sp(0);
-      if (ntiles > 1) issue_sp(1);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % FB_STAGES;
-        mbar_wait(&ds_full[j & 1], (j >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < FB_C / 16; ++kk)  // contraction over the 64 keys of this tile
-          umma_bf16(tmem_base + FB_ACC0_COL, make_smem_desc(aDS + (j & 1) * FB_PBYTES + kk * 32, 16, 1024),
-                    make_smem_desc(aK + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0 ? 1u : 0u);
-        umma_commit(&in_empty[s]);
-        if (j + 2 < ntiles) issue_sp(j + 2);
-      }
-      umma_commit(acc_done);
-    }
-  } else {
-    const int c = warp >> 2;
-    const int r = (warp & 3) * 32 + lane;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const int sw = r & 7;
-    const int row = q0 + r;
-    const int64_t lo = ((int64_t)b * H + h) * Nq + (row < Nq ? row : 0);
-    const float lse2 = row < Nq ? lse[lo] * 1.4426950408889634f : INFINITY;
-    const float dl = row < Nq ? delta[lo] : 0.f;
-    for (int j = 0; j < ntiles; ++j) {
-      const int buf = j & 1;
-      mbar_wait(&sp_full[buf], (j >> 1) & 1);
-      tc_fence_after();
-      float sv[32], dp[32];
-      tmem_ld32(t_lane + buf * 128 + c * 32, sv);
-      tmem_ld32(t_lane + buf * 128 + 64 + c * 32, dp);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const float p = fast_exp2(fmaf(sv[e], scale_log2, -lse2));
-        dp[e] = p * (dp[e] - dl) * scale;
-      }
-      store_row_chunk32(sDS + buf * FB_PBYTES + r * 128, sw, c, dp);
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ds_full[buf]);
-    }
-    mbar_wait(acc_done, 0);
-    tc_fence_after();
-    store_out_cols32(dq + (((int64_t)b * Nq + (row < Nq ? row : 0)) * H + h) * FA_D + c * 32,
-                     t_lane + FB_ACC0_COL + c * 32, row < Nq);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, FB_TMEM_COLS);
-}
 
 // ---------------------------------------------------------------------------------------------
 // BACKWARD v3: every A operand lives in tensor memory.
@@ -626,7 +301,7 @@ constexpr int F3_CW = FB_C / F3_NWG;         // 16 columns per warpgroup
 constexpr int F3_SWARPS = 4 * F3_NWG;        // 16 softmax warps: latency hiding for the exp / pack chain
 constexpr int F3_THREADS = (F3_SWARPS + 2) * 32;
 constexpr int F3_STAGES = 8;  // 128 KiB of staging: deep TMA prefetch, and forces one CTA per SM (TMEM = 512 columns)
-constexpr int F3_SMEM = F3_STAGES * 2 * FB_CBYTES + 2 * 2 * FB_C * 4 + 256;
+constexpr int F3_SMEM = F3_STAGES * 2 * FB_CBYTES + 256;
 
 __device__ __forceinline__ void store_out_cols16(__nv_bfloat16* dst, uint32_t taddr, bool valid) {
   float v[16];
@@ -660,6 +335,15 @@ __device__ __forceinline__ void load_row_part_to_tmem(const __nv_bfloat16* row_p
 }
 static_assert(F3_NWG == 4, "the v3 backward kernels are written for 4 softmax warpgroups of 16 columns");
 
+// Warp-local staging of the per-query lse / delta of a 16-query slice: lanes 0-15 carry lse * log2(e),
+// lanes 16-31 delta; values are broadcast with shuffles (no shared memory, no block-wide barrier).
+__device__ __forceinline__ float load_lse_delta(const float* lse_row, const float* delta_row, int q_first, int Nq,
+                                                int lane, bool tile_valid) {
+  const int qi = q_first + (lane & 15);
+  if (!tile_valid || qi >= Nq) return lane < 16 ? INFINITY : 0.f;
+  return lane < 16 ? lse_row[qi] * 1.4426950408889634f : delta_row[qi];
+}
+
 __global__ void __launch_bounds__(F3_THREADS, 1)
     attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                            const __nv_bfloat16* __restrict__ kg, const __nv_bfloat16* __restrict__ vg,
@@ -669,9 +353,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                                // [F3_STAGES]
   uint8_t* sDO = sQ + F3_STAGES * FB_CBYTES;         // [F3_STAGES]
-  float* sLse = reinterpret_cast<float*>(sDO + F3_STAGES * FB_CBYTES);  // [2][64]
-  float* sDel = sLse + 2 * FB_C;                                        // [2][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDel + 2 * FB_C);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDO + F3_STAGES * FB_CBYTES);
   uint64_t* a_ready = bars;
   uint64_t* in_full = bars + 1;               // [F3_STAGES]
   uint64_t* in_empty = in_full + F3_STAGES;   // [F3_STAGES]
@@ -710,6 +392,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == F3_SWARPS) {
+    // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       for (int i = 0; i < ntiles; ++i) {
         const int s = i % F3_STAGES;
@@ -720,54 +403,62 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
       }
     }
   } else if (warp == F3_SWARPS + 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (K|V) in TMEM x (Q|dO) K-major
-      constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // (P^T|dS^T) in TMEM x (dO|Q) MN-major
-      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO);
-      auto issue_sp = [&](int i) {
-        const int s = i % F3_STAGES;
-        const uint32_t tb = tmem_base + F3_BUF0 + (i & 1) * 128;
-        mbar_wait(&in_full[s], (i / F3_STAGES) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16_ts(tb, tmem_base + F3_A0 + kk * 8, make_smem_desc(aQ + s * FB_CBYTES + kk * 32, 16, 1024),
-                       idesc_s, kk != 0 ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16_ts(tb + 64, tmem_base + F3_A1 + kk * 8, make_smem_desc(aDO + s * FB_CBYTES + kk * 32, 16, 1024),
-                       idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(&sp_full[i & 1]);
-      };
-      mbar_wait(a_ready, 0);
+    // ------------------------------------------------------------------ MMA issuer (warp-convergent, elected lane)
+    constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (K|V) in TMEM x (Q|dO) K-major
+    constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // (P^T|dS^T) in TMEM x (dO|Q) MN-major
+    const uint64_t dQk = make_smem_desc(smem_u32(sQ), 16, 1024), dDOk = make_smem_desc(smem_u32(sDO), 16, 1024);
+    const uint64_t dQm = make_smem_desc(smem_u32(sQ), 8192, 1024), dDOm = make_smem_desc(smem_u32(sDO), 8192, 1024);
+    const bool leader = elect_one();
+    auto issue_sp = [&](int i) {  // S^T and dP^T of query tile i into TMEM buffer i&1
+      const int s = i % F3_STAGES;
+      mbar_wait(&in_full[s], (i / F3_STAGES) & 1);
       tc_fence_after();
-      issue_sp(0);
-      if (ntiles > 1) issue_sp(1);
-      for (int i = 0; i < ntiles; ++i) {
-        const int s = i % F3_STAGES;
+      if (leader) {
         const uint32_t tb = tmem_base + F3_BUF0 + (i & 1) * 128;
-        mbar_wait(&pds_full[i & 1], (i >> 1) & 1);
-        tc_fence_after();
+        const uint64_t so = (uint64_t)((s * FB_CBYTES) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < FB_C / 16; ++kk)  // P^T of queries [kk*16, kk*16+16): half kk/2, 8 columns each
-          umma_bf16_ts(tmem_base + F3_ACC0, tb + ((kk * 16) / F3_CW) * F3_CW + ((kk * 16) % F3_CW) / 2,
-                       make_smem_desc(aDO + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (i | kk) != 0 ? 1u : 0u);
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16_ts(tb, tmem_base + F3_A0 + kk * 8, dQk + so + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16_ts(tb + 64, tmem_base + F3_A1 + kk * 8, dDOk + so + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(&sp_full[i & 1]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    issue_sp(0);
+    if (ntiles > 1) issue_sp(1);
+    for (int i = 0; i < ntiles; ++i) {
+      const int s = i % F3_STAGES;
+      mbar_wait(&pds_full[i & 1], (i >> 1) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t tb = tmem_base + F3_BUF0 + (i & 1) * 128;
+        const uint64_t so = (uint64_t)((s * FB_CBYTES) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < FB_C / 16; ++kk)  // warpgroup kk wrote P^T of queries [kk*16, kk*16+16) at S col kk*16
+          umma_bf16_ts(tmem_base + F3_ACC0, tb + kk * F3_CW, dDOm + so + (uint64_t)(kk * 128), idesc_acc,
+                       (i | kk) != 0 ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < FB_C / 16; ++kk)
-          umma_bf16_ts(tmem_base + F3_ACC1, tb + 64 + ((kk * 16) / F3_CW) * F3_CW + ((kk * 16) % F3_CW) / 2,
-                       make_smem_desc(aQ + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (i | kk) != 0 ? 1u : 0u);
+          umma_bf16_ts(tmem_base + F3_ACC1, tb + 64 + kk * F3_CW, dQm + so + (uint64_t)(kk * 128), idesc_acc,
+                       (i | kk) != 0 ? 1u : 0u);
         umma_commit(&in_empty[s]);
-        if (i + 2 < ntiles) issue_sp(i + 2);
       }
-      umma_commit(acc_done);
+      __syncwarp();
+      if (i + 2 < ntiles) issue_sp(i + 2);
     }
+    if (leader) umma_commit(acc_done);
+    __syncwarp();
   } else {
-    const int c = warp >> 2;                 // column half handled by this warpgroup
+    // ------------------------------------------------------------------ softmax warps
+    const int c = warp >> 2;                 // 16-query column slice handled by this warpgroup
     const int r = (warp & 3) * 32 + lane;    // key row within the tile == TMEM lane
-    const int tid = threadIdx.x;             // 0..511
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int row = k0 + r;
-    {  // resident A operands: this thread's half row of K and V -> TMEM
+    {  // resident A operands: this thread's 16-channel slice of its K and V rows -> TMEM
       const int64_t o = (((int64_t)kb * Nk + (row < Nk ? row : 0)) * H + h) * FA_D + c * F3_CW;
       load_row_part_to_tmem(kg + o, row < Nk, t_lane + F3_A0 + c * (F3_CW / 2));
       load_row_part_to_tmem(vg + o, row < Nk, t_lane + F3_A1 + c * (F3_CW / 2));
@@ -776,23 +467,14 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
     }
-    auto fetch = [&](int i) -> float {
-      const int qi = i * FB_C + (tid & 63);
-      const int64_t o = ((int64_t)qb * H + h) * Nq + (qi < Nq ? qi : 0);
-      if (tid < 64) return (i < ntiles && qi < Nq) ? lse[o] * 1.4426950408889634f : INFINITY;
-      return (i < ntiles && qi < Nq) ? delta[o] : 0.f;
-    };
-    auto stage = [&](int i, float val) {
-      if (tid < 64) sLse[(i & 1) * FB_C + tid] = val;
-      else if (tid < 128) sDel[(i & 1) * FB_C + (tid - 64)] = val;
-    };
-    float pre = 0.f;
-    if (tid < 128) stage(0, fetch(0));
+    const float* lse_row = lse + ((int64_t)qb * H + h) * Nq;
+    const float* del_row = delta + ((int64_t)qb * H + h) * Nq;
+    float nxt = load_lse_delta(lse_row, del_row, c * F3_CW, Nq, lane, true);
     for (int i = 0; i < ntiles; ++i) {
       const int buf = i & 1;
       const uint32_t tb = t_lane + F3_BUF0 + buf * 128;
-      if (tid < 128) pre = fetch(i + 1);
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      const float cur = nxt;
+      nxt = load_lse_delta(lse_row, del_row, (i + 1) * FB_C + c * F3_CW, Nq, lane, i + 1 < ntiles);
       mbar_wait(&sp_full[buf], (i >> 1) & 1);
       tc_fence_after();
       float sv[F3_CW], dp[F3_CW];
@@ -802,12 +484,12 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
       uint32_t pw[F3_CW / 2], dw[F3_CW / 2];
 #pragma unroll
       for (int e = 0; e < F3_CW; e += 2) {
-        const float p0 = fast_exp2(fmaf(sv[e], scale_log2, -sLse[buf * FB_C + c * F3_CW + e]));
-        const float p1 = fast_exp2(fmaf(sv[e + 1], scale_log2, -sLse[buf * FB_C + c * F3_CW + e + 1]));
-        const float d0 = p0 * (dp[e] - sDel[buf * FB_C + c * F3_CW + e]) * scale;
-        const float d1 = p1 * (dp[e + 1] - sDel[buf * FB_C + c * F3_CW + e + 1]) * scale;
+        const float l0 = __shfl_sync(0xffffffffu, cur, e), l1 = __shfl_sync(0xffffffffu, cur, e + 1);
+        const float e0 = __shfl_sync(0xffffffffu, cur, 16 + e), e1 = __shfl_sync(0xffffffffu, cur, 17 + e);
+        const float p0 = fast_exp2(fmaf(sv[e], scale_log2, -l0));
+        const float p1 = fast_exp2(fmaf(sv[e + 1], scale_log2, -l1));
         pw[e >> 1] = pack_bf16(p0, p1);
-        dw[e >> 1] = pack_bf16(d0, d1);
+        dw[e >> 1] = pack_bf16(p0 * (dp[e] - e0) * scale, p1 * (dp[e + 1] - e1) * scale);
       }
       tmem_st8(tb + c * F3_CW, pw);        // P^T over the S columns this warpgroup just consumed
       tmem_st8(tb + 64 + c * F3_CW, dw);   // dS^T over the dP columns
@@ -815,7 +497,6 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[buf]);
-      if (tid < 128 && i + 1 < ntiles) stage(i + 1, pre);
     }
     mbar_wait(acc_done, 0);
     tc_fence_after();
@@ -837,7 +518,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;                                // [F3_STAGES]
   uint8_t* sV = sK + F3_STAGES * FB_CBYTES;          // [F3_STAGES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + F3_STAGES * FB_CBYTES + 1024);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + F3_STAGES * FB_CBYTES);
   uint64_t* a_ready = bars;
   uint64_t* in_full = bars + 1;
   uint64_t* in_empty = in_full + F3_STAGES;
@@ -886,43 +567,50 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
       }
     }
   } else if (warp == F3_SWARPS + 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (Q|dO) in TMEM x (K|V) K-major
-      constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // dS in TMEM x K_j MN-major
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-      auto issue_sp = [&](int j) {
-        const int s = j % F3_STAGES;
-        const uint32_t tb = tmem_base + F3_BUF0 + (j & 1) * 128;
-        mbar_wait(&in_full[s], (j / F3_STAGES) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16_ts(tb, tmem_base + F3_A0 + kk * 8, make_smem_desc(aK + s * FB_CBYTES + kk * 32, 16, 1024), idesc_s,
-                       kk != 0 ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16_ts(tb + 64, tmem_base + F3_A1 + kk * 8, make_smem_desc(aV + s * FB_CBYTES + kk * 32, 16, 1024),
-                       idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(&sp_full[j & 1]);
-      };
-      mbar_wait(a_ready, 0);
+    constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (Q|dO) in TMEM x (K|V) K-major
+    constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // dS in TMEM x K_j MN-major
+    const uint64_t dKk = make_smem_desc(smem_u32(sK), 16, 1024), dVk = make_smem_desc(smem_u32(sV), 16, 1024);
+    const uint64_t dKm = make_smem_desc(smem_u32(sK), 8192, 1024);
+    const bool leader = elect_one();
+    auto issue_sp = [&](int j) {
+      const int s = j % F3_STAGES;
+      mbar_wait(&in_full[s], (j / F3_STAGES) & 1);
       tc_fence_after();
-      issue_sp(0);
-      if (ntiles > 1) issue_sp(1);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % F3_STAGES;
+      if (leader) {
         const uint32_t tb = tmem_base + F3_BUF0 + (j & 1) * 128;
-        mbar_wait(&ds_full[j & 1], (j >> 1) & 1);
-        tc_fence_after();
+        const uint64_t so = (uint64_t)((s * FB_CBYTES) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < FB_C / 16; ++kk)  // dS of keys [kk*16, kk*16+16) sits in the dP columns
-          umma_bf16_ts(tmem_base + F3_ACC0, tb + 64 + ((kk * 16) / F3_CW) * F3_CW + ((kk * 16) % F3_CW) / 2,
-                       make_smem_desc(aK + s * FB_CBYTES + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0 ? 1u : 0u);
-        umma_commit(&in_empty[s]);
-        if (j + 2 < ntiles) issue_sp(j + 2);
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16_ts(tb, tmem_base + F3_A0 + kk * 8, dKk + so + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16_ts(tb + 64, tmem_base + F3_A1 + kk * 8, dVk + so + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(&sp_full[j & 1]);
       }
-      umma_commit(acc_done);
+      __syncwarp();
+    };
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    issue_sp(0);
+    if (ntiles > 1) issue_sp(1);
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = j % F3_STAGES;
+      mbar_wait(&ds_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t tb = tmem_base + F3_BUF0 + (j & 1) * 128;
+        const uint64_t so = (uint64_t)((s * FB_CBYTES) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < FB_C / 16; ++kk)  // dS of keys [kk*16, kk*16+16) sits at dP column kk*16
+          umma_bf16_ts(tmem_base + F3_ACC0, tb + 64 + kk * F3_CW, dKm + so + (uint64_t)(kk * 128), idesc_acc,
+                       (j | kk) != 0 ? 1u : 0u);
+        umma_commit(&in_empty[s]);
+      }
+      __syncwarp();
+      if (j + 2 < ntiles) issue_sp(j + 2);
     }
+    if (leader) umma_commit(acc_done);
+    __syncwarp();
   } else {
     const int c = warp >> 2;
     const int r = (warp & 3) * 32 + lane;
@@ -977,16 +665,8 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, co
                 cudaStream_t stream) {
   int rc = attn_delta<__nv_bfloat16>(out, dout, delta, B, Nq, H, stream);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_DKV_SMEM);
-    LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_DQ_SMEM);
-    LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
   const float sl2 = scale * 1.4426950408889634f;
-  if (!env_flag("LGB200_ATTN_BWD_V2")) {
+  {
     static bool configured3 = false;
     if (!configured3) {
       cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
@@ -1008,30 +688,8 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, co
         static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv), B, Nq, Nk, H, kv_shift, scale, sl2);
     return check_launch("attn_bwd_tc(v3)");
   }
-  {
-    CUtensorMap tq, tk, tv, tdo;
-    if ((rc = make_qkv_tmap(&tq, q, B, Nq, H, FB_R))) return rc;
-    if ((rc = make_qkv_tmap(&tdo, dout, B, Nq, H, FB_R))) return rc;
-    if ((rc = make_qkv_tmap(&tk, k, B, Nk, H, FB_C))) return rc;
-    if ((rc = make_qkv_tmap(&tv, v, B, Nk, H, FB_C))) return rc;
-    dim3 grid((Nq + FB_R - 1) / FB_R, H, B);
-    attn_bwd_dq_tc_kernel<<<grid, FB_THREADS, FB_DQ_SMEM, stream>>>(tq, tk, tv, tdo, lse, delta,
-                                                            static_cast<__nv_bfloat16*>(dq), B, Nq, Nk, H, kv_shift,
-                                                            scale, sl2);
-  }
-  {
-    CUtensorMap tq, tk, tv, tdo;
-    if ((rc = make_qkv_tmap(&tq, q, B, Nq, H, FB_C))) return rc;
-    if ((rc = make_qkv_tmap(&tdo, dout, B, Nq, H, FB_C))) return rc;
-    if ((rc = make_qkv_tmap(&tk, k, B, Nk, H, FB_R))) return rc;
-    if ((rc = make_qkv_tmap(&tv, v, B, Nk, H, FB_R))) return rc;
-    dim3 grid((Nk + FB_R - 1) / FB_R, H, B);
-    attn_bwd_dkv_tc_kernel<<<grid, FB_THREADS, FB_DKV_SMEM, stream>>>(tq, tk, tv, tdo, lse, delta,
-                                                              static_cast<__nv_bfloat16*>(dk),
-                                                              static_cast<__nv_bfloat16*>(dv), B, Nq, Nk, H, kv_shift,
-                                                              scale, sl2);
-  }
   return check_launch("attn_bwd_tc");
 }
 
 }  // namespace lgb
+
