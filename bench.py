@@ -297,7 +297,13 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear down without destroy_process_group(): with NCCL work captured inside a live CUDA graph the
+        # communicator teardown was observed to hang on this stack.  Drop the graph, sync, barrier, hard-exit.
+        trainer._graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def kernel_roofline(trainer, pool_dev, B, dev):

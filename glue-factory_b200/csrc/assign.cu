@@ -433,45 +433,65 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
   return t;
 }
 
-__global__ void __launch_bounds__(256) head_terms_fwd_kernel(HeadArgs a) {
+// grid (chunks of 256 tokens over [side-0 rows | side-1 columns], B); per-chunk partial sums, then the last
+// CTA of each pair to finish adds the partials in chunk order (deterministic) and writes the four outputs.
+__global__ void __launch_bounds__(256) head_terms_fwd_kernel(HeadArgs a, float* __restrict__ part,
+                                                            unsigned* __restrict__ counter) {
   __shared__ float red[8];
-  const int b = blockIdx.x, M = a.M, N = a.N;
+  __shared__ bool s_last;
+  const int b = blockIdx.y, M = a.M, N = a.N;
   const int64_t t0 = (int64_t)a.B * M;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
   float pos = 0.f, neg = 0.f, c0 = 0.f, c1 = 0.f;
-  for (int i = threadIdx.x; i < M; i += 256) {
-    const int64_t r = (int64_t)b * M + i;
+  if (idx < M) {
+    const int64_t r = (int64_t)b * M + idx;
     const float2 z = *reinterpret_cast<const float2*>(a.zt + 2 * r);
     const float ls = log_sigmoid(z.x), du = ls - z.x;
-    pos += a.pos_row_sum[r] + a.rowcnt[r] * ls;
-    neg += a.neg0[r] * du;
+    pos = a.pos_row_sum[r] + a.rowcnt[r] * ls;
+    neg = a.neg0[r] * du;
     if (a.fin0) {
       const int arg = du > a.rowmax[r] ? N : a.rowarg[r];
       const float y = (a.fin0[r] == arg) ? 1.f : 0.f;
-      c0 += fmaxf(z.y, 0.f) - z.y * y + log1pf(expf(-fabsf(z.y)));
+      c0 = fmaxf(z.y, 0.f) - z.y * y + log1pf(expf(-fabsf(z.y)));
     }
-  }
-  for (int j = threadIdx.x; j < N; j += 256) {
-    const int64_t r = (int64_t)b * N + j;
+  } else if (idx < M + N) {
+    const int64_t r = (int64_t)b * N + (idx - M);
     const float2 z = *reinterpret_cast<const float2*>(a.zt + 2 * (t0 + r));
     const float ls = log_sigmoid(z.x), du = ls - z.x;
-    pos += a.colcnt[r] * ls;
-    neg += a.neg1[r] * du;
+    pos = a.colcnt[r] * ls;
+    neg = a.neg1[r] * du;
     if (a.fin1) {
       const int arg = du > a.colmax[r] ? M : a.colarg[r];
       const float y = (a.fin1[r] == arg) ? 1.f : 0.f;
-      c1 += fmaxf(z.y, 0.f) - z.y * y + log1pf(expf(-fabsf(z.y)));
+      c1 = fmaxf(z.y, 0.f) - z.y * y + log1pf(expf(-fabsf(z.y)));
     }
   }
   pos = block_sum_256(pos, red);
   neg = block_sum_256(neg, red);
   c0 = block_sum_256(c0, red);
   c1 = block_sum_256(c1, red);
+  const int nchunk = gridDim.x;
   if (threadIdx.x == 0) {
-    const float np = -pos / a.num_pos[b], nn = -neg / a.num_neg[b];
+    float4* dst = reinterpret_cast<float4*>(part) + (int64_t)b * nchunk + blockIdx.x;
+    *dst = make_float4(pos, neg, c0, c1);
+    __threadfence();
+    const unsigned prev = atomicAdd(&counter[b], 1u);
+    s_last = (prev == (unsigned)nchunk - 1);
+    if (s_last) counter[b] = 0u;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    float sp = 0.f, sn = 0.f, s0 = 0.f, s1 = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(part) + (int64_t)b * nchunk + c);
+      sp += v.x; sn += v.y; s0 += v.z; s1 += v.w;
+    }
+    const float np = -sp / a.num_pos[b], nn = -sn / a.num_neg[b];
     a.nll_pos[b] = np;
     a.nll_neg[b] = nn;
     a.nll[b] = a.bal * np + (1.f - a.bal) * nn;
-    a.conf[b] = a.fin0 ? 0.5f * (c0 / M + c1 / N) : 0.f;
+    a.conf[b] = a.fin0 ? 0.5f * (s0 / M + s1 / N) : 0.f;
   }
 }
 
@@ -552,14 +572,15 @@ int lgb200_head_terms_fwd(const float* zt, const float* pos_row_sum, const float
                           const float* neg0, const float* neg1, const float* rowmax, const int* rowarg,
                           const float* colmax, const int* colarg, const int* fin0, const int* fin1,
                           const float* num_pos, const float* num_neg, float bal, float* nll, float* nll_pos,
-                          float* nll_neg, float* conf, int B, int M, int N, cudaStream_t stream) {
+                          float* nll_neg, float* conf, float* ws, unsigned* counters, int B, int M, int N,
+                          cudaStream_t stream) {
   HeadArgs a;
   int rc = fill_head_args(a, zt, pos_row_sum, rowcnt, colcnt, neg0, neg1, rowmax, rowarg, colmax, colarg, fin0, fin1,
                           num_pos, num_neg, bal, B, M, N);
   if (rc) return rc;
-  LGB_REQUIRE(nll && nll_pos && nll_neg && conf, kErrInvalid, "head_terms_fwd: null output");
+  LGB_REQUIRE(nll && nll_pos && nll_neg && conf && ws && counters, kErrInvalid, "head_terms_fwd: null output");
   a.nll = nll; a.nll_pos = nll_pos; a.nll_neg = nll_neg; a.conf = conf;
-  head_terms_fwd_kernel<<<B, 256, 0, stream>>>(a);
+  head_terms_fwd_kernel<<<dim3((M + N + 255) / 256, B), 256, 0, stream>>>(a, ws, counters);
   return check_launch("head_terms_fwd");
 }
 

@@ -215,17 +215,18 @@ __global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const T* __restrict__ 
                                                          const float* __restrict__ beta, const float* __restrict__ mean,
                                                          const float* __restrict__ rstd, T* __restrict__ dx,
                                                          float* __restrict__ dgamma_part,
-                                                         float* __restrict__ dbeta_part, int64_t ntok) {
+                                                         float* __restrict__ dbeta_part,
+                                                         float* __restrict__ dxsum_part, int64_t ntok) {
   constexpr int W = 128 * VPL;
   __shared__ float s_red[8][W];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float g[VPL][4], bb[VPL][4], dg[VPL][4], db[VPL][4];
+  float g[VPL][4], bb[VPL][4], dg[VPL][4], db[VPL][4], dxs[VPL][4];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     load4<float>(gamma + i * 128 + lane * 4, g[i]);
     load4<float>(beta + i * 128 + lane * 4, bb[i]);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) dg[i][e] = db[i][e] = 0.f;
+    for (int e = 0; e < 4; ++e) dg[i][e] = db[i][e] = dxs[i][e] = 0.f;
   }
   for (int64_t tok = (int64_t)blockIdx.x * 8 + warp; tok < ntok; tok += (int64_t)gridDim.x * 8) {
     const float mu = mean[tok], rs = rstd[tok];
@@ -254,23 +255,28 @@ __global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const T* __restrict__ 
     for (int i = 0; i < VPL; ++i) {
       float o[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = rs * (dz[i][e] - s1 - xh[i][e] * s2);
+      for (int e = 0; e < 4; ++e) {
+        o[e] = rs * (dz[i][e] - s1 - xh[i][e] * s2);
+        dxs[i][e] += o[e];
+      }
       store4<T>(dx + tok * W + i * 128 + lane * 4, o);
     }
   }
-  // reduce dgamma then dbeta over the 8 warps
+  // reduce dgamma, dbeta and the column sums of dx over the 8 warps
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) s_red[warp][i * 128 + lane * 4 + e] = pass == 0 ? dg[i][e] : db[i][e];
+      for (int e = 0; e < 4; ++e)
+        s_red[warp][i * 128 + lane * 4 + e] = pass == 0 ? dg[i][e] : (pass == 1 ? db[i][e] : dxs[i][e]);
     __syncthreads();
+    float* dst = pass == 0 ? dgamma_part : (pass == 1 ? dbeta_part : dxsum_part);
     for (int c = threadIdx.x; c < W; c += 256) {
       float acc = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) acc += s_red[w][c];
-      (pass == 0 ? dgamma_part : dbeta_part)[(int64_t)blockIdx.x * W + c] = acc;
+      dst[(int64_t)blockIdx.x * W + c] = acc;
     }
     __syncthreads();
   }
@@ -343,9 +349,11 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 // (8 elements = one 128-bit load for bf16), row slabs across blockIdx.y, deterministic two-stage sum.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ a, float* __restrict__ part,
-                                                            int64_t rows, int cols, int rows_per_slab) {
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ a, float* __restrict__ part,
+                                                    float* __restrict__ out, unsigned* __restrict__ counter,
+                                                    int64_t rows, int cols, int rows_per_slab) {
   __shared__ float s_red[32][65];
+  __shared__ bool s_last;
   const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
   const int col0 = blockIdx.x * 64 + cx * 8;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab;
@@ -367,13 +375,24 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
     for (int r = 0; r < 32; ++r) t += s_red[r][threadIdx.x];
     part[(int64_t)blockIdx.y * cols + blockIdx.x * 64 + threadIdx.x] = t;
   }
-}
-__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int cols, int nslabs) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float t = 0.f;
-  for (int sidx = 0; sidx < nslabs; ++sidx) t += part[(int64_t)sidx * cols + c];
-  out[c] = t;
+  // the last CTA of this column block to finish sums the slab partials in slab order (deterministic)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(&counter[blockIdx.x], 1u);
+    s_last = (prev == gridDim.y - 1);
+    if (s_last) counter[blockIdx.x] = 0u;  // self-resetting for the next call
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    if (threadIdx.x < 64 && c < cols) {
+      float t = 0.f;
+      for (unsigned sidx = 0; sidx < gridDim.y; ++sidx) t += __ldcg(&part[(int64_t)sidx * cols + c]);
+      out[c] = t;
+    }
+  }
 }
 
 // x_out = x + y (fp32 residual stream) and its compute-dtype copy for the next GEMM, in one pass
@@ -417,19 +436,19 @@ int lgb200_colsum_slabs(int64_t rows, int cols) {
   return (int)(n < 1 ? 1 : n);
 }
 
-int lgb200_colsum(const void* a, float* out, float* ws, int64_t rows, int cols, int dtype, cudaStream_t stream) {
-  LGB_REQUIRE(a && out && ws && rows > 0 && cols > 0, kErrInvalid, "colsum: bad arguments");
+int lgb200_colsum(const void* a, float* out, float* ws, unsigned* counters, int64_t rows, int cols, int dtype,
+                  cudaStream_t stream) {
+  LGB_REQUIRE(a && out && ws && counters && rows > 0 && cols > 0, kErrInvalid, "colsum: bad arguments");
   LGB_REQUIRE(cols % 8 == 0, kErrInvalid, "colsum: cols must be a multiple of 8");
   const int nslabs = lgb200_colsum_slabs(rows, cols);
   const int rps = (int)((rows + nslabs - 1) / nslabs);
   dim3 grid((cols + 63) / 64, nslabs);
   if (dtype == LGB200_F32)
-    colsum_partial_kernel<float><<<grid, 256, 0, stream>>>((const float*)a, ws, rows, cols, rps);
+    colsum_kernel<float><<<grid, 256, 0, stream>>>((const float*)a, ws, out, counters, rows, cols, rps);
   else if (dtype == LGB200_BF16)
-    colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)a, ws, rows, cols, rps);
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)a, ws, out, counters, rows, cols, rps);
   else
     LGB_REQUIRE(false, kErrInvalid, "colsum: bad dtype %d", dtype);
-  colsum_final_kernel<<<(cols + 127) / 128, 128, 0, stream>>>(ws, out, cols, nslabs);
   return check_launch("colsum");
 }
 
@@ -519,13 +538,13 @@ int lgb200_ln_gelu_bwd_parts(int64_t ntok) {
 
 template <typename T>
 static int ln_gelu_bwd_dispatch(const void* dy, const void* x, const float* gamma, const float* beta,
-                                const float* mean, const float* rstd, void* dx, float* dgp, float* dbp, int64_t ntok,
-                                int W, cudaStream_t stream) {
+                                const float* mean, const float* rstd, void* dx, float* dgp, float* dbp, float* dxp,
+                                int64_t ntok, int W, cudaStream_t stream) {
   const unsigned grid = (unsigned)lgb200_ln_gelu_bwd_parts(ntok);
   switch (W) {
-    case 256: ln_gelu_bwd_kernel<T, 2><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, ntok); break;
-    case 512: ln_gelu_bwd_kernel<T, 4><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, ntok); break;
-    case 1024: ln_gelu_bwd_kernel<T, 8><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, ntok); break;
+    case 256: ln_gelu_bwd_kernel<T, 2><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, dxp, ntok); break;
+    case 512: ln_gelu_bwd_kernel<T, 4><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, dxp, ntok); break;
+    case 1024: ln_gelu_bwd_kernel<T, 8><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, dxp, ntok); break;
     default: LGB_REQUIRE(false, kErrUnsupported, "ln_gelu: width %d not in {256,512,1024}", W);
   }
   return check_launch("ln_gelu_bwd");
@@ -534,15 +553,17 @@ static int ln_gelu_bwd_dispatch(const void* dy, const void* x, const float* gamm
 extern "C" {
 
 int lgb200_ln_gelu_bwd(const void* dy, const void* x, const float* gamma, const float* beta, const float* mean,
-                       const float* rstd, void* dx, float* dgamma_part, float* dbeta_part, int64_t ntok, int W,
-                       int dtype, cudaStream_t stream) {
-  LGB_REQUIRE(dy && x && gamma && beta && mean && rstd && dx && dgamma_part && dbeta_part, kErrInvalid,
+                       const float* rstd, void* dx, float* dgamma_part, float* dbeta_part, float* dxsum_part,
+                       int64_t ntok, int W, int dtype, cudaStream_t stream) {
+  LGB_REQUIRE(dy && x && gamma && beta && mean && rstd && dx && dgamma_part && dbeta_part && dxsum_part, kErrInvalid,
               "ln_gelu_bwd: null pointer");
   LGB_REQUIRE(ntok > 0, kErrInvalid, "ln_gelu_bwd: empty input");
   if (dtype == LGB200_F32)
-    return ln_gelu_bwd_dispatch<float>(dy, x, gamma, beta, mean, rstd, dx, dgamma_part, dbeta_part, ntok, W, stream);
+    return ln_gelu_bwd_dispatch<float>(dy, x, gamma, beta, mean, rstd, dx, dgamma_part, dbeta_part, dxsum_part, ntok, W,
+                                       stream);
   if (dtype == LGB200_BF16)
-    return ln_gelu_bwd_dispatch<__nv_bfloat16>(dy, x, gamma, beta, mean, rstd, dx, dgamma_part, dbeta_part, ntok, W, stream);
+    return ln_gelu_bwd_dispatch<__nv_bfloat16>(dy, x, gamma, beta, mean, rstd, dx, dgamma_part, dbeta_part, dxsum_part,
+                                               ntok, W, stream);
   LGB_REQUIRE(false, kErrInvalid, "ln_gelu_bwd: bad dtype %d", dtype);
 }
 

@@ -20,6 +20,8 @@ import torch.nn.functional as F
 from . import ops
 
 _OUT_DTYPE_OK = True
+_ADDMM_DTYPE_OK = True
+_head_counters = {}
 
 
 def _wgrad(dy, a):
@@ -37,6 +39,20 @@ def _wgrad(dy, a):
 
 def _bgrad(dy):
     return ops.colsum(dy)
+
+
+def _dgrad_acc(acc, dy, w):
+    """acc (fp32 [T, in]) + dy (compute dtype [T, out]) @ w ([out, in]) -> fp32, in the GEMM epilogue when
+    torch exposes addmm(out_dtype=...) for bf16 operands, else GEMM + mixed-dtype add."""
+    global _ADDMM_DTYPE_OK
+    if dy.dtype == torch.float32:
+        return torch.addmm(acc, dy, w)
+    if _ADDMM_DTYPE_OK:
+        try:
+            return torch.addmm(acc, dy, w, out_dtype=torch.float32)
+        except (TypeError, RuntimeError):
+            _ADDMM_DTYPE_OK = False
+    return acc + torch.mm(dy, w)
 
 
 def _attend_fwd(q, k, v, sizes, H, cross):
@@ -141,12 +157,11 @@ class LayerFn(torch.autograd.Function):
         dy2 = dx.to(cdt)
         dW3c, db3c = _wgrad(dy2, gg), _bgrad(dy2)
         dgg = torch.mm(dy2, W3c)
-        dh2, dg2, dbe2 = ops.ln_gelu_bwd(dgg, h2, g2, be2, mean2, rstd2)
+        dh2, dg2, dbe2, db0c = ops.ln_gelu_bwd(dgg, h2, g2, be2, mean2, rstd2, want_dxsum=True)
         del dgg
-        db0c = _bgrad(dh2)
         dW0c = torch.cat([_wgrad(dh2, x1_16), _wgrad(dh2, msg2)], 1)
         dmsg2 = torch.mm(dh2, W0c[:, D:])
-        dx1 = dx + torch.mm(dh2, W0c[:, :D])  # fp32 accumulation of the residual-stream gradient
+        dx1 = _dgrad_acc(dx, dh2, W0c[:, :D])  # fp32 accumulation of the residual-stream gradient
         del dh2
         dWout, dbout = _wgrad(dmsg2, m), _bgrad(dmsg2)
         dm = torch.mm(dmsg2, Wout)
@@ -154,25 +169,24 @@ class LayerFn(torch.autograd.Function):
         dqk = dq_.add_(dk_)  # the shared to_qk projection is query in one direction and key in the other
         dWqk, dbqk = _wgrad(dqk, x1_16), _bgrad(dqk)
         dWv, dbv = _wgrad(dvv, x1_16), _bgrad(dvv)
-        dx1.add_(torch.mm(dqk, Wqk))
-        dx1.add_(torch.mm(dvv, Wv))
+        dx1 = _dgrad_acc(dx1, dqk, Wqk)
+        dx1 = _dgrad_acc(dx1, dvv, Wv)
         # ---- self block
         dy = dx1.to(cdt)
         dW3, db3 = _wgrad(dy, g), _bgrad(dy)
         dg = torch.mm(dy, W3)
-        dh, dg1, dbe1 = ops.ln_gelu_bwd(dg, h, g1, be1, mean1, rstd1)
+        dh, dg1, dbe1, db0 = ops.ln_gelu_bwd(dg, h, g1, be1, mean1, rstd1, want_dxsum=True)
         del dg
-        db0 = _bgrad(dh)
         dW0 = torch.cat([_wgrad(dh, x16), _wgrad(dh, msg)], 1)
         dmsg = torch.mm(dh, W0[:, D:])
-        dx0 = dx1.add_(torch.mm(dh, W0[:, :D]))
+        dx0 = _dgrad_acc(dx1, dh, W0[:, :D])
         del dh
         dWo, dbo = _wgrad(dmsg, att), _bgrad(dmsg)
         datt = torch.mm(dmsg, Wo)
         dq, dk, dv = _attend_bwd(q, k, v, att, lse1, datt, sizes, H, cross=False)
         dqkv, dtheta = ops.rope_bwd(dq, dk, dv, q, k, theta, H)
         dWqkv, dbqkv = _wgrad(dqkv, x16), _bgrad(dqkv)
-        dx0.add_(torch.mm(dqkv, Wqkv))
+        dx0 = _dgrad_acc(dx0, dqkv, Wqkv)
         grads = (dWqkv, dbqkv, dWo, dbo, dW0, db0, dg1, dbe1, dW3, db3,
                  dWqk, dbqk, dWv, dbv, dWout, dbout, dW0c, db0c, dg2, dbe2, dW3c, db3c)
         return (dx0, dtheta, None, None, None, None, None) + grads
@@ -208,11 +222,16 @@ class HeadFn(torch.autograd.Function):
         st = ops.assign_stats(sim, ls0, ls1, du0, du1, gt_u8=gt["u8"], dense=False)
         out = torch.empty(4, B, device=dev, dtype=torch.float32)
         f0, f1 = (fin if (fin is not None and has_tok) else (None, None))
+        hws = torch.empty(4 * B * ((M + N + 255) // 256), device=dev, dtype=torch.float32)
+        cnt = _head_counters.get(dev)
+        if cnt is None:
+            cnt = _head_counters[dev] = torch.zeros(4096, device=dev, dtype=torch.int32)
+        assert B <= 4096
         ops.call("lgb200_head_terms_fwd", ops.ptr(zt), ops.ptr(st["pos_row_sum"]), ops.ptr(gt["rowcnt"]),
                  ops.ptr(gt["colcnt"]), ops.ptr(gt["neg0"]), ops.ptr(gt["neg1"]), ops.ptr(st["rowmax"]),
                  ops.ptr(st["rowarg"]), ops.ptr(st["colmax"]), ops.ptr(st["colarg"]), ops.ptr(f0), ops.ptr(f1),
                  ops.ptr(gt["num_pos"]), ops.ptr(gt["num_neg"]), float(bal), ops.ptr(out[0]), ops.ptr(out[1]),
-                 ops.ptr(out[2]), ops.ptr(out[3]), B, M, N, ops.stream_ptr())
+                 ops.ptr(out[2]), ops.ptr(out[3]), ops.ptr(hws), ops.ptr(cnt), B, M, N, ops.stream_ptr())
         nll, nll_pos, nll_neg, conf = out[0], out[1], out[2], out[3]
         saved = [x, x16, md, sim, st["lse_row"], st["lse_col"], zt, st["rowmax"], st["rowarg"], st["colmax"],
                  st["colarg"], wfp, wm, gt["u8"], gt["rowcnt"], gt["colcnt"], gt["neg0"], gt["neg1"], gt["num_pos"],

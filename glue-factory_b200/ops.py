@@ -131,16 +131,19 @@ def ln_gelu_fwd(x, g, b, eps):
     return y, mean, rstd
 
 
-def ln_gelu_bwd(dy, x, g, b, mean, rstd):
+def ln_gelu_bwd(dy, x, g, b, mean, rstd, want_dxsum=False):
+    """Returns dx, dgamma, dbeta (and, on request, the column sums of dx = bias gradient of the Linear before)."""
     T, W = x.shape
     dy = dy.contiguous()
     dx = torch.empty_like(x)
     parts = _lib.load().lgb200_ln_gelu_bwd_parts(T)
-    dg = torch.empty(parts, W, device=x.device, dtype=torch.float32)
-    db = torch.empty_like(dg)
-    call("lgb200_ln_gelu_bwd", ptr(dy), ptr(x), ptr(g), ptr(b), ptr(mean), ptr(rstd), ptr(dx), ptr(dg), ptr(db),
-         T, W, _code(x.dtype), stream_ptr())
-    return dx, dg.sum(0), db.sum(0)
+    red = torch.empty(3, parts, W, device=x.device, dtype=torch.float32)
+    call("lgb200_ln_gelu_bwd", ptr(dy), ptr(x), ptr(g), ptr(b), ptr(mean), ptr(rstd), ptr(dx), ptr(red[0]), ptr(red[1]),
+         ptr(red[2]), T, W, _code(x.dtype), stream_ptr())
+    sums = red.sum(1)  # one reduction for the three partial sets
+    if want_dxsum:
+        return dx, sums[0], sums[1], sums[2]
+    return dx, sums[0], sums[1]
 
 
 class LnGelu(torch.autograd.Function):
@@ -157,15 +160,23 @@ class LnGelu(torch.autograd.Function):
         return dx, dg, db, None
 
 
+_colsum_counters = {}
+
+
 def colsum(a):
-    """[rows, cols] (fp32 / bf16) -> fp32 [cols] column sums (bias gradients)."""
+    """[rows, cols] (fp32 / bf16) -> fp32 [cols] column sums (bias gradients); one launch."""
     _chk(a)
     rows, cols = a.shape
     if cols % 8:
         return a.sum(0, dtype=torch.float32)
-    out = torch.empty(cols, device=a.device, dtype=torch.float32)
-    ws = torch.empty(_lib.load().lgb200_colsum_slabs(rows, cols) * cols, device=a.device, dtype=torch.float32)
-    call("lgb200_colsum", ptr(a), ptr(out), ptr(ws), rows, cols, _code(a.dtype), stream_ptr())
+    dev = a.device
+    cnt = _colsum_counters.get(dev)
+    if cnt is None:  # self-resetting arrival counters, zeroed once per device
+        cnt = _colsum_counters[dev] = torch.zeros(64, device=dev, dtype=torch.int32)
+    assert cols <= 64 * 64
+    out = torch.empty(cols, device=dev, dtype=torch.float32)
+    ws = torch.empty(_lib.load().lgb200_colsum_slabs(rows, cols) * cols, device=dev, dtype=torch.float32)
+    call("lgb200_colsum", ptr(a), ptr(out), ptr(ws), ptr(cnt), rows, cols, _code(a.dtype), stream_ptr())
     return out
 
 

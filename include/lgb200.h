@@ -79,11 +79,12 @@ int lgb200_attn_bwd(const void* q, const void* k, const void* v, const void* out
  * x,y [ntok, W], W in {256,512,1024}; mean,rstd [ntok] saved for backward.                       */
 int lgb200_ln_gelu_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                        int64_t ntok, int W, float eps, int dtype, cudaStream_t stream);
-/* number of partial rows written to dgamma_part/dbeta_part [parts, W] (caller sums over parts)  */
+/* number of partial rows written to dgamma_part / dbeta_part / dxsum_part [parts, W] (caller sums over
+ * parts); dxsum = column sums of dx = the bias gradient of the Linear that feeds the LayerNorm.  */
 int lgb200_ln_gelu_bwd_parts(int64_t ntok);
 int lgb200_ln_gelu_bwd(const void* dy, const void* x, const float* gamma, const float* beta, const float* mean,
-                       const float* rstd, void* dx, float* dgamma_part, float* dbeta_part, int64_t ntok, int W,
-                       int dtype, cudaStream_t stream);
+                       const float* rstd, void* dx, float* dgamma_part, float* dbeta_part, float* dxsum_part,
+                       int64_t ntok, int W, int dtype, cudaStream_t stream);
 
 /* ---- batched bf16 tensor-core GEMM (tcgen05, fp32 accumulate) ---------------------------------------
  * replaces torch.einsum("bmd,bnd->bmn") of MatchAssignment (lightglue.py:283) and its two backward
@@ -136,7 +137,9 @@ int lgb200_head_terms_fwd(const float* zt, const float* pos_row_sum, const float
                           const float* neg0, const float* neg1, const float* rowmax, const int* rowarg,
                           const float* colmax, const int* colarg, const int* fin0, const int* fin1,
                           const float* num_pos, const float* num_neg, float bal, float* nll, float* nll_pos,
-                          float* nll_neg, float* conf, int B, int M, int N, cudaStream_t stream);
+                          float* nll_neg, float* conf, float* ws /* 4*B*ceil((M+N)/256) floats, 16-byte aligned */,
+                          unsigned* counters /* B uint32, zero before the first call, left zero */, int B, int M, int N,
+                          cudaStream_t stream);
 int lgb200_head_terms_bwd(const float* zt, const float* rowcnt, const float* colcnt, const float* neg0,
                           const float* neg1, const float* rowmax, const int* rowarg, const float* colmax,
                           const int* colarg, const int* fin0, const int* fin1, const float* num_pos,
@@ -154,9 +157,11 @@ int lgb200_sinkhorn(const float* sim, float alpha, int iters, float* out, void* 
                     cudaStream_t stream);
 
 /* column sums of a tall [rows, cols] matrix = bias gradient of an nn.Linear (autograd of lightglue.py:156 etc.).
- * ws: lgb200_colsum_slabs(rows, cols) * cols floats of scratch; cols % 8 == 0.                       */
+ * ws: lgb200_colsum_slabs(rows, cols) * cols floats of scratch; counters: (cols+63)/64 uint32, zero before the
+ * FIRST call (the kernel leaves them zero again); cols % 8 == 0.  One launch, deterministic summation order. */
 int lgb200_colsum_slabs(int64_t rows, int cols);
-int lgb200_colsum(const void* a, float* out, float* ws, int64_t rows, int cols, int dtype, cudaStream_t stream);
+int lgb200_colsum(const void* a, float* out, float* ws, unsigned* counters, int64_t rows, int cols, int dtype,
+                  cudaStream_t stream);
 
 /* ---- flat-buffer optimiser (train.py:358-361, 513) and casts --------------------------------------- */
 /* step: 1-based step count for the bias correction; when step_dev != NULL the count is read from device

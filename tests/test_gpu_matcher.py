@@ -152,6 +152,7 @@ def test_cuda_graph_step_matches_eager_step():
     def run(graphed):
         model = _build(conf, synthetic.make_weights(conf, seed=51), "bf16")
         tr = MatcherTrainer(model, lr=1e-3)
+        tr.step(batches[0])  # one eager step in both runs (it is also the capture warm-up)
         if graphed:
             tr.capture(batches[0], DEV, warmup=0)
         losses = []
