@@ -58,16 +58,22 @@ __global__ void __launch_bounds__(256) assign_lse_kernel(const float* __restrict
     rs[t] = 0.f;
     rows[t] = strip * kStripRows + w + kWarps * t;
   }
-  int buf = 0;
-  for (int c0 = 0; c0 < N; c0 += kChunk, buf ^= 1) {
+  auto load_chunk = [&](int c0, float4* dst) {
     const int col = c0 + lane * 4;
     const int valid = min(4, N - col);  // may be <= 0
+#pragma unroll
+    for (int t = 0; t < kRowsPerWarp; ++t)
+      dst[t] = (rows[t] < M && valid > 0) ? ld4(base + (int64_t)rows[t] * N + col, vec, valid)
+                                           : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+  };
+  int buf = 0;
+  float4 xn[kRowsPerWarp];
+  load_chunk(0, xn);
+  for (int c0 = 0; c0 < N; c0 += kChunk, buf ^= 1) {
     float4 x[kRowsPerWarp];
 #pragma unroll
-    for (int t = 0; t < kRowsPerWarp; ++t) {
-      x[t] = (rows[t] < M && valid > 0) ? ld4(base + (int64_t)rows[t] * N + col, vec, valid)
-                                         : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
-    }
+    for (int t = 0; t < kRowsPerWarp; ++t) x[t] = xn[t];
+    if (c0 + kChunk < N) load_chunk(c0 + kChunk, xn);  // next chunk in flight while this one is reduced
     // ---- row statistics (online, rescale only when the running max moves)
 #pragma unroll
     for (int t = 0; t < kRowsPerWarp; ++t) {
@@ -128,26 +134,35 @@ __global__ void __launch_bounds__(256) assign_lse_kernel(const float* __restrict
   }
 }
 
-__global__ void assign_col_lse_merge_kernel(const float* __restrict__ colpart_m, const float* __restrict__ colpart_s,
-                                            float* __restrict__ lse_col, int N, int nstrips) {
-  const int b = blockIdx.y;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= N) return;
-  const float* pm = colpart_m + (int64_t)b * nstrips * N + j;
-  const float* ps = colpart_s + (int64_t)b * nstrips * N + j;
+// 32 columns x 8 strip-groups per CTA: max pass (no exp), then one exp per partial; groups merged through smem
+__global__ void __launch_bounds__(256) assign_col_lse_merge_kernel(const float* __restrict__ colpart_m,
+                                                                  const float* __restrict__ colpart_s,
+                                                                  float* __restrict__ lse_col, int N, int nstrips) {
+  __shared__ float s_a[8][33];
+  const int b = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  const bool ok = j < N;
+  const float* pm = colpart_m + (int64_t)b * nstrips * N + (ok ? j : 0);
+  const float* ps = colpart_s + (int64_t)b * nstrips * N + (ok ? j : 0);
   float m = kNegInf;
-  for (int st = 0; st < nstrips; ++st) m = fmaxf(m, pm[(int64_t)st * N]);
-  const float ref = (m == kNegInf) ? 0.f : m;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int st = 0;
-  for (; st + 4 <= nstrips; st += 4) {
-    s0 += ps[(int64_t)(st + 0) * N] * __expf(pm[(int64_t)(st + 0) * N] - ref);
-    s1 += ps[(int64_t)(st + 1) * N] * __expf(pm[(int64_t)(st + 1) * N] - ref);
-    s2 += ps[(int64_t)(st + 2) * N] * __expf(pm[(int64_t)(st + 2) * N] - ref);
-    s3 += ps[(int64_t)(st + 3) * N] * __expf(pm[(int64_t)(st + 3) * N] - ref);
+  for (int st = ty; st < nstrips; st += 8) m = fmaxf(m, pm[(int64_t)st * N]);
+  s_a[ty][tx] = m;
+  __syncthreads();
+  float gm = s_a[0][tx];
+#pragma unroll
+  for (int g = 1; g < 8; ++g) gm = fmaxf(gm, s_a[g][tx]);
+  const float ref = (gm == kNegInf) ? 0.f : gm;
+  float sum = 0.f;
+  for (int st = ty; st < nstrips; st += 8) sum += ps[(int64_t)st * N] * __expf(pm[(int64_t)st * N] - ref);
+  __syncthreads();
+  s_a[ty][tx] = sum;
+  __syncthreads();
+  if (ty == 0 && ok) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += s_a[g][tx];  // fixed order: deterministic
+    lse_col[(int64_t)b * N + j] = gm + logf(t);
   }
-  for (; st < nstrips; ++st) s0 += ps[(int64_t)st * N] * __expf(pm[(int64_t)st * N] - ref);
-  lse_col[(int64_t)b * N + j] = m + logf((s0 + s1) + (s2 + s3));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -196,10 +211,35 @@ __global__ void __launch_bounds__(256) assign_scores_kernel(ScoreArgs a) {
     psum[t] = 0.f;
     esum[t] = 0.f;
   }
+  auto load_chunk = [&](int c0, float4* dx, uint32_t* dg) {
+    const int col = c0 + lane * 4;
+    const int valid = min(4, N - col);
+#pragma unroll
+    for (int t = 0; t < kRowsPerWarp; ++t) {
+      dx[t] = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+      dg[t] = 0;
+      if (rows[t] >= M || valid <= 0) continue;
+      const int64_t roff = (int64_t)rows[t] * N + col;
+      dx[t] = ld4(base + roff, vec, valid);
+      if (gbase) {
+        if (vec && valid >= 4) dg[t] = *reinterpret_cast<const uint32_t*>(gbase + roff);
+        else
+          for (int e = 0; e < valid; ++e) dg[t] |= (uint32_t)gbase[roff + e] << (8 * e);
+      }
+    }
+  };
   int buf = 0;
+  float4 xn[kRowsPerWarp];
+  uint32_t gn[kRowsPerWarp];
+  load_chunk(0, xn, gn);
   for (int c0 = 0; c0 < N; c0 += kChunk, buf ^= 1) {
     const int col = c0 + lane * 4;
     const int valid = min(4, N - col);
+    float4 xc[kRowsPerWarp];
+    uint32_t gc[kRowsPerWarp];
+#pragma unroll
+    for (int t = 0; t < kRowsPerWarp; ++t) { xc[t] = xn[t]; gc[t] = gn[t]; }
+    if (c0 + kChunk < N) load_chunk(c0 + kChunk, xn, gn);  // next chunk in flight while this one is processed
     float lc[4], l1[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -213,15 +253,8 @@ __global__ void __launch_bounds__(256) assign_scores_kernel(ScoreArgs a) {
 #pragma unroll
     for (int t = 0; t < kRowsPerWarp; ++t) {
       if (rows[t] >= M || valid <= 0) continue;
-      const int64_t roff = (int64_t)rows[t] * N + col;
-      float4 x4 = ld4(base + roff, vec, valid);
-      float x[4] = {x4.x, x4.y, x4.z, x4.w};
-      uint32_t g = 0;
-      if (gbase) {
-        if (vec && valid >= 4) g = *reinterpret_cast<const uint32_t*>(gbase + roff);
-        else
-          for (int e = 0; e < valid; ++e) g |= (uint32_t)gbase[roff + e] << (8 * e);
-      }
+      const float x[4] = {xc[t].x, xc[t].y, xc[t].z, xc[t].w};
+      const uint32_t g = gc[t];
       float sc[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -283,25 +316,37 @@ __global__ void __launch_bounds__(256) assign_scores_kernel(ScoreArgs a) {
   }
 }
 
-__global__ void assign_col_arg_merge_kernel(const float* __restrict__ colpart_v, const int* __restrict__ colpart_i,
-                                            const float* __restrict__ dust1, float* __restrict__ colmax,
-                                            int* __restrict__ colarg, float* __restrict__ scores, int M, int N,
-                                            int nstrips) {
-  const int b = blockIdx.y;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j > N) return;
+__global__ void __launch_bounds__(256) assign_col_arg_merge_kernel(const float* __restrict__ colpart_v,
+                                                                  const int* __restrict__ colpart_i,
+                                                                  const float* __restrict__ dust1,
+                                                                  float* __restrict__ colmax, int* __restrict__ colarg,
+                                                                  float* __restrict__ scores, int M, int N,
+                                                                  int nstrips) {
+  __shared__ float s_v[8][33];
+  __shared__ int s_i[8][33];
+  const int b = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  float v = kNegInf;
+  int i = 0x7fffffff;
+  if (j < N) {
+    for (int st = ty; st < nstrips; st += 8) {
+      const int64_t o = ((int64_t)b * nstrips + st) * N + j;
+      const float v2 = colpart_v[o];
+      const int i2 = colpart_i[o];
+      if (better(v2, i2, v, i)) { v = v2; i = i2; }
+    }
+  }
+  s_v[ty][tx] = v;
+  s_i[ty][tx] = i;
+  __syncthreads();
+  if (ty != 0 || j > N) return;
   if (j == N) {
     if (scores) scores[((int64_t)b * (M + 1) + M) * (N + 1) + N] = 0.f;
     return;
   }
-  float v = kNegInf;
-  int i = 0x7fffffff;
-  for (int st = 0; st < nstrips; ++st) {
-    const int64_t o = ((int64_t)b * nstrips + st) * N + j;
-    const float v2 = colpart_v[o];
-    const int i2 = colpart_i[o];
-    if (better(v2, i2, v, i)) { v = v2; i = i2; }
-  }
+#pragma unroll
+  for (int g = 1; g < 8; ++g)
+    if (better(s_v[g][tx], s_i[g][tx], v, i)) { v = s_v[g][tx]; i = s_i[g][tx]; }
   colmax[(int64_t)b * N + j] = v;
   colarg[(int64_t)b * N + j] = i;
   if (scores) scores[((int64_t)b * (M + 1) + M) * (N + 1) + j] = dust1[(int64_t)b * N + j];
@@ -612,7 +657,7 @@ int lgb200_assign_lse(const float* sim, float* lse_row, float* lse_col, void* ws
   float* pm = static_cast<float*>(ws);
   float* ps = pm + (size_t)B * nstrips * N;
   assign_lse_kernel<<<dim3(nstrips, B), 256, 0, stream>>>(sim, lse_row, pm, ps, M, N, nstrips);
-  assign_col_lse_merge_kernel<<<dim3((N + 63) / 64, B), 64, 0, stream>>>(pm, ps, lse_col, N, nstrips);
+  assign_col_lse_merge_kernel<<<dim3((N + 31) / 32, B), 256, 0, stream>>>(pm, ps, lse_col, N, nstrips);
   return check_launch("assign_lse");
 }
 
@@ -632,8 +677,8 @@ int lgb200_assign_scores(const float* sim, const float* lse_row, const float* ls
   a.colpart_i = reinterpret_cast<int*>(a.colpart_v + (size_t)B * nstrips * N);
   a.pos_row_sum = pos_row_sum; a.row_expsum = row_expsum; a.M = M; a.N = N; a.nstrips = nstrips;
   assign_scores_kernel<<<dim3(nstrips, B), 256, 0, stream>>>(a);
-  assign_col_arg_merge_kernel<<<dim3((N + 1 + 127) / 128, B), 128, 0, stream>>>(a.colpart_v, a.colpart_i, dust1, colmax,
-                                                                                colarg, scores, M, N, nstrips);
+  assign_col_arg_merge_kernel<<<dim3((N + 1 + 31) / 32, B), 256, 0, stream>>>(a.colpart_v, a.colpart_i, dust1, colmax,
+                                                                              colarg, scores, M, N, nstrips);
   return check_launch("assign_scores");
 }
 
