@@ -43,33 +43,37 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (one `nvidia-smi -lms` process
+    started before and stopped after it)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self._stop = index, [], threading.Event()
-        self.t = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self.index, self.rows, self.proc = index, [], None
 
     def __enter__(self):
-        self.t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            time.sleep(0.15)  # let the first samples arrive before the timed region starts
+        except Exception:
+            self.proc = None
+        self.t0 = time.time()
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self.t.join(2)
+        if self.proc is None:
+            return
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        self.rows = [[c.strip() for c in line.split(",")] for line in out.strip().splitlines() if line.strip()]
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
@@ -78,8 +82,8 @@ class ClockSampler:
             if any(len(r) > col and r[col].lower().startswith("active") for r in self.rows):
                 reasons.append(name)
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
 
 
 def host_threads():
@@ -179,7 +183,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("LGB200_BENCH_BATCH", "8")), help="pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("LGB200_BENCH_BATCH", "32")), help="pairs per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
@@ -334,7 +338,8 @@ def kernel_roofline(trainer, pool_dev, B, dev):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(name)
+            per_seq = json.load(f).get(name + "_per_sequence")
+        traffic = per_seq * 2 * B if per_seq else None  # one launch covers the 2B sequences of the batch
     return {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / peaks["tflops_sustained"], "traffic": traffic, "avg_launch_ms": avg_ms,
             "launches_timed": len(times), "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)"}

@@ -173,9 +173,10 @@ def make_pairs(B, N, seed=1234, D=256, image_size=1024, frac=0.4, M=None, with_g
         "H_0to1": t(Hs),
     }
     if with_gt:
-        ga, m0, m1 = gt_matches_from_homography(
-            data["keypoints0"].double(), data["keypoints1"].double(), data["H_0to1"].double())
-        data.update({"gt_assignment": ga, "gt_matches0": m0, "gt_matches1": m1})
+        gts = [gt_matches_from_homography(data["keypoints0"][b:b + 1].double(), data["keypoints1"][b:b + 1].double(),
+                                          data["H_0to1"][b:b + 1].double()) for b in range(B)]  # per pair: bounded memory
+        data.update({"gt_assignment": torch.cat([g[0] for g in gts]), "gt_matches0": torch.cat([g[1] for g in gts]),
+                     "gt_matches1": torch.cat([g[2] for g in gts])})
     return data
 
 
