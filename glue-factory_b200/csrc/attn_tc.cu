@@ -337,11 +337,13 @@ static_assert(F3_NWG == 4, "the v3 backward kernels are written for 4 softmax wa
 
 // Warp-local staging of the per-query lse / delta of a 16-query slice: lanes 0-15 carry lse * log2(e),
 // lanes 16-31 delta; values are broadcast with shuffles (no shared memory, no block-wide barrier).
+// The value is returned RAW (no arithmetic on it) so that the load can stay in flight for a whole tile; the
+// log2(e) factor is applied when the value is consumed one iteration later.
 __device__ __forceinline__ float load_lse_delta(const float* lse_row, const float* delta_row, int q_first, int Nq,
                                                 int lane, bool tile_valid) {
   const int qi = q_first + (lane & 15);
   if (!tile_valid || qi >= Nq) return lane < 16 ? INFINITY : 0.f;
-  return lane < 16 ? lse_row[qi] * 1.4426950408889634f : delta_row[qi];
+  return lane < 16 ? __ldg(lse_row + qi) : __ldg(delta_row + qi);
 }
 
 __global__ void __launch_bounds__(F3_THREADS, 1)
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
     for (int i = 0; i < ntiles; ++i) {
       const int buf = i & 1;
       const uint32_t tb = t_lane + F3_BUF0 + buf * 128;
-      const float cur = nxt;
+      const float cur = lane < 16 ? nxt * 1.4426950408889634f : nxt;  // lse -> log2 domain (inf stays inf)
       nxt = load_lse_delta(lse_row, del_row, (i + 1) * FB_C + c * F3_CW, Nq, lane, i + 1 < ntiles);
       mbar_wait(&sp_full[buf], (i >> 1) & 1);
       tc_fence_after();
