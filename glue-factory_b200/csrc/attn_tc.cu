@@ -335,31 +335,108 @@ __device__ __forceinline__ void load_row_part_to_tmem(const __nv_bfloat16* row_p
 }
 static_assert(F3_NWG == 4, "the v3 backward kernels are written for 4 softmax warpgroups of 16 columns");
 
-// Warp-local staging of the per-query lse / delta of a 16-query slice: lanes 0-15 carry lse * log2(e),
-// lanes 16-31 delta; values are broadcast with shuffles (no shared memory, no block-wide barrier).
-// The value is returned RAW (no arithmetic on it) so that the load can stay in flight for a whole tile; the
-// log2(e) factor is applied when the value is consumed one iteration later.
-__device__ __forceinline__ float load_lse_delta(const float* lse_row, const float* delta_row, int q_first, int Nq,
-                                                int lane, bool tile_valid) {
-  const int qi = q_first + (lane & 15);
-  if (!tile_valid || qi >= Nq) return lane < 16 ? INFINITY : 0.f;
-  return lane < 16 ? __ldg(lse_row + qi) : __ldg(delta_row + qi);
+// Optional clock64 pipeline trace of CTA (0,0,0) (-DLGB_TRACE; read back with lgb200_debug_read_trace):
+// role 0 = producer, 1 = MMA issuer, 2 = softmax warp 0, 3 = softmax warp 15; 4 time stamps per tile.
+#ifdef LGB_TRACE
+__device__ long long g_trace[4 * 64 * 4];
+#define LGB_TR(role, i, k)                                                                         \
+  do {                                                                                             \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (i) < 64) g_trace[((role) * 64 + (i)) * 4 + (k)] = clock64(); \
+  } while (0)
+// whole-CTA life time (clock64 + globaltimer at entry / exit) of CTAs 0 and 300 of the grid, in role 0 rows 40, 41
+#define LGB_TR_LIFE(k)                                                                              \
+  do {                                                                                              \
+    const int lin_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);               \
+    if (threadIdx.x == 0 && (lin_ == 0 || lin_ == 300)) {                                           \
+      unsigned long long gt_;                                                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                       \
+      g_trace[(40 + (lin_ == 300)) * 4 + (k)] = clock64();                                          \
+      g_trace[(40 + (lin_ == 300)) * 4 + (k) + 2] = (long long)gt_;                                 \
+    }                                                                                               \
+  } while (0)
+#else
+#define LGB_TR(role, i, k) do {} while (0)
+#define LGB_TR_LIFE(k) do {} while (0)
+#endif
+
+// dKV kernel: the per-QUERY softmax statistics are per-COLUMN quantities of S^T / dP^T (thread == key row), so
+// every thread would need all of them.  Instead they are folded into the contraction: the K and V rows held in
+// TMEM get 16 extra K-elements [1, 1, 0, ...] and every streamed Q / dO tile gets a 16-column side tile
+//     Q' extra = [-(lse/scale)_hi, -(lse/scale)_lo, 0...]      dO' extra = [-delta_hi, -delta_lo, 0...]
+// (hi/lo = bf16 split, ~2^-17 relative), so one more K-step of the same MMAs yields directly
+//     S'^T = K Q^T - lse/scale          dP'^T = V dO^T - delta
+// and the softmax warps are left with p = exp2(c S'), ds = p dP' scale: no broadcasts, no FFMA/FSUB per element.
+// The side tiles are written once per backward by attn_bwd_prep_kernel ([B,H,Nq,16] bf16, next to delta) and
+// arrive by TMA (SWIZZLE_32B) with the Q / dO tile.  Queries past Nq load as zeros: p = 1 there, but their dO row
+// and dP' are zero, so they add nothing to dV or dK.
+constexpr int F4_A0 = 0, F4_A1 = 40, F4_BUF0 = 80, F4_ACC0 = 336, F4_ACC1 = 400;  // TMEM columns (464 used)
+constexpr int F4_STAGES = 8;
+constexpr int F4_XBYTES = FB_C * 32;                             // side tile: 64 rows x 16 bf16
+constexpr int F4_STAGE_BYTES = 2 * FB_CBYTES + 2 * F4_XBYTES;    // Q, dO, Q-side, dO-side
+constexpr int F4_SMEM = F4_STAGES * F4_STAGE_BYTES + 256;
+
+__device__ __forceinline__ uint4 neg_hi_lo_row(float x) {
+  // bf16 (-hi, -lo, 0, ...) with hi = bf16(x), lo = bf16(x - hi)
+  const __nv_bfloat16 hi = __float2bfloat16(x);
+  return make_uint4(pack_bf16(-__bfloat162float(hi), -(x - __bfloat162float(hi))), 0u, 0u, 0u);
+}
+
+// delta[b,h,i] = sum_d dout[b,i,h,d] * out[b,i,h,d] (8 lanes per row) and the two side arrays of the dKV kernel.
+__global__ void __launch_bounds__(256)
+    attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                         const float* __restrict__ lse, float* __restrict__ delta, uint4* __restrict__ qx,
+                         uint4* __restrict__ dox, int64_t nrows /*B*N*H*/, int N, int H, float inv_scale) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = gid >> 3;  // (b, n, h) flattened token-major
+  const int sub = (int)(gid & 7);
+  float acc = 0.f;
+  if (r < nrows) {
+    const uint4 a = *reinterpret_cast<const uint4*>(out + r * FA_D + sub * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(dout + r * FA_D + sub * 8);
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pg = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __bfloat1622float2(pa[e]), fg = __bfloat1622float2(pg[e]);
+      acc = fmaf(fa.x, fg.x, acc);
+      acc = fmaf(fa.y, fg.y, acc);
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (r < nrows && sub < 4) {
+    const int h = (int)(r % H);
+    const int64_t bn = r / H;
+    const int n = (int)(bn % N);
+    const int64_t o = ((bn / N) * H + h) * N + n;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    if (sub == 0) {
+      delta[o] = acc;
+      dox[o * 2] = neg_hi_lo_row(acc);
+    } else if (sub == 1) {
+      dox[o * 2 + 1] = zero;
+    } else if (sub == 2) {
+      qx[o * 2] = neg_hi_lo_row(lse[o] * inv_scale);
+    } else {
+      qx[o * 2 + 1] = zero;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(F3_THREADS, 1)
     attn_bwd_dkv_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                           const __grid_constant__ CUtensorMap tmQx, const __grid_constant__ CUtensorMap tmDOx,
                            const __nv_bfloat16* __restrict__ kg, const __nv_bfloat16* __restrict__ vg,
-                           const float* __restrict__ lse, const float* __restrict__ delta,
                            __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int B, int Nq, int Nk,
                            int H, int kv_shift, float scale, float scale_log2) {
+  LGB_TR_LIFE(0);
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;                                // [F3_STAGES]
-  uint8_t* sDO = sQ + F3_STAGES * FB_CBYTES;         // [F3_STAGES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDO + F3_STAGES * FB_CBYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F4_STAGES * F4_STAGE_BYTES);
   uint64_t* a_ready = bars;
-  uint64_t* in_full = bars + 1;               // [F3_STAGES]
-  uint64_t* in_empty = in_full + F3_STAGES;   // [F3_STAGES]
-  uint64_t* sp_full = in_empty + F3_STAGES;   // [2]
+  uint64_t* in_full = bars + 1;               // [F4_STAGES]
+  uint64_t* in_empty = in_full + F4_STAGES;   // [F4_STAGES]
+  uint64_t* sp_full = in_empty + F4_STAGES;   // [2]
   uint64_t* pds_full = sp_full + 2;           // [2]
   uint64_t* acc_done = pds_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
@@ -372,7 +449,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(a_ready, F3_SWARPS);
-    for (int s = 0; s < F3_STAGES; ++s) {
+    for (int s = 0; s < F4_STAGES; ++s) {
       mbar_init(&in_full[s], 1);
       mbar_init(&in_empty[s], 1);
     }
@@ -386,6 +463,8 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
   if (warp == F3_SWARPS && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmQx);
+    tma_prefetch_desc(&tmDOx);
   }
   if (warp == F3_SWARPS + 1) tmem_alloc(tmem_slot, FB_TMEM_COLS);
   tc_fence_before();
@@ -397,33 +476,43 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       for (int i = 0; i < ntiles; ++i) {
-        const int s = i % F3_STAGES;
-        mbar_wait(&in_empty[s], ((i / F3_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&in_full[s], 2 * FB_CBYTES);
-        tma_load_4d(sQ + s * FB_CBYTES, &tmQ, &in_full[s], 0, h, i * FB_C, qb);
-        tma_load_4d(sDO + s * FB_CBYTES, &tmDO, &in_full[s], 0, h, i * FB_C, qb);
+        const int s = i % F4_STAGES;
+        uint8_t* st = smem + s * F4_STAGE_BYTES;
+        mbar_wait(&in_empty[s], ((i / F4_STAGES) & 1) ^ 1);
+        LGB_TR(0, i, 0);
+        mbar_expect_tx(&in_full[s], F4_STAGE_BYTES);
+        tma_load_4d(st, &tmQ, &in_full[s], 0, h, i * FB_C, qb);
+        tma_load_4d(st + FB_CBYTES, &tmDO, &in_full[s], 0, h, i * FB_C, qb);
+        tma_load_3d(st + 2 * FB_CBYTES, &tmQx, &in_full[s], 0, i * FB_C, qb * H + h);
+        tma_load_3d(st + 2 * FB_CBYTES + F4_XBYTES, &tmDOx, &in_full[s], 0, i * FB_C, qb * H + h);
+        LGB_TR(0, i, 1);
       }
     }
   } else if (warp == F3_SWARPS + 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-convergent, elected lane)
-    constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (K|V) in TMEM x (Q|dO) K-major
+    constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (K'|V') in TMEM x (Q'|dO') K-major
     constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // (P^T|dS^T) in TMEM x (dO|Q) MN-major
-    const uint64_t dQk = make_smem_desc(smem_u32(sQ), 16, 1024), dDOk = make_smem_desc(smem_u32(sDO), 16, 1024);
-    const uint64_t dQm = make_smem_desc(smem_u32(sQ), 8192, 1024), dDOm = make_smem_desc(smem_u32(sDO), 8192, 1024);
+    const uint64_t dk0 = make_smem_desc(smem_u32(smem), 16, 1024);     // K-major view of a stage's tiles
+    const uint64_t dm0 = make_smem_desc(smem_u32(smem), 8192, 1024);   // MN-major view
+    const uint64_t dx0 = make_smem_desc(smem_u32(smem) + 2 * FB_CBYTES, 16, 256, 6);  // side tiles (SWIZZLE_32B)
     const bool leader = elect_one();
-    auto issue_sp = [&](int i) {  // S^T and dP^T of query tile i into TMEM buffer i&1
-      const int s = i % F3_STAGES;
-      mbar_wait(&in_full[s], (i / F3_STAGES) & 1);
+    auto issue_sp = [&](int i) {  // S'^T and dP'^T of query tile i into TMEM buffer i&1 (5 K-steps each)
+      const int s = i % F4_STAGES;
+      mbar_wait(&in_full[s], (i / F4_STAGES) & 1);
       tc_fence_after();
       if (leader) {
-        const uint32_t tb = tmem_base + F3_BUF0 + (i & 1) * 128;
-        const uint64_t so = (uint64_t)((s * FB_CBYTES) >> 4);
+        const uint32_t tb = tmem_base + F4_BUF0 + (i & 1) * 128;
+        const uint64_t so = (uint64_t)((s * F4_STAGE_BYTES) >> 4);
+        const uint64_t tq = dk0 + so, tdo = dk0 + so + (FB_CBYTES >> 4);
+        const uint64_t tqx = dx0 + so, tdox = dx0 + so + (F4_XBYTES >> 4);
 #pragma unroll
         for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16_ts(tb, tmem_base + F3_A0 + kk * 8, dQk + so + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+          umma_bf16_ts(tb, tmem_base + F4_A0 + kk * 8, tq + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+        umma_bf16_ts(tb, tmem_base + F4_A0 + 32, tqx, idesc_s, 1u);
 #pragma unroll
         for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16_ts(tb + 64, tmem_base + F3_A1 + kk * 8, dDOk + so + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+          umma_bf16_ts(tb + 64, tmem_base + F4_A1 + kk * 8, tdo + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+        umma_bf16_ts(tb + 64, tmem_base + F4_A1 + 32, tdox, idesc_s, 1u);
         umma_commit(&sp_full[i & 1]);
       }
       __syncwarp();
@@ -433,24 +522,28 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
     issue_sp(0);
     if (ntiles > 1) issue_sp(1);
     for (int i = 0; i < ntiles; ++i) {
-      const int s = i % F3_STAGES;
+      const int s = i % F4_STAGES;
       mbar_wait(&pds_full[i & 1], (i >> 1) & 1);
       tc_fence_after();
+      if (leader) LGB_TR(1, i, 0);
       if (leader) {
-        const uint32_t tb = tmem_base + F3_BUF0 + (i & 1) * 128;
-        const uint64_t so = (uint64_t)((s * FB_CBYTES) >> 4);
+        const uint32_t tb = tmem_base + F4_BUF0 + (i & 1) * 128;
+        const uint64_t so = (uint64_t)((s * F4_STAGE_BYTES) >> 4);
+        const uint64_t mq = dm0 + so, mdo = dm0 + so + (FB_CBYTES >> 4);
 #pragma unroll
         for (int kk = 0; kk < FB_C / 16; ++kk)  // warpgroup kk wrote P^T of queries [kk*16, kk*16+16) at S col kk*16
-          umma_bf16_ts(tmem_base + F3_ACC0, tb + kk * F3_CW, dDOm + so + (uint64_t)(kk * 128), idesc_acc,
+          umma_bf16_ts(tmem_base + F4_ACC0, tb + kk * F3_CW, mdo + (uint64_t)(kk * 128), idesc_acc,
                        (i | kk) != 0 ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < FB_C / 16; ++kk)
-          umma_bf16_ts(tmem_base + F3_ACC1, tb + 64 + kk * F3_CW, dQm + so + (uint64_t)(kk * 128), idesc_acc,
+          umma_bf16_ts(tmem_base + F4_ACC1, tb + 64 + kk * F3_CW, mq + (uint64_t)(kk * 128), idesc_acc,
                        (i | kk) != 0 ? 1u : 0u);
         umma_commit(&in_empty[s]);
       }
+      if (leader) LGB_TR(1, i, 1);
       __syncwarp();
       if (i + 2 < ntiles) issue_sp(i + 2);
+      if (leader) LGB_TR(1, i, 2);
     }
     if (leader) umma_commit(acc_done);
     __syncwarp();
@@ -460,55 +553,57 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
     const int r = (warp & 3) * 32 + lane;    // key row within the tile == TMEM lane
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int row = k0 + r;
-    {  // resident A operands: this thread's 16-channel slice of its K and V rows -> TMEM
+    {  // resident A operands: this thread's 16-channel slice of its K and V rows (+ the [1,1,0..] extension) -> TMEM
       const int64_t o = (((int64_t)kb * Nk + (row < Nk ? row : 0)) * H + h) * FA_D + c * F3_CW;
-      load_row_part_to_tmem(kg + o, row < Nk, t_lane + F3_A0 + c * (F3_CW / 2));
-      load_row_part_to_tmem(vg + o, row < Nk, t_lane + F3_A1 + c * (F3_CW / 2));
+      load_row_part_to_tmem(kg + o, row < Nk, t_lane + F4_A0 + c * (F3_CW / 2));
+      load_row_part_to_tmem(vg + o, row < Nk, t_lane + F4_A1 + c * (F3_CW / 2));
+      if (c == 0) {
+        const uint32_t ext[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // bf16 (1, 1) then zeros
+        tmem_st8(t_lane + F4_A0 + 32, ext);
+        tmem_st8(t_lane + F4_A1 + 32, ext);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
     }
-    const float* lse_row = lse + ((int64_t)qb * H + h) * Nq;
-    const float* del_row = delta + ((int64_t)qb * H + h) * Nq;
-    float nxt = load_lse_delta(lse_row, del_row, c * F3_CW, Nq, lane, true);
     for (int i = 0; i < ntiles; ++i) {
       const int buf = i & 1;
-      const uint32_t tb = t_lane + F3_BUF0 + buf * 128;
-      const float cur = lane < 16 ? nxt * 1.4426950408889634f : nxt;  // lse -> log2 domain (inf stays inf)
-      nxt = load_lse_delta(lse_row, del_row, (i + 1) * FB_C + c * F3_CW, Nq, lane, i + 1 < ntiles);
+      const uint32_t tb = t_lane + F4_BUF0 + buf * 128;
       mbar_wait(&sp_full[buf], (i >> 1) & 1);
       tc_fence_after();
+      if (lane == 0 && (warp == 0 || warp == 15)) LGB_TR(2 + (warp == 15), i, 0);
       float sv[F3_CW], dp[F3_CW];
       tmem_ld16(tb + c * F3_CW, sv);
       tmem_ld16(tb + 64 + c * F3_CW, dp);
       tmem_ld_wait();
+      if (lane == 0 && (warp == 0 || warp == 15)) LGB_TR(2 + (warp == 15), i, 1);
       uint32_t pw[F3_CW / 2], dw[F3_CW / 2];
 #pragma unroll
       for (int e = 0; e < F3_CW; e += 2) {
-        const float l0 = __shfl_sync(0xffffffffu, cur, e), l1 = __shfl_sync(0xffffffffu, cur, e + 1);
-        const float e0 = __shfl_sync(0xffffffffu, cur, 16 + e), e1 = __shfl_sync(0xffffffffu, cur, 17 + e);
-        const float p0 = fast_exp2(fmaf(sv[e], scale_log2, -l0));
-        const float p1 = fast_exp2(fmaf(sv[e + 1], scale_log2, -l1));
+        const float p0 = fast_exp2(sv[e] * scale_log2), p1 = fast_exp2(sv[e + 1] * scale_log2);
         pw[e >> 1] = pack_bf16(p0, p1);
-        dw[e >> 1] = pack_bf16(p0 * (dp[e] - e0) * scale, p1 * (dp[e + 1] - e1) * scale);
+        dw[e >> 1] = pack_bf16(p0 * dp[e] * scale, p1 * dp[e + 1] * scale);
       }
+      if (lane == 0 && (warp == 0 || warp == 15)) LGB_TR(2 + (warp == 15), i, 2);
       tmem_st8(tb + c * F3_CW, pw);        // P^T over the S columns this warpgroup just consumed
       tmem_st8(tb + 64 + c * F3_CW, dw);   // dS^T over the dP columns
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[buf]);
+      if (lane == 0 && (warp == 0 || warp == 15)) LGB_TR(2 + (warp == 15), i, 3);
     }
     mbar_wait(acc_done, 0);
     tc_fence_after();
     const int64_t o = (((int64_t)kb * Nk + (row < Nk ? row : 0)) * H + h) * FA_D + c * F3_CW;
-    store_out_cols16(dv + o, t_lane + F3_ACC0 + c * F3_CW, row < Nk);
-    store_out_cols16(dk + o, t_lane + F3_ACC1 + c * F3_CW, row < Nk);
+    store_out_cols16(dv + o, t_lane + F4_ACC0 + c * F3_CW, row < Nk);
+    store_out_cols16(dk + o, t_lane + F4_ACC1 + c * F3_CW, row < Nk);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == F3_SWARPS + 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
+  LGB_TR_LIFE(1);
 }
 
 __global__ void __launch_bounds__(F3_THREADS, 1)
@@ -665,19 +760,28 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
 int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
                 void* dq, void* dk, void* dv, float* delta, int B, int Nq, int Nk, int H, int kv_shift, float scale,
                 cudaStream_t stream) {
-  int rc = attn_delta<__nv_bfloat16>(out, dout, delta, B, Nq, H, stream);
-  if (rc) return rc;
+  // workspace: delta [B*H*Nq] fp32, then the dKV side arrays qx, dox [B*H*Nq, 16] bf16 (16-byte aligned)
+  const int64_t nq_all = ((int64_t)B * H * Nq + 3) & ~(int64_t)3;
+  __nv_bfloat16* qx = reinterpret_cast<__nv_bfloat16*>(delta + nq_all);
+  __nv_bfloat16* dox = qx + nq_all * 16;
+  int rc = 0;
+  {
+    const int64_t nrows = (int64_t)B * Nq * H;
+    attn_bwd_prep_kernel<<<(unsigned)((nrows * 8 + 255) / 256), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), lse, delta,
+        reinterpret_cast<uint4*>(qx), reinterpret_cast<uint4*>(dox), nrows, Nq, H, 1.f / scale);
+  }
   const float sl2 = scale * 1.4426950408889634f;
   {
     static bool configured3 = false;
     if (!configured3) {
-      cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
+      cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM);
       LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       e = cudaFuncSetAttribute(attn_bwd_dq_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
       LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       configured3 = true;
     }
-    CUtensorMap tq, tk, tv, tdo;
+    CUtensorMap tq, tk, tv, tdo, tqx, tdox;
     if ((rc = make_qkv_tmap(&tk, k, B, Nk, H, FB_C))) return rc;
     if ((rc = make_qkv_tmap(&tv, v, B, Nk, H, FB_C))) return rc;
     attn_bwd_dq_v3_kernel<<<dim3((Nq + FB_R - 1) / FB_R, H, B), F3_THREADS, F3_SMEM, stream>>>(
@@ -685,8 +789,15 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, co
         static_cast<__nv_bfloat16*>(dq), B, Nq, Nk, H, kv_shift, scale, sl2);
     if ((rc = make_qkv_tmap(&tq, q, B, Nq, H, FB_C))) return rc;
     if ((rc = make_qkv_tmap(&tdo, dout, B, Nq, H, FB_C))) return rc;
-    attn_bwd_dkv_v3_kernel<<<dim3((Nk + FB_R - 1) / FB_R, H, B), F3_THREADS, F3_SMEM, stream>>>(
-        tq, tdo, static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v), lse, delta,
+    {
+      const uint64_t dims[3] = {16, (uint64_t)Nq, (uint64_t)B * H};
+      const uint64_t str[2] = {32, (uint64_t)Nq * 32};
+      const uint32_t box[3] = {16, (uint32_t)FB_C, 1};
+      if ((rc = make_tmap_bf16(&tqx, qx, 3, dims, str, box, 32))) return rc;
+      if ((rc = make_tmap_bf16(&tdox, dox, 3, dims, str, box, 32))) return rc;
+    }
+    attn_bwd_dkv_v3_kernel<<<dim3((Nk + FB_R - 1) / FB_R, H, B), F3_THREADS, F4_SMEM, stream>>>(
+        tq, tdo, tqx, tdox, static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v),
         static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv), B, Nq, Nk, H, kv_shift, scale, sl2);
     return check_launch("attn_bwd_tc(v3)");
   }
@@ -694,4 +805,10 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, co
 }
 
 }  // namespace lgb
+
+#ifdef LGB_TRACE
+extern "C" int lgb200_debug_read_trace(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, lgb::g_trace, sizeof(long long) * (n < 1024 ? n : 1024));
+}
+#endif
 

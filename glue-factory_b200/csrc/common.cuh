@@ -234,13 +234,16 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 //   K-major : rows of 128 B (64 bf16 along K), 8-row groups SBO = 1024 B apart; LBO unused.
 //   MN-major: rows of 128 B (64 bf16 along M/N) indexed by k, 8-k groups SBO = 1024 B apart,
 //             64-element M/N chunks LBO bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   layout: 2 = SWIZZLE_128B (default), 6 = SWIZZLE_32B (K-major rows of 32 B = one K=16 step, 8-row groups
+//   SBO = 256 B apart).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout = 2) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= static_cast<uint64_t>(1) << 46;  // descriptor version
-  d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout) << 61;
   return d;
 }
 

@@ -69,7 +69,8 @@ int lgb200_rope_split_bwd(const void* dq, const void* dk, const void* dv, const 
  * directions in one launch; 0 = self-attention).                                                */
 int lgb200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Nq, int Nk, int H,
                     int kv_shift, float scale, int dtype, cudaStream_t stream);
-/* dq [B,Nq,H,64]; dk,dv [B,Nk,H,64] (indexed by KEY batch); delta_ws: B*H*Nq floats of scratch. */
+/* dq [B,Nq,H,64]; dk,dv [B,Nk,H,64] (indexed by KEY batch); delta_ws: 17 * round_up(B*H*Nq, 4) floats of
+ * scratch (rowsum(dout*out) and the per-query side tiles of the dK/dV kernel), 16-byte aligned.        */
 int lgb200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
                     void* dq, void* dk, void* dv, float* delta_ws, int B, int Nq, int Nk, int H, int kv_shift,
                     float scale, int dtype, cudaStream_t stream);

@@ -19,3 +19,14 @@ tf = t(lambda: ops.attn_fwd(q, k, v, B // 2, 0.125))
 tb = t(lambda: ops.attn_bwd(q, k, v, out, lse, go, B // 2, 0.125))
 fl = 4 * N * N * 64 * B * H
 print(f"fwd {tf*1e3:.1f} us  {fl/tf/1e9:.0f} TFLOP/s | bwd {tb*1e3:.1f} us  {2*fl/tb/1e9:.0f} TFLOP/s (algorithmic)")
+try:  # per-kernel durations (CUPTI sees the ctypes-launched kernels too)
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(5):
+            ops.attn_fwd(q, k, v, B // 2, 0.125)
+            ops.attn_bwd(q, k, v, out, lse, go, B // 2, 0.125)
+        torch.cuda.synchronize()
+    for ev in prof.key_averages():
+        print(f"  {ev.key[:60]:60s} n={ev.count:3d} avg={ev.device_time_total / max(ev.count,1):8.1f} us")
+except Exception as ex:  # noqa: BLE001
+    print("profiler unavailable:", ex)

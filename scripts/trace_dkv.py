@@ -1,0 +1,28 @@
+"""Reads the -DLGB_TRACE clock64 pipeline trace of the dKV kernel (CTA 0) and prints per-tile deltas."""
+import ctypes, os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gluefactory_b200 import ops, _lib
+B, N, H = 8, 2048, 4
+g = torch.Generator(device="cuda").manual_seed(0)
+q, k, v, go = (torch.randn(B, N, H, 64, device="cuda", generator=g).to(torch.bfloat16) for _ in range(4))
+for _ in range(2):
+    out, lse = ops.attn_fwd(q, k, v, B // 2, 0.125)
+    ops.attn_bwd(q, k, v, out, lse, go, B // 2, 0.125)
+torch.cuda.synchronize()
+lib = _lib.load()
+buf = (ctypes.c_longlong * 1024)()
+rc = lib.lgb200_debug_read_trace(buf, 1024)
+t = torch.tensor(list(buf)).view(4, 64, 4)
+t0 = int(t[t > 0].min())
+names = ["producer: empty-wait done, side tile arrive",
+         "mma: pds-wait done, acc issued, sp(i+2) issued",
+         "softmax w0: sp-wait done, ld done, math done, arrive",
+         "softmax w15: sp-wait done, ld done, math done, arrive"]
+for role in range(4):
+    print(names[role])
+    for i in range(32):
+        row = [int(x) - t0 if x > 0 else -1 for x in t[role, i]]
+        print(f"  tile {i:2d}: " + " ".join(f"{x:7d}" for x in row))
+for r, name in ((40, "CTA 0"), (41, "CTA 300")):
+    c0, c1, g0, g1 = (int(x) for x in t[0, r])
+    print(f"{name}: life {c1 - c0} clk = {g1 - g0} ns  ({(c1 - c0) / max(g1 - g0, 1):.3f} GHz); entry at {c0 - t0} clk rel. to first stamp")
