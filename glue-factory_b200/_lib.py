@@ -36,6 +36,9 @@ SIGNATURES = {
     "lgb200_assign_bwd": (_i, [_vp] * 8 + [_i, _i, _i, _i, _vp]),
     "lgb200_filter_matches": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_head_logsig": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "lgb200_head_token_bwd_ws_floats": (_i, [_i]),
+    "lgb200_head_token_fwd": (_i, [_vp] * 9 + [_i64, _i, _i, _vp]),
+    "lgb200_head_token_bwd": (_i, [_vp] * 9 + [_i64, _i, _i, _vp]),
     "lgb200_head_terms_fwd": (_i, [_vp] * 14 + [_f] + [_vp] * 6 + [_i, _i, _i, _vp]),
     "lgb200_head_terms_bwd": (_i, [_vp] * 13 + [_f] + [_vp] * 3 + [_i, _i, _i, _vp]),
     "lgb200_heads_ws_bytes": (_sz, [_i, _i, _i]),

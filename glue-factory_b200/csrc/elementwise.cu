@@ -138,138 +138,224 @@ __global__ void __launch_bounds__(256) rope_split_bwd_kernel(const T* __restrict
 // ---------------------------------------------------------------------------------------------
 // LayerNorm + GELU: one warp per token, W = 128 * VPL channels (VPL float4/bf16x4 groups per lane)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// Phi(z) = 0.5 (1 + erf(z / sqrt 2)) and e = exp(-z^2 / 2) from ONE exponential and ONE reciprocal:
+// erfc(|x|) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-x^2), t = 1 / (1 + p |x|)   (Abramowitz-Stegun 7.1.26,
+// |error| <= 1.5e-7 absolute, i.e. fp32 round-off level; libdevice erff + expf cost ~3x the instructions).
+__device__ __forceinline__ void gauss_cdf_pdf(float z, float& cdf, float& ez) {
+  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678118654752f, fabsf(z), 1.f));
+  ez = fast_exp2(-0.72134752044448170f * z * z);
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float half_erfc = 0.5f * p * t * ez;  // Phi(-|z|)
+  cdf = z >= 0.f ? 1.f - half_erfc : half_erfc;
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float cdf, ez;
+  gauss_cdf_pdf(x, cdf, ez);
+  return x * cdf;
+}
 __device__ __forceinline__ float gelu_grad(float x) {
-  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, ez;
+  gauss_cdf_pdf(x, cdf, ez);
+  return fmaf(x * 0.3989422804014327f, ez, cdf);
 }
 
-template <typename T> __device__ __forceinline__ void load4(const T* p, float* o);
-template <> __device__ __forceinline__ void load4<float>(const float* p, float* o) {
-  float4 a = *reinterpret_cast<const float4*>(p);
-  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
-}
-template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float* o) {
-  uint2 u = *reinterpret_cast<const uint2*>(p);
-  o[0] = __uint_as_float(u.x << 16); o[1] = __uint_as_float(u.x & 0xffff0000u);
-  o[2] = __uint_as_float(u.y << 16); o[3] = __uint_as_float(u.y & 0xffff0000u);
-}
-template <typename T> __device__ __forceinline__ void store4(T* p, const float* o);
-template <> __device__ __forceinline__ void store4<float>(float* p, const float* o) {
+// 8 consecutive elements as loaded (conversion deferred so a prefetched token costs 4 registers per chunk in bf16)
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ static Raw8 load(const float* p) {
+    Raw8 r;
+    r.a = *reinterpret_cast<const float4*>(p);
+    r.b = *reinterpret_cast<const float4*>(p + 4);
+    return r;
+  }
+  __device__ void unpack(float* o) const {
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+};
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 u;
+  __device__ static Raw8 load(const __nv_bfloat16* p) {
+    Raw8 r;
+    r.u = *reinterpret_cast<const uint4*>(p);
+    return r;
+  }
+  __device__ void unpack(float* o) const {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      o[2 * i] = __uint_as_float(w[i] << 16);
+      o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+template <typename T> __device__ __forceinline__ void store8(T* p, const float* o);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float* o) {
   *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
 }
-template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float* o) {
-  uint2 u;
-  u.x = pack_bf16(o[0], o[1]);
-  u.y = pack_bf16(o[2], o[3]);
-  *reinterpret_cast<uint2*>(p) = u;
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float* o) {
+  uint4 u;
+  u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+  *reinterpret_cast<uint4*>(p) = u;
 }
 
-template <typename T, int VPL>
+// forward: one warp per token, 16-byte accesses (lane owns 8 consecutive features of every 256-wide chunk), the
+// loads of TPW tokens in flight together; two-pass mean / variance on the registers.
+template <typename T, int NCH, int TPW>
 __global__ void __launch_bounds__(256) ln_gelu_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, T* __restrict__ y,
                                                          float* __restrict__ mean, float* __restrict__ rstd,
                                                          int64_t ntok, float eps) {
-  constexpr int W = 128 * VPL;
-  const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  constexpr int W = 256 * NCH;
   const int lane = threadIdx.x & 31;
-  if (tok >= ntok) return;
-  float v[VPL][4];
-  float sum = 0.f;
+  const int64_t tok0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * TPW;
+  if (tok0 >= ntok) return;
+  Raw8<T> raw[TPW][NCH];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    load4<T>(x + tok * W + i * 128 + lane * 4, v[i]);
-    sum += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
-  }
-  const float mu = warp_sum(sum) * (1.f / W);
-  float sq = 0.f;
+  for (int t = 0; t < TPW; ++t)
+    if (tok0 + t < ntok) {
 #pragma unroll
-  for (int i = 0; i < VPL; ++i)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float d = v[i][e] - mu;
-      sq += d * d;
+      for (int ch = 0; ch < NCH; ++ch) raw[t][ch] = Raw8<T>::load(x + (tok0 + t) * W + ch * 256 + lane * 8);
     }
-  const float rs = rsqrtf(warp_sum(sq) * (1.f / W) + eps);
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    float g[4], bb[4], o[4];
-    load4<float>(gamma + i * 128 + lane * 4, g);
-    load4<float>(beta + i * 128 + lane * 4, bb);
+  for (int t = 0; t < TPW; ++t) {
+    const int64_t tok = tok0 + t;
+    if (tok >= ntok) break;
+    float v[NCH][8];
+    float sum = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) o[e] = gelu_f((v[i][e] - mu) * rs * g[e] + bb[e]);
-    store4<T>(y + tok * W + i * 128 + lane * 4, o);
-  }
-  if (lane == 0) {
-    mean[tok] = mu;
-    rstd[tok] = rs;
+    for (int ch = 0; ch < NCH; ++ch) {
+      raw[t][ch].unpack(v[ch]);
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) sum += v[ch][e] + v[ch][e + 1];
+    }
+    const float mu = warp_sum(sum) * (1.f / W);
+    float sq = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[ch][e] - mu;
+        sq = fmaf(d, d, sq);
+      }
+    const float rs = rsqrtf(warp_sum(sq) * (1.f / W) + eps);
+    const float nmr = -mu * rs;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      float g[8], bb[8], o[8];
+      Raw8<float>::load(gamma + ch * 256 + lane * 8).unpack(g);
+      Raw8<float>::load(beta + ch * 256 + lane * 8).unpack(bb);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = gelu_f(fmaf(fmaf(v[ch][e], rs, nmr), g[e], bb[e]));
+      store8<T>(y + tok * W + ch * 256 + lane * 8, o);
+    }
+    if (lane == 0) {
+      mean[tok] = mu;
+      rstd[tok] = rs;
+    }
   }
 }
 
-// backward: each CTA (8 warps) walks tokens blockIdx.x*8 + warp, + gridDim.x*8, ... and keeps per-lane
-// partial dgamma/dbeta; the 8 warps are reduced through smem and written as one partial row per CTA.
-template <typename T, int VPL>
-__global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
-                                                         const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, const float* __restrict__ mean,
-                                                         const float* __restrict__ rstd, T* __restrict__ dx,
-                                                         float* __restrict__ dgamma_part,
-                                                         float* __restrict__ dbeta_part,
-                                                         float* __restrict__ dxsum_part, int64_t ntok) {
-  constexpr int W = 128 * VPL;
-  __shared__ float s_red[8][W];
+// backward: each CTA (8 warps) walks tokens blockIdx.x*8 + warp, + gridDim.x*8, ... with the next token's x / dy
+// already in flight, and keeps per-lane partial dgamma / dbeta / sum(dx); the 8 warps are reduced through smem and
+// written as one partial row per CTA.
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256, (NCH <= 2 ? 2 : 1))
+    ln_gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const float* __restrict__ mean,
+                       const float* __restrict__ rstd, T* __restrict__ dx, float* __restrict__ dgamma_part,
+                       float* __restrict__ dbeta_part, float* __restrict__ dxsum_part, int64_t ntok) {
+  constexpr int W = 256 * NCH;
+  __shared__ __align__(16) float s_red[8][W];
+  __shared__ __align__(16) float s_g[W], s_b[W];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float g[VPL][4], bb[VPL][4], dg[VPL][4], db[VPL][4], dxs[VPL][4];
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    load4<float>(gamma + i * 128 + lane * 4, g[i]);
-    load4<float>(beta + i * 128 + lane * 4, bb[i]);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) dg[i][e] = db[i][e] = dxs[i][e] = 0.f;
+  for (int c = threadIdx.x; c < W; c += 256) {
+    s_g[c] = gamma[c];
+    s_b[c] = beta[c];
   }
-  for (int64_t tok = (int64_t)blockIdx.x * 8 + warp; tok < ntok; tok += (int64_t)gridDim.x * 8) {
-    const float mu = mean[tok], rs = rstd[tok];
-    float xh[VPL][4], dz[VPL][4];
+  __syncthreads();
+  float dg[NCH][8], db[NCH][8], dxs[NCH][8];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dg[ch][e] = db[ch][e] = dxs[ch][e] = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * 8;
+  int64_t tok = (int64_t)blockIdx.x * 8 + warp;
+  Raw8<T> rx[NCH], rg[NCH];
+  float mu = 0.f, rs = 0.f;
+  if (tok < ntok) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      rx[ch] = Raw8<T>::load(x + tok * W + ch * 256 + lane * 8);
+      rg[ch] = Raw8<T>::load(dy + tok * W + ch * 256 + lane * 8);
+    }
+    mu = mean[tok];
+    rs = rstd[tok];
+  }
+  while (tok < ntok) {
+    float xh[NCH][8], dz[NCH][8];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      rx[ch].unpack(xh[ch]);
+      rg[ch].unpack(dz[ch]);
+    }
+    const float crs = rs, nmr = -mu * rs;
+    const int64_t nxt = tok + stride;
+    if (nxt < ntok) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        rx[ch] = Raw8<T>::load(x + nxt * W + ch * 256 + lane * 8);
+        rg[ch] = Raw8<T>::load(dy + nxt * W + ch * 256 + lane * 8);
+      }
+      mu = mean[nxt];
+      rs = rstd[nxt];
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      float xv[4], gy[4];
-      load4<T>(x + tok * W + i * 128 + lane * 4, xv);
-      load4<T>(dy + tok * W + i * 128 + lane * 4, gy);
+    for (int ch = 0; ch < NCH; ++ch) {
+      float g[8], bb[8];
+      Raw8<float>::load(s_g + ch * 256 + lane * 8).unpack(g);
+      Raw8<float>::load(s_b + ch * 256 + lane * 8).unpack(bb);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        xh[i][e] = (xv[e] - mu) * rs;
-        const float z = xh[i][e] * g[i][e] + bb[i][e];
-        const float dzz = gy[e] * gelu_grad(z);  // dL/dz (LN output)
-        dg[i][e] += dzz * xh[i][e];
-        db[i][e] += dzz;
-        dz[i][e] = dzz * g[i][e];  // dL/dxhat
-        s1 += dz[i][e];
-        s2 += dz[i][e] * xh[i][e];
+      for (int e = 0; e < 8; ++e) {
+        const float h = fmaf(xh[ch][e], crs, nmr);   // normalised input
+        const float dzz = dz[ch][e] * gelu_grad(fmaf(h, g[e], bb[e]));  // dL/d(LN output)
+        dg[ch][e] = fmaf(dzz, h, dg[ch][e]);
+        db[ch][e] += dzz;
+        const float d = dzz * g[e];                  // dL/dxhat
+        s1 += d;
+        s2 = fmaf(d, h, s2);
+        xh[ch][e] = h;
+        dz[ch][e] = d;
       }
     }
     s1 = warp_sum(s1) * (1.f / W);
     s2 = warp_sum(s2) * (1.f / W);
+    const float c0 = -crs * s1, c2 = -crs * s2;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      float o[4];
+    for (int ch = 0; ch < NCH; ++ch) {
+      float o[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        o[e] = rs * (dz[i][e] - s1 - xh[i][e] * s2);
-        dxs[i][e] += o[e];
+      for (int e = 0; e < 8; ++e) {
+        o[e] = fmaf(xh[ch][e], c2, fmaf(dz[ch][e], crs, c0));  // rs (d - s1 - xhat s2)
+        dxs[ch][e] += o[e];
       }
-      store4<T>(dx + tok * W + i * 128 + lane * 4, o);
+      store8<T>(dx + tok * W + ch * 256 + lane * 8, o);
     }
+    tok = nxt;
   }
   // reduce dgamma, dbeta and the column sums of dx over the 8 warps
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
-    for (int i = 0; i < VPL; ++i)
+    for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        s_red[warp][i * 128 + lane * 4 + e] = pass == 0 ? dg[i][e] : (pass == 1 ? db[i][e] : dxs[i][e]);
+      for (int e = 0; e < 8; ++e)
+        s_red[warp][ch * 256 + lane * 8 + e] = pass == 0 ? dg[ch][e] : (pass == 1 ? db[ch][e] : dxs[ch][e]);
     __syncthreads();
     float* dst = pass == 0 ? dgamma_part : (pass == 1 ? dbeta_part : dxsum_part);
     for (int c = threadIdx.x; c < W; c += 256) {
@@ -360,7 +446,14 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ a, fl
   const int64_t r1 = min(rows, r0 + rows_per_slab);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col0 < cols) {
-    for (int64_t r = r0 + ry; r < r1; r += 32) {
+    int64_t r = r0 + ry;
+    for (; r + 96 < r1; r += 128) {  // four independent 16-byte loads in flight per thread
+      Vec8<T> v0 = Vec8<T>::load(a + r * cols + col0), v1 = Vec8<T>::load(a + (r + 32) * cols + col0);
+      Vec8<T> v2 = Vec8<T>::load(a + (r + 64) * cols + col0), v3 = Vec8<T>::load(a + (r + 96) * cols + col0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += (v0.v[e] + v1.v[e]) + (v2.v[e] + v3.v[e]);
+    }
+    for (; r < r1; r += 32) {
       Vec8<T> v = Vec8<T>::load(a + r * cols + col0);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += v.v[e];
@@ -422,6 +515,148 @@ __global__ void __launch_bounds__(256) residual_add_cast_kernel(const float* __r
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Token heads of one supervised layer (matchability lightglue.py:259-267, token confidence :74-83):
+// one warp per token, lane owns 8 consecutive features per 256-column chunk.
+//   fwd: zt[t] = (x.wm + bm, x.wt + bt), ls/du = log sigmoid(+-zt[t,0]), and the compute-dtype copy of x that feeds
+//        final_proj -- one pass over x instead of cast + skinny GEMM + logsigmoid.
+//   bwd: dx = float(dmdw) + dzt[:,0] wm  (the confidence head reads a detached x),
+//        dW2[j] = sum_t dzt[t,j] x[t], db2[j] = sum_t dzt[t,j]; per-CTA partials, last CTA sums them in order.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256) head_token_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wm,
+                                                            const float* __restrict__ bm,
+                                                            const float* __restrict__ wt,
+                                                            const float* __restrict__ bt, T* __restrict__ xc,
+                                                            float* __restrict__ zt, float* __restrict__ ls,
+                                                            float* __restrict__ du, int64_t ntok, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Vec8<float> m[NCH], c[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int col = ch * 256 + lane * 8;
+    if (col < D) {
+      m[ch] = Vec8<float>::load(wm + col);
+      c[ch] = Vec8<float>::load((wt ? wt : wm) + col);
+    }
+  }
+  const float b0 = *bm, b1 = wt ? *bt : *bm;
+  for (int64_t tok = (int64_t)blockIdx.x * 8 + warp; tok < ntok; tok += (int64_t)gridDim.x * 8) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int col = ch * 256 + lane * 8;
+      if (col < D) {
+        const Vec8<float> v = Vec8<float>::load(x + tok * D + col);
+        if (xc) {
+          Vec8<T> o;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o.v[e] = v.v[e];
+          o.store(xc + tok * D + col);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          s0 = fmaf(v.v[e], m[ch].v[e], s0);
+          s1 = fmaf(v.v[e], c[ch].v[e], s1);
+        }
+      }
+    }
+    s0 = warp_sum(s0) + b0;
+    s1 = warp_sum(s1) + b1;
+    if (lane == 0) {
+      *reinterpret_cast<float2*>(zt + 2 * tok) = make_float2(s0, s1);
+      const float l = log_sigmoid(s0);
+      ls[tok] = l;
+      du[tok] = l - s0;
+    }
+  }
+}
+
+constexpr int kHeadBwdParts = 592;  // 4 CTAs per SM
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256) head_token_bwd_kernel(const float* __restrict__ x, const T* __restrict__ dmdw,
+                                                            const float* __restrict__ dzt,
+                                                            const float* __restrict__ wm, float* __restrict__ dx,
+                                                            float* __restrict__ dW2, float* __restrict__ db2,
+                                                            float* __restrict__ part, unsigned* __restrict__ counter,
+                                                            int64_t ntok, int D) {
+  __shared__ float s_red[8][2 * 256 * NCH + 2];
+  __shared__ bool s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Vec8<float> m[NCH];
+  float a0[NCH][8], a1[NCH][8], sb0 = 0.f, sb1 = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int col = ch * 256 + lane * 8;
+    if (col < D) m[ch] = Vec8<float>::load(wm + col);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a0[ch][e] = a1[ch][e] = 0.f;
+  }
+  for (int64_t tok = (int64_t)blockIdx.x * 8 + warp; tok < ntok; tok += (int64_t)gridDim.x * 8) {
+    const float2 dz = *reinterpret_cast<const float2*>(dzt + 2 * tok);
+    sb0 += dz.x;
+    sb1 += dz.y;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int col = ch * 256 + lane * 8;
+      if (col < D) {
+        const Vec8<float> v = Vec8<float>::load(x + tok * D + col);
+        const Vec8<T> g = Vec8<T>::load(dmdw + tok * D + col);
+        Vec8<float> o;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          o.v[e] = fmaf(dz.x, m[ch].v[e], g.v[e]);
+          a0[ch][e] = fmaf(dz.x, v.v[e], a0[ch][e]);
+          a1[ch][e] = fmaf(dz.y, v.v[e], a1[ch][e]);
+        }
+        o.store(dx + tok * D + col);
+      }
+    }
+  }
+  // CTA partial: [dW2 row 0 (D) | dW2 row 1 (D) | db2 (2)]
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int col = ch * 256 + lane * 8;
+    if (col < D) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s_red[warp][col + e] = a0[ch][e];
+        s_red[warp][D + col + e] = a1[ch][e];
+      }
+    }
+  }
+  if (lane == 0) {
+    s_red[warp][2 * D] = sb0;
+    s_red[warp][2 * D + 1] = sb1;
+  }
+  __syncthreads();
+  const int width = 2 * D + 2;
+  for (int c = threadIdx.x; c < width; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_red[w][c];
+    part[(int64_t)blockIdx.x * width + c] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(counter, 1u);
+    s_last = (prev == gridDim.x - 1);
+    if (s_last) *counter = 0u;  // self-resetting for the next call
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int c = threadIdx.x; c < width; c += 256) {
+      float t = 0.f;
+      for (unsigned p = 0; p < gridDim.x; ++p) t += __ldcg(&part[(int64_t)p * width + c]);
+      if (c < 2 * D) dW2[c] = t; else db2[c - 2 * D] = t;
+    }
+  }
+}
+
 }  // namespace lgb
 
 using namespace lgb;
@@ -430,7 +665,7 @@ extern "C" {
 
 int lgb200_colsum_slabs(int64_t rows, int cols) {
   const int cb = (cols + 63) / 64;
-  int64_t want = (2 * 148 + cb - 1) / cb;           // ~2 CTAs per SM in total
+  int64_t want = (4 * 148 + cb - 1) / cb;           // ~4 CTAs per SM in total
   int64_t maxs = (rows + 255) / 256;                // at least 256 rows per slab
   int64_t n = want < maxs ? want : maxs;
   return (int)(n < 1 ? 1 : n);
@@ -508,11 +743,11 @@ int lgb200_rope_split_bwd(const void* dq, const void* dk, const void* dv, const 
 template <typename T>
 static int ln_gelu_fwd_dispatch(const void* x, const float* gamma, const float* beta, void* y, float* mean,
                                 float* rstd, int64_t ntok, int W, float eps, cudaStream_t stream) {
-  const unsigned grid = (unsigned)((ntok + 7) / 8);
+  const unsigned grid2 = (unsigned)((ntok + 15) / 16), grid1 = (unsigned)((ntok + 7) / 8);
   switch (W) {
-    case 256: ln_gelu_fwd_kernel<T, 2><<<grid, 256, 0, stream>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, ntok, eps); break;
-    case 512: ln_gelu_fwd_kernel<T, 4><<<grid, 256, 0, stream>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, ntok, eps); break;
-    case 1024: ln_gelu_fwd_kernel<T, 8><<<grid, 256, 0, stream>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, ntok, eps); break;
+    case 256: ln_gelu_fwd_kernel<T, 1, 2><<<grid2, 256, 0, stream>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, ntok, eps); break;
+    case 512: ln_gelu_fwd_kernel<T, 2, 2><<<grid2, 256, 0, stream>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, ntok, eps); break;
+    case 1024: ln_gelu_fwd_kernel<T, 4, 1><<<grid1, 256, 0, stream>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, ntok, eps); break;
     default: LGB_REQUIRE(false, kErrUnsupported, "ln_gelu: width %d not in {256,512,1024}", W);
   }
   return check_launch("ln_gelu_fwd");
@@ -542,9 +777,9 @@ static int ln_gelu_bwd_dispatch(const void* dy, const void* x, const float* gamm
                                 int64_t ntok, int W, cudaStream_t stream) {
   const unsigned grid = (unsigned)lgb200_ln_gelu_bwd_parts(ntok);
   switch (W) {
-    case 256: ln_gelu_bwd_kernel<T, 2><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, dxp, ntok); break;
-    case 512: ln_gelu_bwd_kernel<T, 4><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, dxp, ntok); break;
-    case 1024: ln_gelu_bwd_kernel<T, 8><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, dxp, ntok); break;
+    case 256: ln_gelu_bwd_kernel<T, 1><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, dxp, ntok); break;
+    case 512: ln_gelu_bwd_kernel<T, 2><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, dxp, ntok); break;
+    case 1024: ln_gelu_bwd_kernel<T, 4><<<grid, 256, 0, stream>>>((const T*)dy, (const T*)x, gamma, beta, mean, rstd, (T*)dx, dgp, dbp, dxp, ntok); break;
     default: LGB_REQUIRE(false, kErrUnsupported, "ln_gelu: width %d not in {256,512,1024}", W);
   }
   return check_launch("ln_gelu_bwd");
@@ -588,6 +823,41 @@ int lgb200_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream
   const unsigned grid = (unsigned)(((n + 7) / 8 + 255) / 256);
   cast_bf16_kernel<<<grid, 256, 0, stream>>>(src, (__nv_bfloat16*)dst, n);
   return check_launch("cast_bf16");
+}
+
+int lgb200_head_token_bwd_ws_floats(int D) { return kHeadBwdParts * (2 * D + 2); }
+
+int lgb200_head_token_fwd(const float* x, const float* wm, const float* bm, const float* wt, const float* bt,
+                          void* x_cast, float* zt, float* ls, float* du, int64_t ntok, int D, int dtype,
+                          cudaStream_t stream) {
+  LGB_REQUIRE(x && wm && bm && zt && ls && du && ntok > 0, kErrInvalid, "head_token_fwd: bad arguments");
+  LGB_REQUIRE((wt == nullptr) == (bt == nullptr), kErrInvalid, "head_token_fwd: wt/bt must both be set or null");
+  LGB_REQUIRE(D % 8 == 0 && D > 0 && D <= 512, kErrUnsupported, "head_token_fwd: D=%d not a multiple of 8 in (0,512]", D);
+  int64_t g = (ntok + 7) / 8;
+  const unsigned grid = (unsigned)(g < 1184 ? g : 1184);
+#define LGB_HT_FWD(T, NCH) \
+  head_token_fwd_kernel<T, NCH><<<grid, 256, 0, stream>>>(x, wm, bm, wt, bt, (T*)x_cast, zt, ls, du, ntok, D)
+  if (dtype == LGB200_F32) { if (D <= 256) LGB_HT_FWD(float, 1); else LGB_HT_FWD(float, 2); }
+  else if (dtype == LGB200_BF16) { if (D <= 256) LGB_HT_FWD(__nv_bfloat16, 1); else LGB_HT_FWD(__nv_bfloat16, 2); }
+  else LGB_REQUIRE(false, kErrInvalid, "head_token_fwd: bad dtype %d", dtype);
+#undef LGB_HT_FWD
+  return check_launch("head_token_fwd");
+}
+
+int lgb200_head_token_bwd(const float* x, const void* dmdw, const float* dzt, const float* wm, float* dx, float* dW2,
+                          float* db2, float* ws, unsigned* counter, int64_t ntok, int D, int dtype,
+                          cudaStream_t stream) {
+  LGB_REQUIRE(x && dmdw && dzt && wm && dx && dW2 && db2 && ws && counter && ntok > 0, kErrInvalid,
+              "head_token_bwd: bad arguments");
+  LGB_REQUIRE(D % 8 == 0 && D > 0 && D <= 512, kErrUnsupported, "head_token_bwd: D=%d not a multiple of 8 in (0,512]", D);
+#define LGB_HT_BWD(T, NCH)                                                                                     \
+  head_token_bwd_kernel<T, NCH><<<kHeadBwdParts, 256, 0, stream>>>(x, (const T*)dmdw, dzt, wm, dx, dW2, db2, ws, \
+                                                                   counter, ntok, D)
+  if (dtype == LGB200_F32) { if (D <= 256) LGB_HT_BWD(float, 1); else LGB_HT_BWD(float, 2); }
+  else if (dtype == LGB200_BF16) { if (D <= 256) LGB_HT_BWD(__nv_bfloat16, 1); else LGB_HT_BWD(__nv_bfloat16, 2); }
+  else LGB_REQUIRE(false, kErrInvalid, "head_token_bwd: bad dtype %d", dtype);
+#undef LGB_HT_BWD
+  return check_launch("head_token_bwd");
 }
 
 }  // extern "C"

@@ -42,17 +42,19 @@ def _bgrad(dy):
 
 
 def _dgrad_acc(acc, dy, w):
-    """acc (fp32 [T, in]) + dy (compute dtype [T, out]) @ w ([out, in]) -> fp32, in the GEMM epilogue when
-    torch exposes addmm(out_dtype=...) for bf16 operands, else GEMM + mixed-dtype add."""
+    """acc (fp32 [T, in]) += dy (compute dtype [T, out]) @ w ([out, in]), IN PLACE, in the GEMM epilogue when
+    torch exposes addmm(out_dtype=..., out=acc) for bf16 operands, else GEMM + mixed-dtype add.  Every `acc`
+    handed in is a gradient buffer this engine owns (HeadFn's fresh dx or autograd's accumulation result), so
+    overwriting it saves the 134 MB copy an out-of-place addmm starts with."""
     global _ADDMM_DTYPE_OK
     if dy.dtype == torch.float32:
-        return torch.addmm(acc, dy, w)
+        return acc.addmm_(dy, w)
     if _ADDMM_DTYPE_OK:
         try:
-            return torch.addmm(acc, dy, w, out_dtype=torch.float32)
+            return torch.addmm(acc, dy, w, out_dtype=torch.float32, out=acc)
         except (TypeError, RuntimeError):
             _ADDMM_DTYPE_OK = False
-    return acc + torch.mm(dy, w)
+    return acc.add_(torch.mm(dy, w))
 
 
 def _attend_fwd(q, k, v, sizes, H, cross):
@@ -138,7 +140,7 @@ class LayerFn(torch.autograd.Function):
         h2.addmm_(msg2, W0c[:, D:].t())
         gg, mean2, rstd2 = ops.ln_gelu_fwd(h2, g2, be2, eps)
         y2 = torch.addmm(b3c, gg, W3c.t())
-        x2 = x1 + y2
+        x2, _ = ops.residual_add_cast(x1, y2, None)
         ctx.save_for_backward(theta, x16, q, k, v, att, msg, h, mean1, rstd1, g, x1_16, qk, vv, m, msg2, h2, mean2,
                               rstd2, gg, *lse1, *lse2, *w)
         ctx.meta = (sizes, H, cdt, len(lse1), len(lse2), D)
@@ -204,7 +206,10 @@ class HeadFn(torch.autograd.Function):
         t0 = B * M
         dev = x.device
         x = x.contiguous()
-        _, x16 = ops.residual_add_cast(x, None, cdt)
+        has_tok = wt is not None
+        # compute-dtype x for final_proj + [matchability logit, token-confidence logit] per token, one pass over x
+        x16, zt, ls, du = ops.head_token_fwd(x, wm.view(-1), bm, wt.view(-1) if has_tok else None,
+                                             bt if has_tok else None, cdt)
         md = torch.addmm(bfp, x16, wfp.t())  # final_proj, un-scaled; d^-1/2 is folded into sim
         md0, md1 = md[:t0].view(B, M, D), md[t0:].view(B, N, D)
         alpha = float(D) ** -0.5
@@ -212,12 +217,6 @@ class HeadFn(torch.autograd.Function):
             sim = ops.gemm_bf16(md0, md1, alpha=alpha)
         else:
             sim = torch.bmm(md0, md1.transpose(1, 2)).mul_(alpha)
-        # [matchability logit, token-confidence logit] per token in one skinny GEMM (fp32)
-        has_tok = wt is not None
-        W2 = torch.cat([wm, wt if has_tok else wm], 0)
-        b2 = torch.cat([bm, bt if has_tok else bm], 0)
-        zt = torch.addmm(b2, x, W2.t())
-        ls, du = ops.head_logsig(zt)
         ls0, ls1, du0, du1 = ls[:t0].view(B, M), ls[t0:].view(B, N), du[:t0].view(B, M), du[t0:].view(B, N)
         st = ops.assign_stats(sim, ls0, ls1, du0, du1, gt_u8=gt["u8"], dense=False)
         out = torch.empty(4, B, device=dev, dtype=torch.float32)
@@ -274,9 +273,7 @@ class HeadFn(torch.autograd.Function):
             dmd1 = torch.bmm(dsim.transpose(1, 2), md0.float()).to(cdt)
         dmd = torch.cat([dmd0.reshape(t0, D), dmd1.reshape(B * N, D)], 0)
         dWfp, dbfp = _wgrad(dmd, x16), _bgrad(dmd)
-        dx = torch.mm(dmd, wfp).float()
-        dx.addr_(dzt[:, 0], wm.view(-1))  # the token-confidence head reads a detached x (lightglue.py:82-83)
-        dW2 = torch.mm(dzt.t(), x)
-        db2 = dzt.sum(0)
+        # dx = dmd W_fp + dzt[:,0] wm (the token-confidence head reads a detached x, lightglue.py:82-83), dW2, db2
+        dx, dW2, db2 = ops.head_token_bwd(x, torch.mm(dmd, wfp), dzt, wm.view(-1))
         dwt, dbt = (dW2[1:2], db2[1:2]) if has_tok else (None, None)
         return dx, None, None, None, None, None, None, None, dWfp, dbfp, dW2[0:1], db2[0:1], dwt, dbt

@@ -181,11 +181,13 @@ def colsum(a):
 
 
 def residual_add_cast(x, y, cdt, want_sum=True):
-    """x fp32 [.., D] + y (compute dtype or None) -> (x_new fp32 or None, cast(x_new) in cdt)."""
+    """x fp32 [.., D] + y (compute dtype or None) -> (x_new fp32 or None, cast(x_new) in cdt).
+    cdt None: only the fp32 sum is produced (y gives the kernel's element type)."""
     _chk(x, torch.float32)
     xo = torch.empty_like(x) if (want_sum and y is not None) else None
-    xc = torch.empty(x.shape, device=x.device, dtype=cdt)
-    call("lgb200_residual_add_cast", ptr(x), ptr(y), ptr(xo), ptr(xc), x.numel(), _code(cdt), stream_ptr())
+    xc = torch.empty(x.shape, device=x.device, dtype=cdt) if cdt is not None else None
+    call("lgb200_residual_add_cast", ptr(x), ptr(y), ptr(xo), ptr(xc), x.numel(),
+         _code(cdt if cdt is not None else y.dtype), stream_ptr())
     return (xo if xo is not None else x), xc
 
 
@@ -285,6 +287,43 @@ def head_logsig(zt):
     du = torch.empty_like(ls)
     call("lgb200_head_logsig", ptr(zt), ptr(ls), ptr(du), T, stream_ptr())
     return ls, du
+
+
+_head_token_counters = {}
+
+
+def head_token_fwd(x, wm, bm, wt, bt, cdt):
+    """x [T,D] fp32 -> (x in cdt, zt [T,2] = (matchability, token-confidence) logits, ls, du); see lgb200.h."""
+    _chk(x, torch.float32)
+    T, D = x.shape
+    dev = x.device
+    xc = torch.empty(T, D, device=dev, dtype=cdt)
+    zt = torch.empty(T, 2, device=dev, dtype=torch.float32)
+    ls = torch.empty(T, device=dev, dtype=torch.float32)
+    du = torch.empty_like(ls)
+    f = lambda t: None if t is None else t.detach().float().contiguous()  # noqa: E731
+    wm, bm, wt, bt = f(wm), f(bm), f(wt), f(bt)
+    call("lgb200_head_token_fwd", ptr(x), ptr(wm), ptr(bm), ptr(wt), ptr(bt), ptr(xc), ptr(zt), ptr(ls), ptr(du), T, D,
+         _code(cdt), stream_ptr())
+    return xc, zt, ls, du
+
+
+def head_token_bwd(x, dmdw, dzt, wm):
+    """-> (dx [T,D] fp32 = float(dmdw) + dzt[:,0] wm, dW2 [2,D] = dzt^T x, db2 [2])."""
+    _chk(x, torch.float32), _chk(dmdw), _chk(dzt, torch.float32)
+    T, D = x.shape
+    dev = x.device
+    cnt = _head_token_counters.get(dev)
+    if cnt is None:
+        cnt = _head_token_counters[dev] = torch.zeros(1, device=dev, dtype=torch.int32)
+    dx = torch.empty_like(x)
+    dW2 = torch.empty(2, D, device=dev, dtype=torch.float32)
+    db2 = torch.empty(2, device=dev, dtype=torch.float32)
+    ws = torch.empty(_lib.load().lgb200_head_token_bwd_ws_floats(D), device=dev, dtype=torch.float32)
+    wmf = wm.detach().float().contiguous()
+    call("lgb200_head_token_bwd", ptr(x), ptr(dmdw), ptr(dzt), ptr(wmf), ptr(dx), ptr(dW2), ptr(db2), ptr(ws), ptr(cnt),
+         T, D, _code(dmdw.dtype), stream_ptr())
+    return dx, dW2, db2
 
 
 def filter_matches(rowmax, rowarg, colarg, th):

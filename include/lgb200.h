@@ -134,6 +134,19 @@ int lgb200_filter_matches(const float* rowmax, const int* rowarg, const int* col
  *                   conf = token-confidence BCE against [argmax incl. dustbin == fin] (0 when fin* NULL)
  *   head_terms_bwd: d zt for upstream g_nll[B], g_conf[B]                                           */
 int lgb200_head_logsig(const float* zt, float* ls, float* du, int64_t T, cudaStream_t stream);
+/* The two per-token linear heads in one pass over x [T,D] fp32 (D % 8 == 0, D <= 512):
+ *   head_token_fwd: zt[t] = (x[t].wm + bm, x[t].wt + bt)  (wt/bt NULL: column 1 repeats column 0),
+ *                   ls/du as head_logsig, x_cast (nullable) = x in `dtype` for final_proj.
+ *   head_token_bwd: dx = float(dmdw) + dzt[:,0] wm   (dmdw [T,D] in `dtype` = d md . W_final_proj; the confidence
+ *                   head reads a detached x, lightglue.py:82-83), dW2 [2,D] = dzt^T x, db2 [2] = column sums of dzt.
+ *                   ws: head_token_bwd_ws_floats(D) floats; counter: one uint32, zero before the first call. */
+int lgb200_head_token_bwd_ws_floats(int D);
+int lgb200_head_token_fwd(const float* x, const float* wm, const float* bm, const float* wt, const float* bt,
+                          void* x_cast, float* zt, float* ls, float* du, int64_t ntok, int D, int dtype,
+                          cudaStream_t stream);
+int lgb200_head_token_bwd(const float* x, const void* dmdw, const float* dzt, const float* wm, float* dx, float* dW2,
+                          float* db2, float* ws, unsigned* counter, int64_t ntok, int D, int dtype,
+                          cudaStream_t stream);
 int lgb200_head_terms_fwd(const float* zt, const float* pos_row_sum, const float* rowcnt, const float* colcnt,
                           const float* neg0, const float* neg1, const float* rowmax, const int* rowarg,
                           const float* colmax, const int* colarg, const int* fin0, const int* fin1,

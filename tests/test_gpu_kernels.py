@@ -214,6 +214,30 @@ def test_colsum_and_residual(dtype, rows, cols):
     assert torch.equal(xc2, x.to(dtype))
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("T,D,has_tok", [(4096, 256, True), (1001, 128, False), (777, 512, True), (5, 64, True)])
+def test_head_token_kernels(dtype, T, D, has_tok):
+    """Fused matchability / token-confidence heads (lightglue.py:74-83, 259-267) against torch in fp64."""
+    x = _rand(T, D, seed=1)
+    wm, bm = _rand(1, D, seed=2) * 0.1, _rand(1, seed=3)
+    wt, bt = (_rand(1, D, seed=4) * 0.1, _rand(1, seed=5)) if has_tok else (None, None)
+    xc, zt, ls, du = ops.head_token_fwd(x, wm.view(-1), bm, wt.view(-1) if has_tok else None, bt, dtype)
+    assert torch.equal(xc, x.to(dtype))
+    z0 = x.double() @ wm.double().t() + bm.double()
+    z1 = x.double() @ wt.double().t() + bt.double() if has_tok else z0
+    assert rel_err(zt, torch.cat([z0, z1], 1)) < 1e-5
+    assert rel_err(ls, torch.nn.functional.logsigmoid(z0[:, 0])) < 1e-5
+    assert rel_err(du, torch.nn.functional.logsigmoid(-z0[:, 0])) < 1e-5
+    # backward
+    dmdw = _rand(T, D, seed=6, dtype=dtype)
+    dzt = _rand(T, 2, seed=7)
+    for _ in range(2):  # second call checks the self-resetting arrival counter
+        dx, dW2, db2 = ops.head_token_bwd(x, dmdw, dzt, wm.view(-1))
+        assert rel_err(dx, dmdw.double() + dzt[:, :1].double() * wm.double()) < 1e-6
+        assert rel_err(dW2, dzt.double().t() @ x.double()) < 1e-5
+        assert rel_err(db2, dzt.double().sum(0)) < 1e-5
+
+
 def test_adam_flat_matches_torch():
     n = 100_003
     p = _rand(n, seed=1)
