@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(256) rope_split_bwd_kernel(const T* __restrict
 // erfc(|x|) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-x^2), t = 1 / (1 + p |x|)   (Abramowitz-Stegun 7.1.26,
 // |error| <= 1.5e-7 absolute, i.e. fp32 round-off level; libdevice erff + expf cost ~3x the instructions).
 __device__ __forceinline__ void gauss_cdf_pdf(float z, float& cdf, float& ez) {
-  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678118654752f, fabsf(z), 1.f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, fabsf(z), 1.f)));
   ez = fast_exp2(-0.72134752044448170f * z * z);
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
@@ -260,108 +261,100 @@ __global__ void __launch_bounds__(256) ln_gelu_fwd_kernel(const T* __restrict__ 
   }
 }
 
-// backward: each CTA (8 warps) walks tokens blockIdx.x*8 + warp, + gridDim.x*8, ... with the next token's x / dy
-// already in flight, and keeps per-lane partial dgamma / dbeta / sum(dx); the 8 warps are reduced through smem and
-// written as one partial row per CTA.
+// backward: a token is handled by NCH cooperating warps (one 256-column chunk each, so a lane carries only
+// 3 x 8 column accumulators and nothing spills); the 8/NCH token slots of a CTA walk tokens
+// blockIdx.x*(8/NCH) + slot, + gridDim.x*(8/NCH), ... with the next token's x / dy already in flight.  The two
+// row sums of the LayerNorm backward are exchanged between the NCH warps through smem and a named barrier.
+// Per-lane partial dgamma / dbeta / sum(dx) are reduced over the token slots and written as one partial row per CTA.
 template <typename T, int NCH>
-__global__ void __launch_bounds__(256, (NCH <= 2 ? 2 : 1))
+__global__ void __launch_bounds__(256, 2)
     ln_gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
                        const float* __restrict__ beta, const float* __restrict__ mean,
                        const float* __restrict__ rstd, T* __restrict__ dx, float* __restrict__ dgamma_part,
                        float* __restrict__ dbeta_part, float* __restrict__ dxsum_part, int64_t ntok) {
   constexpr int W = 256 * NCH;
-  __shared__ __align__(16) float s_red[8][W];
-  __shared__ __align__(16) float s_g[W], s_b[W];
+  constexpr int SLOTS = 8 / NCH;
+  __shared__ __align__(16) float s_red[SLOTS][W];
+  __shared__ float2 s_rows[2][SLOTS][NCH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = threadIdx.x; c < W; c += 256) {
-    s_g[c] = gamma[c];
-    s_b[c] = beta[c];
-  }
-  __syncthreads();
-  float dg[NCH][8], db[NCH][8], dxs[NCH][8];
+  const int sub = warp % NCH, slot = warp / NCH;
+  const int col = sub * 256 + lane * 8;
+  float g[8], bb[8], dg[8], db[8], dxs[8];
+  Raw8<float>::load(gamma + col).unpack(g);
+  Raw8<float>::load(beta + col).unpack(bb);
 #pragma unroll
-  for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) dg[ch][e] = db[ch][e] = dxs[ch][e] = 0.f;
-  const int64_t stride = (int64_t)gridDim.x * 8;
-  int64_t tok = (int64_t)blockIdx.x * 8 + warp;
-  Raw8<T> rx[NCH], rg[NCH];
+  for (int e = 0; e < 8; ++e) dg[e] = db[e] = dxs[e] = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * SLOTS;
+  int64_t tok = (int64_t)blockIdx.x * SLOTS + slot;
+  Raw8<T> rx, rg;
   float mu = 0.f, rs = 0.f;
   if (tok < ntok) {
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      rx[ch] = Raw8<T>::load(x + tok * W + ch * 256 + lane * 8);
-      rg[ch] = Raw8<T>::load(dy + tok * W + ch * 256 + lane * 8);
-    }
+    rx = Raw8<T>::load(x + tok * W + col);
+    rg = Raw8<T>::load(dy + tok * W + col);
     mu = mean[tok];
     rs = rstd[tok];
   }
+  int par = 0;
   while (tok < ntok) {
-    float xh[NCH][8], dz[NCH][8];
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      rx[ch].unpack(xh[ch]);
-      rg[ch].unpack(dz[ch]);
-    }
+    float xh[8], dz[8];
+    rx.unpack(xh);
+    rg.unpack(dz);
     const float crs = rs, nmr = -mu * rs;
     const int64_t nxt = tok + stride;
     if (nxt < ntok) {
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        rx[ch] = Raw8<T>::load(x + nxt * W + ch * 256 + lane * 8);
-        rg[ch] = Raw8<T>::load(dy + nxt * W + ch * 256 + lane * 8);
-      }
+      rx = Raw8<T>::load(x + nxt * W + col);
+      rg = Raw8<T>::load(dy + nxt * W + col);
       mu = mean[nxt];
       rs = rstd[nxt];
     }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      float g[8], bb[8];
-      Raw8<float>::load(s_g + ch * 256 + lane * 8).unpack(g);
-      Raw8<float>::load(s_b + ch * 256 + lane * 8).unpack(bb);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float h = fmaf(xh[ch][e], crs, nmr);   // normalised input
-        const float dzz = dz[ch][e] * gelu_grad(fmaf(h, g[e], bb[e]));  // dL/d(LN output)
-        dg[ch][e] = fmaf(dzz, h, dg[ch][e]);
-        db[ch][e] += dzz;
-        const float d = dzz * g[e];                  // dL/dxhat
-        s1 += d;
-        s2 = fmaf(d, h, s2);
-        xh[ch][e] = h;
-        dz[ch][e] = d;
-      }
+    for (int e = 0; e < 8; ++e) {
+      const float h = fmaf(xh[e], crs, nmr);                       // normalised input
+      const float dzz = dz[e] * gelu_grad(fmaf(h, g[e], bb[e]));   // dL/d(LN output)
+      dg[e] = fmaf(dzz, h, dg[e]);
+      db[e] += dzz;
+      const float d = dzz * g[e];                                  // dL/dxhat
+      s1 += d;
+      s2 = fmaf(d, h, s2);
+      xh[e] = h;
+      dz[e] = d;
     }
-    s1 = warp_sum(s1) * (1.f / W);
-    s2 = warp_sum(s2) * (1.f / W);
-    const float c0 = -crs * s1, c2 = -crs * s2;
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (NCH > 1) {
+      if (lane == 0) s_rows[par][slot][sub] = make_float2(s1, s2);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(32 * NCH) : "memory");
+      s1 = s2 = 0.f;
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      float o[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        o[e] = fmaf(xh[ch][e], c2, fmaf(dz[ch][e], crs, c0));  // rs (d - s1 - xhat s2)
-        dxs[ch][e] += o[e];
+      for (int k = 0; k < NCH; ++k) {
+        const float2 v = s_rows[par][slot][k];
+        s1 += v.x;
+        s2 += v.y;
       }
-      store8<T>(dx + tok * W + ch * 256 + lane * 8, o);
+      par ^= 1;  // the other buffer is free again once every warp of the slot passed this token's barrier
     }
+    const float c0 = -crs * s1 * (1.f / W), c2 = -crs * s2 * (1.f / W);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      o[e] = fmaf(xh[e], c2, fmaf(dz[e], crs, c0));  // rs (d - mean(d) - xhat mean(d xhat))
+      dxs[e] += o[e];
+    }
+    store8<T>(dx + tok * W + col, o);
     tok = nxt;
   }
-  // reduce dgamma, dbeta and the column sums of dx over the 8 warps
+  // reduce dgamma, dbeta and the column sums of dx over the token slots
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        s_red[warp][ch * 256 + lane * 8 + e] = pass == 0 ? dg[ch][e] : (pass == 1 ? db[ch][e] : dxs[ch][e]);
+    for (int e = 0; e < 8; ++e) s_red[slot][col + e] = pass == 0 ? dg[e] : (pass == 1 ? db[e] : dxs[e]);
     __syncthreads();
     float* dst = pass == 0 ? dgamma_part : (pass == 1 ? dbeta_part : dxsum_part);
     for (int c = threadIdx.x; c < W; c += 256) {
       float acc = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) acc += s_red[w][c];
+      for (int w = 0; w < SLOTS; ++w) acc += s_red[w][c];
       dst[(int64_t)blockIdx.x * W + c] = acc;
     }
     __syncthreads();
@@ -766,7 +759,7 @@ int lgb200_ln_gelu_fwd(const void* x, const float* gamma, const float* beta, voi
 
 int lgb200_ln_gelu_bwd_parts(int64_t ntok) {
   int64_t p = (ntok + 7) / 8;
-  return (int)(p < 296 ? p : 296);  // 2 CTAs per SM on 148 SMs
+  return (int)(p < 296 ? p : 296);  // 2 resident CTAs per SM x 148 SMs (3 per SM spills and measured 35 % slower)
 }
 
 }  // extern "C"

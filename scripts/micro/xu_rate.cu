@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(512, 1) k(float* out, long long* clk, int iter
       if (OP == 1) { unsigned r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x[i]), "f"(x[(i + 1) & 15])); acc ^= r; }
       if (OP == 2) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(x[i]));
       if (OP == 3) x[i] = __shfl_sync(0xffffffffu, x[i], (i + it) & 31);
+      if (OP == 5 && (i & 1) == 0) { float2 a = make_float2(x[i], x[i + 1]); a = __ffma2_rn(a, a, a); x[i] = a.x; x[i + 1] = a.y; }
       if (OP == 4) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i])); unsigned r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x[i]), "f"(x[(i + 1) & 15])); acc ^= r; }
     }
   }
@@ -39,5 +40,6 @@ template <int OP> void run(const char* name, int per) {
 }
 int main() {
   run<0>("MUFU.EX2", 1); run<1>("F2FP.BF16x2 (per instr)", 1); run<2>("FFMA", 1); run<3>("SHFL", 1); run<4>("EX2 + F2FP pair", 1);
+  run<5>("FFMA2 (instr; 2 FMA each)", 1);
   return 0;
 }
