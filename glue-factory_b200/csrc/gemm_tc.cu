@@ -3,9 +3,11 @@
 // sim = mdesc0 . mdesc1^T (lightglue.py:283) and its two backward contractions, which need every
 // combination of K-major / MN-major operands.
 //
-// One CTA computes a 128x128 tile of C.  Warp roles: warps 0-3 epilogue (TMEM -> registers ->
-// global), warp 4 TMA producer (one elected lane), warp 5 MMA issuer (one elected lane) + TMEM owner.
-// 4-stage smem ring, 64-wide K blocks (one 128-byte swizzle atom per operand row).
+// Persistent CTAs (one per SM) walk 128x128 tiles of C, n fastest so neighbouring CTAs share the A tile in L2.
+// Warp roles: warps 0-3 epilogue, warp 4 TMA producer (one elected lane), warp 5 MMA issuer (warp-convergent, one
+// elected lane) + TMEM owner.  4-stage smem ring of 64-wide K blocks (one 128-byte swizzle atom per operand row)
+// that runs ahead across tile boundaries; TWO accumulators in TMEM, so the MMAs of tile i+1 overlap the epilogue
+// of tile i; the epilogue transposes 32x32 blocks through swizzled smem and writes full 128-byte row segments.
 #include "common.cuh"
 #include "host_util.h"
 #include "lgb200.h"
@@ -14,22 +16,25 @@ namespace lgb {
 
 constexpr int GB_M = 128, GB_N = 128, GB_K = 64, G_STAGES = 4;
 constexpr int G_TILE = GB_M * GB_K * 2;  // 16 KiB per operand per stage
-constexpr int G_SMEM = G_STAGES * 2 * G_TILE + 256;
+constexpr int G_EPI = 4 * 32 * 32 * 4;   // per-warp 32x32 fp32 staging blocks
+constexpr int G_SMEM = G_STAGES * 2 * G_TILE + G_EPI + 256;
 
 template <bool A_MN, bool B_MN, typename OutT>
 __global__ void __launch_bounds__(192, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     OutT* __restrict__ C, int M, int N, int K, int64_t ldc, int64_t strideC, float alpha) {
+                     OutT* __restrict__ C, int M, int N, int K, int64_t ldc, int64_t strideC, float alpha,
+                     int tiles_m, int tiles_n, int ntiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + G_STAGES * G_TILE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * G_STAGES * G_TILE);
+  float* sE = reinterpret_cast<float*>(smem + 2 * G_STAGES * G_TILE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * G_STAGES * G_TILE + G_EPI);
   uint64_t* empty = full + G_STAGES;
-  uint64_t* done = empty + G_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* acc_full = empty + G_STAGES;  // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N, b = blockIdx.z;
   const int nk = (K + GB_K - 1) / GB_K;
 
   if (threadIdx.x == 0) {
@@ -38,14 +43,17 @@ __global__ void __launch_bounds__(192, 1)
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(done, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
     mbar_fence_init();
   }
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 5) tmem_alloc(tmem_slot, 128);
+  if (warp == 5) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -53,91 +61,118 @@ __global__ void __launch_bounds__(192, 1)
 
   if (warp == 4) {
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % G_STAGES;
-        const uint32_t ph = (kb / G_STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], 2 * G_TILE);
-        uint8_t* a = sA + s * G_TILE;
-        uint8_t* bb = sB + s * G_TILE;
-        if (!A_MN) {
-          tma_load_3d(a, &tmA, &full[s], kb * GB_K, m0, b);
-        } else {
-          tma_load_3d(a, &tmA, &full[s], m0, kb * GB_K, b);
-          tma_load_3d(a + 8192, &tmA, &full[s], m0 + 64, kb * GB_K, b);
-        }
-        if (!B_MN) {
-          tma_load_3d(bb, &tmB, &full[s], kb * GB_K, n0, b);
-        } else {
-          tma_load_3d(bb, &tmB, &full[s], n0, kb * GB_K, b);
-          tma_load_3d(bb + 8192, &tmB, &full[s], n0 + 64, kb * GB_K, b);
+      int it = 0;  // running k-block count across tiles (ring position)
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int n0 = (t % tiles_n) * GB_N, m0 = ((t / tiles_n) % tiles_m) * GB_M, b = t / (tiles_n * tiles_m);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % G_STAGES;
+          mbar_wait(&empty[s], ((it / G_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full[s], 2 * G_TILE);
+          uint8_t* a = sA + s * G_TILE;
+          uint8_t* bb = sB + s * G_TILE;
+          if (!A_MN) {
+            tma_load_3d(a, &tmA, &full[s], kb * GB_K, m0, b);
+          } else {
+            tma_load_3d(a, &tmA, &full[s], m0, kb * GB_K, b);
+            tma_load_3d(a + 8192, &tmA, &full[s], m0 + 64, kb * GB_K, b);
+          }
+          if (!B_MN) {
+            tma_load_3d(bb, &tmB, &full[s], kb * GB_K, n0, b);
+          } else {
+            tma_load_3d(bb, &tmB, &full[s], n0, kb * GB_K, b);
+            tma_load_3d(bb + 8192, &tmB, &full[s], n0 + 64, kb * GB_K, b);
+          }
         }
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GB_M, GB_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % G_STAGES;
-        const uint32_t ph = (kb / G_STAGES) & 1;
-        mbar_wait(&full[s], ph);
+    constexpr uint32_t idesc = make_idesc_bf16(GB_M, GB_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const uint64_t ad0 = A_MN ? make_smem_desc(smem_u32(sA), 8192, 1024) : make_smem_desc(smem_u32(sA), 16, 1024);
+    const uint64_t bd0 = B_MN ? make_smem_desc(smem_u32(sB), 8192, 1024) : make_smem_desc(smem_u32(sB), 16, 1024);
+    constexpr uint64_t a_step = (A_MN ? 2048 : 32) >> 4, b_step = (B_MN ? 2048 : 32) >> 4;
+    const bool leader = elect_one();
+    int it = 0, lt = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);  // epilogue drained this accumulator (2 tiles ago)
+      tc_fence_after();
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int s = it % G_STAGES;
+        mbar_wait(&full[s], (it / G_STAGES) & 1);
         tc_fence_after();
+        if (leader) {
+          const uint64_t so = (uint64_t)((s * G_TILE) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < GB_K / 16; ++kk) {
-          const uint64_t ad = A_MN ? make_smem_desc(a0 + s * G_TILE + kk * 2048, 8192, 1024)
-                                   : make_smem_desc(a0 + s * G_TILE + kk * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_smem_desc(b0 + s * G_TILE + kk * 2048, 8192, 1024)
-                                   : make_smem_desc(b0 + s * G_TILE + kk * 32, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < GB_K / 16; ++kk)
+            umma_bf16(tmem_base + acc * GB_N, ad0 + so + kk * a_step, bd0 + so + kk * b_step, idesc,
+                      (kb | kk) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        __syncwarp();
       }
-      umma_commit(done);
+      if (leader) umma_commit(&acc_full[acc]);
+      __syncwarp();
     }
   } else {
-    mbar_wait(done, 0);
-    tc_fence_after();
-    const int row = m0 + warp * 32 + lane;
-    OutT* crow = C + (int64_t)b * strideC + (int64_t)row * ldc + n0;
+    float* blk = sE + warp * 1024;  // this warp's 32x32 staging block, 16-byte chunks XOR-swizzled by row
     const bool vec_ok = ((ldc * sizeof(OutT)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
                         ((strideC * sizeof(OutT)) % 16 == 0);
+    int lt = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      const int n0 = (t % tiles_n) * GB_N, m0 = ((t / tiles_n) % tiles_m) * GB_M, b = t / (tiles_n * tiles_m);
+      const int acc = lt & 1;
+      mbar_wait(&acc_full[acc], (lt >> 1) & 1);
+      tc_fence_after();
+      OutT* cbase = C + (int64_t)b * strideC + (int64_t)(m0 + warp * 32) * ldc + n0;
 #pragma unroll 1
-    for (int c = 0; c < GB_N / 32; ++c) {
-      float v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
+      for (int c = 0; c < GB_N / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * GB_N + c * 32, v);
+        tmem_ld_wait();
+        if (c == GB_N / 32 - 1) {  // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
 #pragma unroll
-      for (int e = 0; e < 32; ++e) v[e] *= alpha;
-      if (row < M) {
-        const int col0 = n0 + c * 32;
-        if (vec_ok && col0 + 32 <= N) {
-          if constexpr (sizeof(OutT) == 4) {
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(blk + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+              make_float4(v[4 * j] * alpha, v[4 * j + 1] * alpha, v[4 * j + 2] * alpha, v[4 * j + 3] * alpha);
+        __syncwarp();
+        const int col = n0 + c * 32 + (lane & 7) * 4;
 #pragma unroll
-            for (int e = 0; e < 32; e += 4)
-              *reinterpret_cast<float4*>(crow + c * 32 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-              uint4 u;
-              u.x = pack_bf16(v[e], v[e + 1]); u.y = pack_bf16(v[e + 2], v[e + 3]);
-              u.z = pack_bf16(v[e + 4], v[e + 5]); u.w = pack_bf16(v[e + 6], v[e + 7]);
-              *reinterpret_cast<uint4*>(crow + c * 32 + e) = u;
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3);
+          const float4 o = *reinterpret_cast<const float4*>(blk + r * 32 + (((lane & 7) ^ (r & 7)) << 2));
+          const int row = m0 + warp * 32 + r;
+          if (row < M) {
+            OutT* dst = cbase + (int64_t)r * ldc + c * 32 + (lane & 7) * 4;
+            if (vec_ok && col + 4 <= N) {
+              if constexpr (sizeof(OutT) == 4) {
+                *reinterpret_cast<float4*>(dst) = o;
+              } else {
+                uint2 u;
+                u.x = pack_bf16(o.x, o.y);
+                u.y = pack_bf16(o.z, o.w);
+                *reinterpret_cast<uint2*>(dst) = u;
+              }
+            } else {
+              const float ov[4] = {o.x, o.y, o.z, o.w};
+              for (int e = 0; e < 4; ++e)
+                if (col + e < N) {
+                  if constexpr (sizeof(OutT) == 4) dst[e] = ov[e];
+                  else dst[e] = __float2bfloat16(ov[e]);
+                }
             }
           }
-        } else {
-          for (int e = 0; e < 32; ++e)
-            if (col0 + e < N) {
-              if constexpr (sizeof(OutT) == 4) crow[c * 32 + e] = v[e];
-              else crow[c * 32 + e] = __float2bfloat16(v[e]);
-            }
         }
+        __syncwarp();
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, 128);
+  if (warp == 5) tmem_dealloc(tmem_base, 256);
 }
 
 template <bool A_MN, bool B_MN, typename OutT>
@@ -145,13 +180,22 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, in
                        int64_t ldc, int64_t strideC, float alpha, cudaStream_t stream) {
   auto kern = gemm_bf16_kernel<A_MN, B_MN, OutT>;
   static bool configured = false;
+  static int num_sms = 0;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
     LGB_REQUIRE(e == cudaSuccess, kErrCuda, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    LGB_REQUIRE(e == cudaSuccess && num_sms > 0, kErrCuda, "gemm: cannot query the SM count");
     configured = true;
   }
-  dim3 grid((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M, batch);
-  kern<<<grid, 192, G_SMEM, stream>>>(ta, tb, static_cast<OutT*>(C), M, N, K, ldc, strideC, alpha);
+  const int tiles_m = (M + GB_M - 1) / GB_M, tiles_n = (N + GB_N - 1) / GB_N;
+  const int64_t ntiles = (int64_t)tiles_m * tiles_n * batch;
+  LGB_REQUIRE(ntiles < (1ll << 31), kErrUnsupported, "gemm: too many tiles");
+  const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);
+  kern<<<grid, 192, G_SMEM, stream>>>(ta, tb, static_cast<OutT*>(C), M, N, K, ldc, strideC, alpha, tiles_m, tiles_n,
+                                      (int)ntiles);
   return check_launch("gemm_bf16");
 }
 
