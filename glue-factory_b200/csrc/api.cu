@@ -50,6 +50,11 @@ static EncodeTiledFn get_encode_fn() {
 // bf16 tensor map with 128-byte swizzle. dims/strides fastest-first; strides in BYTES for dims 1..rank-1.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, int swizzle_bytes) {
+  return make_tmap(out, base, /*fp32=*/false, rank, dims, strides_bytes, box, swizzle_bytes);
+}
+
+int make_tmap(CUtensorMap* out, const void* base, bool fp32, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return kErrCuda;
   LGB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, kErrInvalid, "TMA base pointer not 16-byte aligned");
@@ -65,7 +70,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
       gstr[i - 1] = strides_bytes[i - 1];
     }
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, estr,
+  CUresult r = fn(out, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -7,7 +7,9 @@
 // Warp roles: warps 0-3 epilogue, warp 4 TMA producer (one elected lane), warp 5 MMA issuer (warp-convergent, one
 // elected lane) + TMEM owner.  4-stage smem ring of 64-wide K blocks (one 128-byte swizzle atom per operand row)
 // that runs ahead across tile boundaries; TWO accumulators in TMEM, so the MMAs of tile i+1 overlap the epilogue
-// of tile i; the epilogue transposes 32x32 blocks through swizzled smem and writes full 128-byte row segments.
+// of tile i; the epilogue stages 32-row x 128-byte blocks in swizzled smem and stores them with TMA.
+#include <string.h>
+
 #include "common.cuh"
 #include "host_util.h"
 #include "lgb200.h"
@@ -16,14 +18,14 @@ namespace lgb {
 
 constexpr int GB_M = 128, GB_N = 128, GB_K = 64, G_STAGES = 4;
 constexpr int G_TILE = GB_M * GB_K * 2;  // 16 KiB per operand per stage
-constexpr int G_EPI = 4 * 32 * 32 * 4;   // per-warp 32x32 fp32 staging blocks
+constexpr int G_EPI = 4 * 2 * 4096;      // per-warp staging: two 32-row x 128-byte blocks
 constexpr int G_SMEM = G_STAGES * 2 * G_TILE + G_EPI + 256;
 
 template <bool A_MN, bool B_MN, typename OutT>
 __global__ void __launch_bounds__(192, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     OutT* __restrict__ C, int M, int N, int K, int64_t ldc, int64_t strideC, float alpha,
-                     int tiles_m, int tiles_n, int ntiles) {
+                     const __grid_constant__ CUtensorMap tmC, OutT* __restrict__ C, int M, int N, int K, int64_t ldc,
+                     int64_t strideC, float alpha, int tiles_m, int tiles_n, int ntiles, int use_tma_store) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + G_STAGES * G_TILE;
@@ -52,6 +54,7 @@ __global__ void __launch_bounds__(192, 1)
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (use_tma_store) tma_prefetch_desc(&tmC);
   }
   if (warp == 5) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
@@ -114,61 +117,76 @@ __global__ void __launch_bounds__(192, 1)
       __syncwarp();
     }
   } else {
-    float* blk = sE + warp * 1024;  // this warp's 32x32 staging block, 16-byte chunks XOR-swizzled by row
-    const bool vec_ok = ((ldc * sizeof(OutT)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
-                        ((strideC * sizeof(OutT)) % 16 == 0);
-    int lt = 0;
+    // Epilogue.  Fast path: each warp stages its 32 rows x 128 bytes (32 fp32 / 64 bf16 columns) in 128B-swizzled
+    // smem and one lane hands the block to TMA (asynchronous, clips the tile at M / N); two blocks per warp so that
+    // the TMEM read-out of the next chunk overlaps the store of the previous one.  Fallback (C not 16-byte
+    // aligned): scalar / vector stores from the same staging block.
+    constexpr int CW = 128 / (int)sizeof(OutT);  // columns per staging block
+    uint8_t* stage = reinterpret_cast<uint8_t*>(sE) + warp * 8192;
+    int lt = 0, nblk = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
       const int n0 = (t % tiles_n) * GB_N, m0 = ((t / tiles_n) % tiles_m) * GB_M, b = t / (tiles_n * tiles_m);
       const int acc = lt & 1;
       mbar_wait(&acc_full[acc], (lt >> 1) & 1);
       tc_fence_after();
-      OutT* cbase = C + (int64_t)b * strideC + (int64_t)(m0 + warp * 32) * ldc + n0;
 #pragma unroll 1
-      for (int c = 0; c < GB_N / 32; ++c) {
-        float v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * GB_N + c * 32, v);
+      for (int c = 0; c < GB_N / CW; ++c, ++nblk) {
+        uint8_t* blk = stage + (nblk & 1) * 4096;
+        float v[CW];
+#pragma unroll
+        for (int q = 0; q < CW / 32; ++q)
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * GB_N + c * CW + q * 32, v + q * 32);
+        if (use_tma_store) {
+          if (lane == 0) tma_store_wait_read<1>();  // the store that used this block two chunks ago has read it
+          __syncwarp();
+        }
         tmem_ld_wait();
-        if (c == GB_N / 32 - 1) {  // accumulator fully read: hand it back to the MMA warp
+        if (c == GB_N / CW - 1) {  // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(blk + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-              make_float4(v[4 * j] * alpha, v[4 * j + 1] * alpha, v[4 * j + 2] * alpha, v[4 * j + 3] * alpha);
-        __syncwarp();
-        const int col = n0 + c * 32 + (lane & 7) * 4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + (lane >> 3);
-          const float4 o = *reinterpret_cast<const float4*>(blk + r * 32 + (((lane & 7) ^ (r & 7)) << 2));
-          const int row = m0 + warp * 32 + r;
-          if (row < M) {
-            OutT* dst = cbase + (int64_t)r * ldc + c * 32 + (lane & 7) * 4;
-            if (vec_ok && col + 4 <= N) {
-              if constexpr (sizeof(OutT) == 4) {
-                *reinterpret_cast<float4*>(dst) = o;
-              } else {
-                uint2 u;
-                u.x = pack_bf16(o.x, o.y);
-                u.y = pack_bf16(o.z, o.w);
-                *reinterpret_cast<uint2*>(dst) = u;
-              }
-            } else {
-              const float ov[4] = {o.x, o.y, o.z, o.w};
-              for (int e = 0; e < 4; ++e)
-                if (col + e < N) {
-                  if constexpr (sizeof(OutT) == 4) dst[e] = ov[e];
-                  else dst[e] = __float2bfloat16(ov[e]);
-                }
+        for (int j = 0; j < 8; ++j) {  // 16-byte chunk j of this thread's row, XOR-swizzled by the row (== SWIZZLE_128B)
+          uint4 u;
+          if constexpr (sizeof(OutT) == 4) {
+            u.x = __float_as_uint(v[4 * j] * alpha); u.y = __float_as_uint(v[4 * j + 1] * alpha);
+            u.z = __float_as_uint(v[4 * j + 2] * alpha); u.w = __float_as_uint(v[4 * j + 3] * alpha);
+          } else {
+            u.x = pack_bf16(v[8 * j] * alpha, v[8 * j + 1] * alpha);
+            u.y = pack_bf16(v[8 * j + 2] * alpha, v[8 * j + 3] * alpha);
+            u.z = pack_bf16(v[8 * j + 4] * alpha, v[8 * j + 5] * alpha);
+            u.w = pack_bf16(v[8 * j + 6] * alpha, v[8 * j + 7] * alpha);
+          }
+          *reinterpret_cast<uint4*>(blk + lane * 128 + ((j ^ (lane & 7)) << 4)) = u;
+        }
+        if (use_tma_store) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmC, blk, n0 + c * CW, m0 + warp * 32, b);
+            tma_store_commit();
+          }
+        } else {
+          __syncwarp();
+          constexpr int EPC = 16 / (int)sizeof(OutT);  // elements per 16-byte chunk
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3), row = m0 + warp * 32 + r;
+            const uint4 o = *reinterpret_cast<const uint4*>(blk + r * 128 + (((lane & 7) ^ (r & 7)) << 4));
+            const OutT* ov = reinterpret_cast<const OutT*>(&o);
+            const int col = n0 + c * CW + (lane & 7) * EPC;
+            if (row < M) {
+              OutT* dst = C + (int64_t)b * strideC + (int64_t)row * ldc + col;
+              for (int e = 0; e < EPC; ++e)
+                if (col + e < N) dst[e] = ov[e];
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
+    if (use_tma_store && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -178,6 +196,18 @@ __global__ void __launch_bounds__(192, 1)
 template <bool A_MN, bool B_MN, typename OutT>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int batch, int M, int N, int K,
                        int64_t ldc, int64_t strideC, float alpha, cudaStream_t stream) {
+  constexpr int ES = (int)sizeof(OutT);
+  CUtensorMap tc;
+  memset(&tc, 0, sizeof(tc));
+  const bool tma_ok = (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc * ES) % 16 == 0 &&
+                      (batch == 1 || (strideC * ES) % 16 == 0);
+  if (tma_ok) {
+    const uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)batch};
+    const uint64_t str[2] = {(uint64_t)ldc * ES, (uint64_t)(batch > 1 ? strideC : (int64_t)M * ldc) * ES};
+    const uint32_t box[3] = {128u / ES, 32u, 1u};
+    int rc = make_tmap(&tc, C, ES == 4, 3, dims, str, box);
+    if (rc) return rc;
+  }
   auto kern = gemm_bf16_kernel<A_MN, B_MN, OutT>;
   static bool configured = false;
   static int num_sms = 0;
@@ -194,8 +224,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, in
   const int64_t ntiles = (int64_t)tiles_m * tiles_n * batch;
   LGB_REQUIRE(ntiles < (1ll << 31), kErrUnsupported, "gemm: too many tiles");
   const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);
-  kern<<<grid, 192, G_SMEM, stream>>>(ta, tb, static_cast<OutT*>(C), M, N, K, ldc, strideC, alpha, tiles_m, tiles_n,
-                                      (int)ntiles);
+  kern<<<grid, 192, G_SMEM, stream>>>(ta, tb, tc, static_cast<OutT*>(C), M, N, K, ldc, strideC, alpha, tiles_m, tiles_n,
+                                      (int)ntiles, tma_ok ? 1 : 0);
   return check_launch("gemm_bf16");
 }
 

@@ -8,6 +8,9 @@ namespace lgb {
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, int swizzle_bytes = 128);
+// same for fp32 (fp32 = true) or bf16 elements
+int make_tmap(CUtensorMap* out, const void* base, bool fp32, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 bool env_flag(const char* name);
 
 // fp32 / bf16 CUDA-core attention (attn_simt.cu)

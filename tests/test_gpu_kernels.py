@@ -41,6 +41,15 @@ def test_gemm_bf16_tcgen05(a_mn, b_mn, shape):
     assert rel_err(c16, ref) < 4e-3
 
 
+def test_gemm_unaligned_output_uses_fallback_epilogue():
+    """N = 130: C rows are not 16-byte multiples, so the TMA-store epilogue is replaced by plain stores."""
+    a = _rand(2, 100, 64, seed=1, dtype=torch.bfloat16)
+    b = _rand(2, 130, 64, seed=2, dtype=torch.bfloat16)
+    ref = a.double() @ b.double().transpose(1, 2)
+    assert rel_err(ops.gemm_bf16(a, b, alpha=0.5), 0.5 * ref) < 1e-5
+    assert rel_err(ops.gemm_bf16(a, b, out_dtype=torch.bfloat16), ref) < 4e-3
+
+
 # ------------------------------------------------------------------------------------------------
 def _attn_ref(q, k, v, shift):
     """fp64 attention on [B,N,H,64] with the kv batch roll."""
