@@ -152,6 +152,10 @@ class LightGlue(nn.Module):
         "loss": {"gamma": 1.0, "fn": "nll", "nll_balancing": 0.5},
         "precision": "bf16",
         "engine": "fused",  # "fused": hand-scheduled layer/head nodes (engine.py); "autograd": op-by-op cross-check
+        # pred["ref_descriptors{0,1}"] = per-layer states stacked [B, L, N, D] (lightglue.py:540-541).  Their only
+        # reader is the matcher's own loss, which the fused engine feeds from the un-stacked layer outputs instead;
+        # "auto" therefore skips the two 0.6 GB stacks while training with engine == "fused".  True: always stack.
+        "stack_ref_descriptors": "auto",
     }
     required_data_keys = ["keypoints0", "keypoints1", "descriptors0", "descriptors1"]
 
@@ -321,12 +325,13 @@ class LightGlue(nn.Module):
             "matches1": m1,
             "matching_scores0": ms0,
             "matching_scores1": ms1,
-            "ref_descriptors0": torch.stack(all0, 1),
-            "ref_descriptors1": torch.stack(all1, 1),
             "log_assignment": st["scores"],
             "prune0": torch.ones_like(ms0) * L,
             "prune1": torch.ones_like(ms1) * L,
         }
+        if conf.stack_ref_descriptors is True or not (fused and self.training):
+            pred["ref_descriptors0"] = torch.stack(all0, 1)
+            pred["ref_descriptors1"] = torch.stack(all1, 1)
         if fused:
             # private side channel for loss(): the per-layer token tensors (both images, [T, D]); avoids
             # slicing the stacked ref_descriptors (whose backward would scatter into 9 zero-filled stacks).
@@ -402,9 +407,12 @@ class LightGlue(nn.Module):
     def loss(self, pred, data):
         """lightglue.py:578-627 without materialising any of the per-layer log-assignment matrices."""
         conf = self.conf
-        ref0, ref1 = pred["ref_descriptors0"], pred["ref_descriptors1"]
-        B, L, M, D = ref0.shape
-        N = ref1.shape[2]
+        ref0, ref1 = pred.get("ref_descriptors0"), pred.get("ref_descriptors1")
+        if ref0 is not None:
+            B, L, M, D = ref0.shape
+            N = ref1.shape[2]
+        else:  # fused training step without the stacked copies (conf.stack_ref_descriptors == "auto")
+            (B, M, N), L = pred["_b200_sizes"], len(pred["_b200_layers"])
         gt = data["gt_assignment"]
         gt_u8 = gt.contiguous().view(torch.uint8) if gt.dtype == torch.bool else gt.to(torch.uint8).contiguous()
         rowcnt = gt.sum(2).float()
