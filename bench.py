@@ -257,7 +257,9 @@ def main():
 
     def step_e2e(i):
         if use_graph:
-            loss, _ = trainer.step_graphed(pool[i % len(pool)])  # H2D of this step's inputs from pinned memory
+            # H2D of this step's inputs from pinned memory: queued one step ahead on a copy stream (prefetch=), so the
+            # transfer of batch i+1 overlaps the compute of batch i; every step still moves its own h2d bytes
+            loss, _ = trainer.step_graphed(pool[i % len(pool)], prefetch=pool[(i + 1) % len(pool)])
         else:
             loss, _ = trainer.step(pool[i % len(pool)], device=dev)
         host_loss.append(loss.item())                             # D2H read of the step's result

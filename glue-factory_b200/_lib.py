@@ -30,6 +30,8 @@ SIGNATURES = {
     "lgb200_ln_gelu_bwd_parts": (_i, [_i64]),
     "lgb200_ln_gelu_bwd": (_i, [_vp] * 10 + [_i64, _i, _i, _vp]),
     "lgb200_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i, _f, _vp]),
+    "lgb200_gemm_splitk_ws_floats": (_i64, [_i, _i, _i]),
+    "lgb200_gemm_bf16_splitk": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _vp]),
     "lgb200_assign_ws_bytes": (_sz, [_i, _i, _i]),
     "lgb200_assign_lse": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_assign_scores": (_i, [_vp] * 16 + [_i, _i, _i, _vp]),
@@ -90,6 +92,7 @@ KERNELS_PER_CALL = {
     "lgb200_ln_gelu_fwd": 1, "lgb200_ln_gelu_bwd": 1, "lgb200_gemm_bf16": 1, "lgb200_assign_lse": 2,
     "lgb200_assign_scores": 2, "lgb200_assign_bwd": 1, "lgb200_filter_matches": 1, "lgb200_log_double_softmax": 3,
     "lgb200_adam_flat": 1, "lgb200_cast_bf16": 1, "lgb200_colsum": 1, "lgb200_residual_add_cast": 1,
+    "lgb200_gemm_bf16_splitk": 2,
 }
 launch_count = 0          # running total of kernels launched through `call`
 timed_entry = None        # when set to an entry-point name, every call of it is bracketed by CUDA events

@@ -25,7 +25,8 @@ template <bool A_MN, bool B_MN, typename OutT>
 __global__ void __launch_bounds__(192, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, OutT* __restrict__ C, int M, int N, int K, int64_t ldc,
-                     int64_t strideC, float alpha, int tiles_m, int tiles_n, int ntiles, int use_tma_store) {
+                     int64_t strideC, float alpha, int tiles_m, int tiles_n, int ntiles, int use_tma_store,
+                     int kps /* split-K: k-blocks per split (0 = off); the tile's batch index is then the split */) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + G_STAGES * G_TILE;
@@ -66,8 +67,10 @@ __global__ void __launch_bounds__(192, 1)
     if (lane == 0) {
       int it = 0;  // running k-block count across tiles (ring position)
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int n0 = (t % tiles_n) * GB_N, m0 = ((t / tiles_n) % tiles_m) * GB_M, b = t / (tiles_n * tiles_m);
-        for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int n0 = (t % tiles_n) * GB_N, m0 = ((t / tiles_n) % tiles_m) * GB_M, bo = t / (tiles_n * tiles_m);
+        const int k_first = kps ? bo * kps : 0, k_last = kps ? min(nk, k_first + kps) : nk;
+        const int b = kps ? 0 : bo;  // split-K reads the one input batch at different k offsets
+        for (int kb = k_first; kb < k_last; ++kb, ++it) {
           const int s = it % G_STAGES;
           mbar_wait(&empty[s], ((it / G_STAGES) & 1) ^ 1);
           mbar_expect_tx(&full[s], 2 * G_TILE);
@@ -99,7 +102,9 @@ __global__ void __launch_bounds__(192, 1)
       const int acc = lt & 1;
       mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);  // epilogue drained this accumulator (2 tiles ago)
       tc_fence_after();
-      for (int kb = 0; kb < nk; ++kb, ++it) {
+      const int bo = t / (tiles_n * tiles_m);
+      const int nk_item = kps ? min(nk, (bo + 1) * kps) - bo * kps : nk;
+      for (int kb = 0; kb < nk_item; ++kb, ++it) {
         const int s = it % G_STAGES;
         mbar_wait(&full[s], (it / G_STAGES) & 1);
         tc_fence_after();
@@ -195,7 +200,7 @@ __global__ void __launch_bounds__(192, 1)
 
 template <bool A_MN, bool B_MN, typename OutT>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int batch, int M, int N, int K,
-                       int64_t ldc, int64_t strideC, float alpha, cudaStream_t stream) {
+                       int64_t ldc, int64_t strideC, float alpha, cudaStream_t stream, int kps = 0) {
   constexpr int ES = (int)sizeof(OutT);
   CUtensorMap tc;
   memset(&tc, 0, sizeof(tc));
@@ -225,13 +230,111 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, in
   LGB_REQUIRE(ntiles < (1ll << 31), kErrUnsupported, "gemm: too many tiles");
   const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);
   kern<<<grid, 192, G_SMEM, stream>>>(ta, tb, tc, static_cast<OutT*>(C), M, N, K, ldc, strideC, alpha, tiles_m, tiles_n,
-                                      (int)ntiles, tma_ok ? 1 : 0);
+                                      (int)ntiles, tma_ok ? 1 : 0, kps);
   return check_launch("gemm_bf16");
+}
+
+// C[m, n] = sum over splits (in split order: deterministic) of the fp32 partial tiles
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, int M,
+                                                           int N, int64_t ldc, int splits) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int64_t total = (int64_t)M * N;
+  if (i >= total) return;
+  if ((N & 3) == 0) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sidx = 0; sidx < splits; ++sidx) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + (int64_t)sidx * total + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float* dst = C + (i / N) * ldc + (i % N);
+    dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w;
+  } else {
+    for (int64_t e = i; e < i + 4 && e < total; ++e) {
+      float acc = 0.f;
+      for (int sidx = 0; sidx < splits; ++sidx) acc += ws[(int64_t)sidx * total + e];
+      C[(e / N) * ldc + (e % N)] = acc;
+    }
+  }
+}
+
+static int num_sms_cached() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// split-K plan for a [M,N] = sum_K product: as many splits as idle SMs allow, at least 4 k-blocks each
+static void splitk_plan(int M, int N, int K, int* splits, int* kps) {
+  const int tiles = ((M + GB_M - 1) / GB_M) * ((N + GB_N - 1) / GB_N);
+  const int nk = (K + GB_K - 1) / GB_K;
+  int s = num_sms_cached() / tiles;
+  if (s > nk / 4) s = nk / 4;
+  if (s < 1) s = 1;
+  *kps = (nk + s - 1) / s;
+  *splits = (nk + *kps - 1) / *kps;
 }
 
 }  // namespace lgb
 
 using namespace lgb;
+
+static int make_ab_maps(CUtensorMap* ta, CUtensorMap* tb, const void* A, const void* B, int batch, int M, int N, int K,
+                        int a_mn_major, int b_mn_major, int64_t lda, int64_t ldb, int64_t strideA, int64_t strideB) {
+  {
+    // A: K-major -> dims {K, M, batch}; MN-major (stored [K,M]) -> dims {M, K, batch}
+    const uint64_t inner = a_mn_major ? (uint64_t)M : (uint64_t)K, outer = a_mn_major ? (uint64_t)K : (uint64_t)M;
+    const uint64_t dims[3] = {inner, outer, (uint64_t)batch};
+    const uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(batch > 1 ? strideA : (int64_t)outer * lda) * 2};
+    const uint32_t box[3] = {64, a_mn_major ? 64u : 128u, 1};
+    int rc = make_tmap_bf16(ta, A, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t inner = b_mn_major ? (uint64_t)N : (uint64_t)K, outer = b_mn_major ? (uint64_t)K : (uint64_t)N;
+    const uint64_t dims[3] = {inner, outer, (uint64_t)batch};
+    const uint64_t str[2] = {(uint64_t)ldb * 2, (uint64_t)(batch > 1 ? strideB : (int64_t)outer * ldb) * 2};
+    const uint32_t box[3] = {64, b_mn_major ? 64u : 128u, 1};
+    int rc = make_tmap_bf16(tb, B, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int64_t lgb200_gemm_splitk_ws_floats(int M, int N, int K) {
+  int splits = 1, kps = 0;
+  splitk_plan(M, N, K, &splits, &kps);
+  return (int64_t)splits * M * N;
+}
+
+extern "C" int lgb200_gemm_bf16_splitk(const void* A, const void* B, float* C, int M, int N, int K, int a_mn_major,
+                                       int b_mn_major, int64_t lda, int64_t ldb, int64_t ldc, float* ws,
+                                       cudaStream_t stream) {
+  LGB_REQUIRE(A && B && C && ws, kErrInvalid, "gemm_bf16_splitk: null pointer");
+  LGB_REQUIRE(M > 0 && N > 0 && K > 0, kErrInvalid, "gemm_bf16_splitk: empty problem %dx%dx%d", M, N, K);
+  LGB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, kErrInvalid, "gemm_bf16_splitk: lda/ldb must be multiples of 8 elements");
+  CUtensorMap ta, tb;
+  int rc = make_ab_maps(&ta, &tb, A, B, 1, M, N, K, a_mn_major, b_mn_major, lda, ldb, 0, 0);
+  if (rc) return rc;
+  int splits = 1, kps = 0;
+  splitk_plan(M, N, K, &splits, &kps);
+#define LGB_SPLITK_CASE(AM, BMJ)                                                                                  \
+  if (a_mn_major == AM && b_mn_major == BMJ)                                                                      \
+    rc = launch_gemm<AM, BMJ, float>(ta, tb, ws, splits, M, N, K, N, (int64_t)M * N, 1.f, stream, kps);
+  LGB_SPLITK_CASE(0, 0)
+  LGB_SPLITK_CASE(0, 1)
+  LGB_SPLITK_CASE(1, 0)
+  LGB_SPLITK_CASE(1, 1)
+#undef LGB_SPLITK_CASE
+  if (rc) return rc;
+  const int64_t quads = ((int64_t)M * N + 3) / 4;
+  splitk_reduce_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, stream>>>(ws, C, M, N, ldc, splits);
+  return check_launch("gemm_bf16_splitk");
+}
 
 extern "C" int lgb200_gemm_bf16(const void* A, const void* B, void* C, int batch, int M, int N, int K, int a_mn_major,
                                 int b_mn_major, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA,
@@ -243,20 +346,7 @@ extern "C" int lgb200_gemm_bf16(const void* A, const void* B, void* C, int batch
               "gemm_bf16: batch strides must be multiples of 8 elements");
   CUtensorMap ta, tb;
   {
-    // A: K-major -> dims {K, M, batch}; MN-major (stored [K,M]) -> dims {M, K, batch}
-    const uint64_t inner = a_mn_major ? (uint64_t)M : (uint64_t)K, outer = a_mn_major ? (uint64_t)K : (uint64_t)M;
-    const uint64_t dims[3] = {inner, outer, (uint64_t)batch};
-    const uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(batch > 1 ? strideA : (int64_t)outer * lda) * 2};
-    const uint32_t box[3] = {64, a_mn_major ? 64u : 128u, 1};
-    int rc = make_tmap_bf16(&ta, A, 3, dims, str, box);
-    if (rc) return rc;
-  }
-  {
-    const uint64_t inner = b_mn_major ? (uint64_t)N : (uint64_t)K, outer = b_mn_major ? (uint64_t)K : (uint64_t)N;
-    const uint64_t dims[3] = {inner, outer, (uint64_t)batch};
-    const uint64_t str[2] = {(uint64_t)ldb * 2, (uint64_t)(batch > 1 ? strideB : (int64_t)outer * ldb) * 2};
-    const uint32_t box[3] = {64, b_mn_major ? 64u : 128u, 1};
-    int rc = make_tmap_bf16(&tb, B, 3, dims, str, box);
+    int rc = make_ab_maps(&ta, &tb, A, B, batch, M, N, K, a_mn_major, b_mn_major, lda, ldb, strideA, strideB);
     if (rc) return rc;
   }
 #define LGB_GEMM_CASE(AM, BMJ)                                                                              \

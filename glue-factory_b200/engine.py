@@ -29,6 +29,11 @@ def _wgrad(dy, a):
     global _OUT_DTYPE_OK
     if dy.dtype == torch.float32:
         return torch.mm(dy.t(), a)
+    # the split-K tcgen05 GEMM beats cuBLAS only while one 128x128 tile grid leaves most SMs to the K splits
+    # (256x256: 38 vs 46 us at T = 131072; wider outputs re-read the operands through L2 and tie at ~50 us)
+    if (dy.dtype == torch.bfloat16 and dy.shape[1] * a.shape[1] <= 256 * 256 and dy.stride(1) == 1 and a.stride(1) == 1
+            and dy.stride(0) % 8 == 0 and a.stride(0) % 8 == 0 and dy.data_ptr() % 16 == 0 and a.data_ptr() % 16 == 0):
+        return ops.wgrad_bf16(dy, a)
     if _OUT_DTYPE_OK:
         try:
             return torch.mm(dy.t(), a, out_dtype=torch.float32)

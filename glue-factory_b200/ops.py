@@ -20,10 +20,13 @@ def _code(dtype):
     raise TypeError(f"lgb200 kernels take float32 or bfloat16 tensors, got {dtype}")
 
 
-def _chk(t, dtype=None):
+def _chk(t, dtype=None, strided_rows=False):
     if not t.is_cuda:
         raise _lib.Lgb200Error("lgb200 ops take CUDA tensors only: there is no CPU fallback")
-    assert t.is_contiguous(), "lgb200 ops need contiguous tensors"
+    if strided_rows:  # 2-D view with unit inner stride (a column slice of a wider matrix)
+        assert t.dim() == 2 and t.stride(1) == 1, "lgb200 op needs rows with unit inner stride"
+    else:
+        assert t.is_contiguous(), "lgb200 ops need contiguous tensors"
     if dtype is not None:
         assert t.dtype == dtype, (t.dtype, dtype)
     return t
@@ -287,6 +290,22 @@ def head_logsig(zt):
     du = torch.empty_like(ls)
     call("lgb200_head_logsig", ptr(zt), ptr(ls), ptr(du), T, stream_ptr())
     return ls, du
+
+
+def wgrad_bf16(dy, a, out=None):
+    """dW [out, in] fp32 = dy^T a for bf16 dy [T, out], a [T, in] (rows may be strided views with unit inner stride):
+    split-K tcgen05 GEMM with both operands consumed MN-major, i.e. exactly as they lie in memory."""
+    _chk(dy, torch.bfloat16, strided_rows=True), _chk(a, torch.bfloat16, strided_rows=True)
+    T, M = dy.shape
+    N = a.shape[1]
+    assert a.shape[0] == T
+    if out is None:
+        out = torch.empty(M, N, device=dy.device, dtype=torch.float32)
+    assert out.stride(1) == 1
+    ws = torch.empty(_lib.load().lgb200_gemm_splitk_ws_floats(M, N, T), device=dy.device, dtype=torch.float32)
+    call("lgb200_gemm_bf16_splitk", ptr(dy), ptr(a), ptr(out), M, N, T, 1, 1, dy.stride(0), a.stride(0), out.stride(0),
+         ptr(ws), stream_ptr())
+    return out
 
 
 _head_token_counters = {}

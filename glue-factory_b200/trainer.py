@@ -98,7 +98,8 @@ class MatcherTrainer:
     def capture(self, example, device, warmup=3):
         """Capture forward + loss + backward + all-reduce + Adam into one CUDA graph.  `example` fixes the
         shapes; later batches are copied into the captured static input buffers."""
-        self._static = to_device(example, device)
+        # private static inputs: to_device() returns device tensors as they are, and step_graphed() overwrites these
+        self._static = _clone(to_device(example, device))
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -111,10 +112,33 @@ class MatcherTrainer:
             self._static_loss, self._static_losses = self._step_impl(self._static, graphed=True)
         return self
 
-    def step_graphed(self, data):
-        """Replay the captured step on a new batch (host or device tensors of the captured shapes)."""
-        _copy_into(self._static, data)
+    def step_graphed(self, data, prefetch=None):
+        """Replay the captured step on a new batch (host or device tensors of the captured shapes).
+
+        `prefetch`: the batch of the NEXT call (pinned host memory).  Its host-to-device copy is queued on a side
+        stream into a staging set right after this step's graph launch, so it overlaps this step's compute; the next
+        call (which must pass that same object as `data`) then only does a device-to-device copy into the captured
+        static inputs."""
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_staged_src", None) is data and data is not None:
+            cur.wait_event(self._staged_ready)
+            _copy_into(self._static, self._staged)
+            self._staged_src = None
+            self._staged_free.record(cur)
+        else:
+            _copy_into(self._static, data)
         self._graph.replay()
+        if prefetch is not None:
+            if getattr(self, "_staged", None) is None:
+                self._staged = _empty_like(self._static)
+                self._copy_stream = torch.cuda.Stream(device=self.fp.flat.device)
+                self._staged_ready, self._staged_free = torch.cuda.Event(), torch.cuda.Event()
+                self._staged_free.record(cur)
+            self._copy_stream.wait_event(self._staged_free)  # the last D2D out of the staging set has finished
+            with torch.cuda.stream(self._copy_stream):
+                _copy_into(self._staged, prefetch)
+                self._staged_ready.record(self._copy_stream)
+            self._staged_src = prefetch
         self.t += 1
         return self._static_loss, self._static_losses
 
@@ -143,6 +167,15 @@ class MatcherTrainer:
             ops.adam_flat_(self.fp.flat, self.fp.grad, self.m, self.v, self.t, self.lr, self.betas, self.eps, self.wd,
                            grad_scale=1.0 / self.world)
         return loss.detach(), losses
+
+
+def _clone(tree):
+    return {k: (_clone(v) if isinstance(v, dict) else v.clone() if torch.is_tensor(v) else v) for k, v in tree.items()}
+
+
+def _empty_like(tree):
+    return {k: (_empty_like(v) if isinstance(v, dict) else torch.empty_like(v) if torch.is_tensor(v) else v)
+            for k, v in tree.items()}
 
 
 def _copy_into(dst, src):

@@ -97,6 +97,13 @@ int lgb200_ln_gelu_bwd(const void* dy, const void* x, const float* gamma, const 
 int lgb200_gemm_bf16(const void* A, const void* B, void* C, int batch, int M, int N, int K, int a_mn_major,
                      int b_mn_major, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
                      int64_t strideC, int c_dtype, float alpha, cudaStream_t stream);
+/* Split-K form for the weight gradients dW = dy^T a of the Linear layers (torch autograd of F.linear,
+ * lightglue.py:139-148 etc.): one fp32 C [M,N] (row pitch ldc) = opA(A) * opB(B) over a very long K (the tokens).
+ * The K range is cut into as many pieces as there are idle SMs; the fp32 partial tiles go to ws
+ * (gemm_splitk_ws_floats(M,N,K) floats) and are summed in split order (deterministic).                 */
+int64_t lgb200_gemm_splitk_ws_floats(int M, int N, int K);
+int lgb200_gemm_bf16_splitk(const void* A, const void* B, float* C, int M, int N, int K, int a_mn_major,
+                            int b_mn_major, int64_t lda, int64_t ldb, int64_t ldc, float* ws, cudaStream_t stream);
 
 /* ---- assignment head: sigmoid_log_double_softmax + NLL terms + argmax --------------------------------
  * replaces lightglue.py:256-268 (two log_softmax, transposed copy, slice assignment),

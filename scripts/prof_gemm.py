@@ -19,3 +19,11 @@ fl = 2 * B * N * N * D
 print(f"sim {t1:.1f} us ({fl/t1/1e6:.0f} TF/s, {B*N*N*4/t1/1e6:.2f} TB/s out) | dmd0 {t2:.1f} us ({fl/t2/1e6:.0f} TF/s) | dmd1 {t3:.1f} us ({fl/t3/1e6:.0f} TF/s)")
 ref = torch.bmm(md0[:2].float(), md1[:2].float().transpose(1, 2)) * 0.0625
 print("max err", (ops.gemm_bf16(md0[:2].contiguous(), md1[:2].contiguous(), alpha=0.0625) - ref).abs().max().item())
+T = B * 2 * N
+dy = torch.randn(T, 512, device="cuda", generator=g).to(torch.bfloat16)
+a = torch.randn(T, 512, device="cuda", generator=g).to(torch.bfloat16)
+for (M_, N_) in ((256, 256), (512, 256), (256, 512), (768, 256)):
+    d_, a_ = dy[:, :M_].contiguous(), a[:, :N_].contiguous()
+    tw = t(lambda: ops.wgrad_bf16(d_, a_))
+    tt = t(lambda: torch.mm(d_.t(), a_, out_dtype=torch.float32))
+    print(f"wgrad [{M_}x{N_}] over T={T}: split-K {tw:.1f} us ({T*(M_+N_)*2/tw/1e6:.2f} TB/s) | cuBLAS {tt:.1f} us")

@@ -41,6 +41,20 @@ def test_gemm_bf16_tcgen05(a_mn, b_mn, shape):
     assert rel_err(c16, ref) < 4e-3
 
 
+@pytest.mark.parametrize("T,M,N", [(4096, 256, 256), (10000, 512, 256), (777, 768, 256), (300, 256, 512), (64, 128, 72)])
+def test_wgrad_splitk(T, M, N):
+    """dW = dy^T a (autograd of F.linear) through the split-K tcgen05 GEMM, both operands MN-major as stored."""
+    dy = _rand(T, M, seed=1, dtype=torch.bfloat16)
+    a = _rand(T, N, seed=2, dtype=torch.bfloat16)
+    ref = dy.double().t() @ a.double()
+    w1 = ops.wgrad_bf16(dy, a)
+    assert rel_err(w1, ref) < 1e-5
+    assert torch.equal(w1, ops.wgrad_bf16(dy, a))  # fixed summation order
+    # strided operand views (column slices of wider activations), as the layer backward passes them
+    wide = _rand(T, 2 * N, seed=3, dtype=torch.bfloat16)
+    assert rel_err(ops.wgrad_bf16(dy, wide[:, N:]), dy.double().t() @ wide[:, N:].double()) < 1e-5
+
+
 def test_gemm_unaligned_output_uses_fallback_epilogue():
     """N = 130: C rows are not 16-byte multiples, so the TMA-store epilogue is replaced by plain stores."""
     a = _rand(2, 100, 64, seed=1, dtype=torch.bfloat16)

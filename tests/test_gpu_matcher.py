@@ -149,15 +149,21 @@ def test_cuda_graph_step_matches_eager_step():
     conf = dict(synthetic.DEFAULT_CONF, n_layers=2)
     batches = [synthetic.to_device(synthetic.make_pairs(2, 256, seed=50 + i), DEV) for i in range(3)]
 
-    def run(graphed):
+    host = [{k: (v.cpu().pin_memory() if torch.is_tensor(v) else {kk: vv.cpu().pin_memory() for kk, vv in v.items()})
+             for k, v in b.items()} for b in batches]
+
+    def run(graphed, prefetch=False):
         model = _build(conf, synthetic.make_weights(conf, seed=51), "bf16")
         tr = MatcherTrainer(model, lr=1e-3)
         tr.step(batches[0])  # one eager step in both runs (it is also the capture warm-up)
         if graphed:
             tr.capture(batches[0], DEV, warmup=0)
         losses = []
-        for b in batches:
-            loss, _ = tr.step_graphed(b) if graphed else tr.step(b)
+        for i, b in enumerate(batches):
+            if prefetch:  # pinned host batches, the next one copied on the side stream during this step
+                loss, _ = tr.step_graphed(host[i], prefetch=host[i + 1] if i + 1 < len(host) else None)
+            else:
+                loss, _ = tr.step_graphed(b) if graphed else tr.step(b)
             losses.append(loss.item())
         return tr.fp.flat.clone(), losses
 
@@ -165,6 +171,9 @@ def test_cuda_graph_step_matches_eager_step():
     p_graph, l_graph = run(True)
     np.testing.assert_allclose(l_graph, l_eager, rtol=1e-5)
     assert rel_err(p_graph, p_eager) < 1e-5
+    p_pre, l_pre = run(True, prefetch=True)
+    np.testing.assert_allclose(l_pre, l_graph, rtol=1e-6)
+    assert rel_err(p_pre, p_graph) < 1e-6
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
