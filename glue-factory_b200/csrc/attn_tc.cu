@@ -47,10 +47,47 @@ constexpr int FA_S_COL = 0, FA_O_COL = 128;
 // softmax warps never wait for Q K^T; P and the per-tile O = P V are double-buffered as well, so the P V of
 // tile j runs while the softmax of tile j+1 is being computed and is folded into the register accumulator
 // one iteration later.
+// Optional clock64 pipeline trace of CTA (0,0,0) (read back with lgb200_debug_read_trace / scripts/trace_dkv.py):
+// -DLGB_TRACE=1 traces the dKV kernel, -DLGB_TRACE=3 the forward kernel.
+// role 0 = producer, 1 = MMA issuer, 2 / 3 = two softmax warps; 4 time stamps per tile.
+#ifdef LGB_TRACE
+__device__ long long g_trace[4 * 64 * 4];
+#define LGB_TR_(role, i, k)                                                                        \
+  do {                                                                                             \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (i) < 64) g_trace[((role) * 64 + (i)) * 4 + (k)] = clock64(); \
+  } while (0)
+// whole-CTA life time (clock64 + globaltimer at entry / exit) of CTAs 0 and 300 of the grid, in role 0 rows 40, 41
+#define LGB_TR_LIFE_(k)                                                                             \
+  do {                                                                                              \
+    const int lin_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);               \
+    if (threadIdx.x == 0 && (lin_ == 0 || lin_ == 300)) {                                           \
+      unsigned long long gt_;                                                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                       \
+      g_trace[(40 + (lin_ == 300)) * 4 + (k)] = clock64();                                          \
+      g_trace[(40 + (lin_ == 300)) * 4 + (k) + 2] = (long long)gt_;                                 \
+    }                                                                                               \
+  } while (0)
+#endif
+#if defined(LGB_TRACE) && LGB_TRACE == 3
+#define LGB_TRF(role, i, k) LGB_TR_(role, i, k)
+#define LGB_TRF_LIFE(k) LGB_TR_LIFE_(k)
+#else
+#define LGB_TRF(role, i, k) do {} while (0)
+#define LGB_TRF_LIFE(k) do {} while (0)
+#endif
+#if defined(LGB_TRACE) && LGB_TRACE != 3
+#define LGB_TR(role, i, k) LGB_TR_(role, i, k)
+#define LGB_TR_LIFE(k) LGB_TR_LIFE_(k)
+#else
+#define LGB_TR(role, i, k) do {} while (0)
+#define LGB_TR_LIFE(k) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(192, 2)
     attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out,
                        float* __restrict__ lse, int B, int Nq, int Nk, int H, int kv_shift, float scale_log2) {
+  LGB_TRF_LIFE(0);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + FA_QBYTES;
@@ -138,6 +175,7 @@ __global__ void __launch_bounds__(192, 2)
       const int s = j % FA_STAGES;
       mbar_wait(&p_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      if (leader) LGB_TRF(1, j, 0);
       if (leader) {
         const uint64_t dp = dP0 + (uint64_t)(((j & 1) * FA_PBYTES) >> 4);
         const uint64_t dv = dV0 + (uint64_t)((s * FA_KBYTES) >> 4);
@@ -148,8 +186,10 @@ __global__ void __launch_bounds__(192, 2)
         umma_commit(&kv_empty[s]);
         umma_commit(&o_full[j & 1]);
       }
+      if (leader) LGB_TRF(1, j, 1);
       __syncwarp();
       if (j + 2 < ntiles) issue_s(j + 2);
+      if (leader) LGB_TRF(1, j, 2);
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroup
@@ -178,10 +218,12 @@ __global__ void __launch_bounds__(192, 2)
       uint8_t* prow = sP + (j & 1) * FA_PBYTES + r * 128;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      if (lane == 0 && (warp == 0 || warp == 3)) LGB_TRF(2 + (warp == 3), j, 0);
       float sv[FA_BN];
       tmem_ld32(t_lane + FA_S_COL + (j & 1) * FA_BN, sv);
       tmem_ld32(t_lane + FA_S_COL + (j & 1) * FA_BN + 32, sv + 32);
       tmem_ld_wait();
+      if (lane == 0 && (warp == 0 || warp == 3)) LGB_TRF(2 + (warp == 3), j, 1);
       if (tail) {
 #pragma unroll
         for (int e = 0; e < FA_BN; ++e)
@@ -204,7 +246,9 @@ __global__ void __launch_bounds__(192, 2)
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
-      if (j > 0) fold_o(j - 1, alpha_prev);  // the P V of the previous tile ran under this tile's softmax
+      if (lane == 0 && (warp == 0 || warp == 3)) LGB_TRF(2 + (warp == 3), j, 2);
+      if (j > 0) fold_o(j - 1, alpha_prev);
+      if (lane == 0 && (warp == 0 || warp == 3)) LGB_TRF(2 + (warp == 3), j, 3);  // the P V of the previous tile ran under this tile's softmax
       l = l * alpha + lsum;
       m = m_new;
       alpha_prev = alpha;
@@ -229,6 +273,7 @@ __global__ void __launch_bounds__(192, 2)
   tc_fence_before();
   __syncthreads();
   if (warp == 5) tmem_dealloc(tmem_base, FA_TMEM_COLS);
+  LGB_TRF_LIFE(1);
 }
 
 // token-major [B, N, H, 64] bf16 -> 4-D tensor map {64, H, N, B}, box {64, 1, rows, 1}
@@ -334,30 +379,6 @@ __device__ __forceinline__ void load_row_part_to_tmem(const __nv_bfloat16* row_p
   tmem_st8(taddr, w);
 }
 static_assert(F3_NWG == 4, "the v3 backward kernels are written for 4 softmax warpgroups of 16 columns");
-
-// Optional clock64 pipeline trace of CTA (0,0,0) (-DLGB_TRACE; read back with lgb200_debug_read_trace):
-// role 0 = producer, 1 = MMA issuer, 2 = softmax warp 0, 3 = softmax warp 15; 4 time stamps per tile.
-#ifdef LGB_TRACE
-__device__ long long g_trace[4 * 64 * 4];
-#define LGB_TR(role, i, k)                                                                         \
-  do {                                                                                             \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (i) < 64) g_trace[((role) * 64 + (i)) * 4 + (k)] = clock64(); \
-  } while (0)
-// whole-CTA life time (clock64 + globaltimer at entry / exit) of CTAs 0 and 300 of the grid, in role 0 rows 40, 41
-#define LGB_TR_LIFE(k)                                                                              \
-  do {                                                                                              \
-    const int lin_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);               \
-    if (threadIdx.x == 0 && (lin_ == 0 || lin_ == 300)) {                                           \
-      unsigned long long gt_;                                                                       \
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                       \
-      g_trace[(40 + (lin_ == 300)) * 4 + (k)] = clock64();                                          \
-      g_trace[(40 + (lin_ == 300)) * 4 + (k) + 2] = (long long)gt_;                                 \
-    }                                                                                               \
-  } while (0)
-#else
-#define LGB_TR(role, i, k) do {} while (0)
-#define LGB_TR_LIFE(k) do {} while (0)
-#endif
 
 // dKV kernel: the per-QUERY softmax statistics are per-COLUMN quantities of S^T / dP^T (thread == key row), so
 // every thread would need all of them.  Instead they are folded into the contraction: the K and V rows held in

@@ -1,4 +1,5 @@
-"""Reads the -DLGB_TRACE clock64 pipeline trace of the dKV kernel (CTA 0) and prints per-tile deltas."""
+"""Reads the clock64 pipeline trace of CTA 0 of an attention kernel and prints the per-tile time stamps.
+Build with LGB200_EXTRA_NVCC_FLAGS=-DLGB_TRACE=1 (dKV backward kernel) or -DLGB_TRACE=3 (forward kernel)."""
 import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gluefactory_b200 import ops, _lib
