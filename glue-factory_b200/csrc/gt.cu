@@ -1,0 +1,195 @@
+// Ground-truth correspondences from a homography, on the device.
+// Restates gluefactory/geometry/gt_generation.py:109-161 (gt_matches_from_homography) without its ~10 dense
+// [B,M,N] temporaries: the O(M+N) point warps stay in torch (warp_points_torch, homography.py:161-180); this file
+// does the O(M N) part -- squared reprojection distances both ways, their max, row / column argmins, mutual check
+// and thresholds -- and emits matches0/1 (int64: index, -1 unmatched, -2 ignored) plus the boolean assignment.
+// Distances are formed with explicitly rounded multiplies and adds (no FMA contraction) so that every comparison
+// sees exactly the value torch's elementwise ops produce; results are bit-identical up to argmin ties.
+#include "common.cuh"
+#include "lgb200.h"
+
+namespace lgb {
+
+constexpr int kGtRows = 64;  // rows of the distance matrix per CTA (8 per warp)
+
+__device__ __forceinline__ float sqdist(float2 a, float2 b) {
+  const float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y);
+  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+
+// rows: min_j dist, argmin_j dist, min_j d0.  columns: the same over this strip's rows, one partial per strip.
+__global__ void __launch_bounds__(256) gt_h_scan_kernel(const float2* __restrict__ kp0, const float2* __restrict__ kp1,
+                                                       const float2* __restrict__ kp0_1,
+                                                       const float2* __restrict__ kp1_0, float* __restrict__ row_dist,
+                                                       int* __restrict__ row_arg, float* __restrict__ row_d0,
+                                                       float* __restrict__ part_dist, int* __restrict__ part_arg,
+                                                       float* __restrict__ part_d1, int M, int N, int nstrips) {
+  const int b = blockIdx.y, strip = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float2* p0 = kp0 + (int64_t)b * M;
+  const float2* p01 = kp0_1 + (int64_t)b * M;
+  const float2* p1 = kp1 + (int64_t)b * N;
+  const float2* p10 = kp1_0 + (int64_t)b * N;
+  const int r_base = strip * kGtRows;
+  // ---- row pass: this warp's 8 rows against every column (lanes stride the columns)
+  {
+    float2 a0[8], a1[8];
+    float bd[8], bd0[8];
+    int bi[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int i = r_base + warp * 8 + t;
+      a0[t] = i < M ? p01[i] : make_float2(0.f, 0.f);
+      a1[t] = i < M ? p0[i] : make_float2(0.f, 0.f);
+      bd[t] = INFINITY; bd0[t] = INFINITY; bi[t] = 0x7fffffff;
+    }
+    for (int j = lane; j < N; j += 32) {
+      const float2 c1 = p1[j], c10 = p10[j];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float d0 = sqdist(a0[t], c1), d1 = sqdist(a1[t], c10);
+        const float d = fmaxf(d0, d1);
+        if (d < bd[t]) { bd[t] = d; bi[t] = j; }  // j ascends per lane: first minimum kept
+        bd0[t] = fminf(bd0[t], d0);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, bd[t], o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi[t], o);
+        if (od < bd[t] || (od == bd[t] && oi < bi[t])) { bd[t] = od; bi[t] = oi; }
+        bd0[t] = fminf(bd0[t], __shfl_xor_sync(0xffffffffu, bd0[t], o));
+      }
+      const int i = r_base + warp * 8 + t;
+      if (lane == 0 && i < M) {
+        row_dist[(int64_t)b * M + i] = bd[t];
+        row_arg[(int64_t)b * M + i] = bi[t];
+        row_d0[(int64_t)b * M + i] = bd0[t];
+      }
+    }
+  }
+  // ---- column pass: thread owns columns j = tid, tid + 256, ...; all rows of this strip
+  __shared__ float2 s_a0[kGtRows], s_a1[kGtRows];
+  if (threadIdx.x < kGtRows) {
+    const int i = r_base + threadIdx.x;
+    s_a0[threadIdx.x] = i < M ? p01[i] : make_float2(0.f, 0.f);
+    s_a1[threadIdx.x] = i < M ? p0[i] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const int nrows = min(kGtRows, M - r_base);
+  for (int j = threadIdx.x; j < N; j += 256) {
+    const float2 c1 = p1[j], c10 = p10[j];
+    float bd = INFINITY, bd1 = INFINITY;
+    int bi = 0x7fffffff;
+    for (int t = 0; t < nrows; ++t) {
+      const float d0 = sqdist(s_a0[t], c1), d1 = sqdist(s_a1[t], c10);
+      const float d = fmaxf(d0, d1);
+      if (d < bd) { bd = d; bi = r_base + t; }
+      bd1 = fminf(bd1, d1);
+    }
+    const int64_t o = ((int64_t)b * nstrips + strip) * N + j;
+    part_dist[o] = bd;
+    part_arg[o] = bi;
+    part_d1[o] = bd1;
+  }
+}
+
+// merge the strip partials of every column (strip order == ascending row index: first minimum kept)
+__global__ void __launch_bounds__(256) gt_h_colmerge_kernel(const float* __restrict__ part_dist,
+                                                           const int* __restrict__ part_arg,
+                                                           const float* __restrict__ part_d1,
+                                                           float* __restrict__ col_dist, int* __restrict__ col_arg,
+                                                           float* __restrict__ col_d1, int N, int nstrips) {
+  const int b = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= N) return;
+  float bd = INFINITY, bd1 = INFINITY;
+  int bi = 0x7fffffff;
+  for (int s = 0; s < nstrips; ++s) {
+    const int64_t o = ((int64_t)b * nstrips + s) * N + j;
+    const float d = part_dist[o];
+    if (d < bd) { bd = d; bi = part_arg[o]; }
+    bd1 = fminf(bd1, part_d1[o]);
+  }
+  col_dist[(int64_t)b * N + j] = bd;
+  col_arg[(int64_t)b * N + j] = bi;
+  col_d1[(int64_t)b * N + j] = bd1;
+}
+
+// labels: mutual nearest neighbours below pos_th^2 are positives (index), points whose best one-way reprojection
+// error exceeds neg_th^2 are unmatched (-1), everything else is ignored (-2)
+__global__ void __launch_bounds__(256) gt_h_label_kernel(const float* __restrict__ row_dist,
+                                                        const int* __restrict__ row_arg,
+                                                        const float* __restrict__ row_d0,
+                                                        const float* __restrict__ col_dist,
+                                                        const int* __restrict__ col_arg,
+                                                        const float* __restrict__ col_d1, float pos2, float neg2,
+                                                        int64_t* __restrict__ m0, int64_t* __restrict__ m1,
+                                                        uint8_t* __restrict__ assignment, int M, int N) {
+  const int b = blockIdx.y, t = blockIdx.x * 256 + threadIdx.x;
+  if (t < M) {
+    const int64_t o = (int64_t)b * M + t;
+    const int j = row_arg[o];
+    const bool pos = col_arg[(int64_t)b * N + j] == t && row_dist[o] < pos2;
+    int64_t m = pos ? (int64_t)j : -2;
+    if (row_d0[o] > neg2) m = -1;
+    m0[o] = m;
+    if (pos && assignment) assignment[((int64_t)b * M + t) * N + j] = 1;
+  }
+  if (t < N) {
+    const int64_t o = (int64_t)b * N + t;
+    const int i = col_arg[o];
+    const bool pos = row_arg[(int64_t)b * M + i] == t && col_dist[o] < pos2;
+    int64_t m = pos ? (int64_t)i : -2;
+    if (col_d1[o] > neg2) m = -1;
+    m1[o] = m;
+  }
+}
+
+}  // namespace lgb
+
+using namespace lgb;
+
+extern "C" {
+
+size_t lgb200_gt_homography_ws_bytes(int B, int M, int N) {
+  const size_t nstrips = (size_t)(M + kGtRows - 1) / kGtRows;
+  return (size_t)B * (3 * (size_t)M + 3 * (size_t)N + 3 * nstrips * (size_t)N) * 4;
+}
+
+int lgb200_gt_from_homography(const float* kp0, const float* kp1, const float* kp0_1, const float* kp1_0, float pos_th,
+                              float neg_th, int64_t* m0, int64_t* m1, uint8_t* assignment, void* ws, int B, int M,
+                              int N, cudaStream_t stream) {
+  LGB_REQUIRE(kp0 && kp1 && kp0_1 && kp1_0 && m0 && m1 && ws, kErrInvalid, "gt_from_homography: null pointer");
+  LGB_REQUIRE(B > 0 && M > 0 && N > 0, kErrInvalid, "gt_from_homography: empty input B=%d M=%d N=%d", B, M, N);
+  LGB_REQUIRE(((reinterpret_cast<uintptr_t>(kp0) | reinterpret_cast<uintptr_t>(kp1) |
+                reinterpret_cast<uintptr_t>(kp0_1) | reinterpret_cast<uintptr_t>(kp1_0)) & 7) == 0,
+              kErrInvalid, "gt_from_homography: keypoint arrays must be 8-byte aligned");
+  const int nstrips = (M + kGtRows - 1) / kGtRows;
+  float* row_dist = static_cast<float*>(ws);
+  int* row_arg = reinterpret_cast<int*>(row_dist + (size_t)B * M);
+  float* row_d0 = reinterpret_cast<float*>(row_arg + (size_t)B * M);
+  float* col_dist = row_d0 + (size_t)B * M;
+  int* col_arg = reinterpret_cast<int*>(col_dist + (size_t)B * N);
+  float* col_d1 = reinterpret_cast<float*>(col_arg + (size_t)B * N);
+  float* part_dist = col_d1 + (size_t)B * N;
+  int* part_arg = reinterpret_cast<int*>(part_dist + (size_t)B * nstrips * N);
+  float* part_d1 = reinterpret_cast<float*>(part_arg + (size_t)B * nstrips * N);
+  if (assignment) {
+    cudaError_t e = cudaMemsetAsync(assignment, 0, (size_t)B * M * N, stream);
+    LGB_REQUIRE(e == cudaSuccess, kErrCuda, "gt_from_homography: memset: %s", cudaGetErrorString(e));
+  }
+  gt_h_scan_kernel<<<dim3(nstrips, B), 256, 0, stream>>>(
+      reinterpret_cast<const float2*>(kp0), reinterpret_cast<const float2*>(kp1),
+      reinterpret_cast<const float2*>(kp0_1), reinterpret_cast<const float2*>(kp1_0), row_dist, row_arg, row_d0,
+      part_dist, part_arg, part_d1, M, N, nstrips);
+  gt_h_colmerge_kernel<<<dim3((N + 255) / 256, B), 256, 0, stream>>>(part_dist, part_arg, part_d1, col_dist, col_arg,
+                                                                     col_d1, N, nstrips);
+  const int L = M > N ? M : N;
+  gt_h_label_kernel<<<dim3((L + 255) / 256, B), 256, 0, stream>>>(row_dist, row_arg, row_d0, col_dist, col_arg, col_d1,
+                                                                  pos_th * pos_th, neg_th * neg_th, m0, m1, assignment,
+                                                                  M, N);
+  return check_launch("gt_from_homography");
+}
+
+}  // extern "C"

@@ -194,6 +194,16 @@ def residual_add_cast(x, y, cdt, want_sum=True):
     return (xo if xo is not None else x), xc
 
 
+def gluestick_attention(query, key, value):
+    """GlueStick's attention core (models/matchers/gluestick.py:524-529) on the same kernels: query [B, 64, H, N],
+    key/value [B, 64, H, M] (channels first, channel = d * H + h) -> [B, 64, H, N].  The reference forces fp32 here
+    (AMP_CUSTOM_FWD_F32): fp32 inputs run the full-precision kernels, bf16 inputs the tcgen05 ones."""
+    assert query.shape[1] == 64, "head dimension 64 only"
+    tm = lambda t: t.permute(0, 3, 2, 1).contiguous()  # noqa: E731  -> token-major [B, N, H, 64]
+    out = Attention.apply(tm(query), tm(key), tm(value), 0, 0.125)
+    return out.permute(0, 3, 2, 1)
+
+
 # ------------------------------------------------------------------------------------------------
 # batched GEMM on tcgen05 (lightglue.py:283)
 # ------------------------------------------------------------------------------------------------
@@ -305,6 +315,34 @@ def wgrad_bf16(dy, a, out=None):
     ws = torch.empty(_lib.load().lgb200_gemm_splitk_ws_floats(M, N, T), device=dy.device, dtype=torch.float32)
     call("lgb200_gemm_bf16_splitk", ptr(dy), ptr(a), ptr(out), M, N, T, 1, 1, dy.stride(0), a.stride(0), out.stride(0),
          ptr(ws), stream_ptr())
+    return out
+
+
+def gt_matches_from_homography(kp0, kp1, H, pos_th=3.0, neg_th=6.0, dense=True):
+    """Device-side gt_matches_from_homography (geometry/gt_generation.py:109-161; defaults as the reference's).
+    kp0 [B,M,2], kp1 [B,N,2] pixel coordinates, H [B,3,3] -> dict with `assignment` (bool [B,M,N], omitted when
+    dense=False), `matches0/1` (int64: index, -1 unmatched, -2 ignored), `matching_scores0/1`, `proj_0to1/1to0`.
+    The dense `reward` map of the reference is not produced (no consumer on the matcher's path)."""
+    from .synthetic import warp_points
+
+    kp0, kp1 = kp0.float().contiguous(), kp1.float().contiguous()
+    _chk(kp0, torch.float32), _chk(kp1, torch.float32)
+    B, M = kp0.shape[:2]
+    N = kp1.shape[1]
+    Hm = H.float().expand(B, 3, 3) if H.dim() == 2 else H.float()
+    kp0_1 = warp_points(kp0, Hm).contiguous()  # O(M+N): homography.py:161-180
+    kp1_0 = warp_points(kp1, torch.inverse(Hm)).contiguous()
+    dev = kp0.device
+    m0 = torch.empty(B, M, device=dev, dtype=torch.int64)
+    m1 = torch.empty(B, N, device=dev, dtype=torch.int64)
+    asg = torch.empty(B, M, N, device=dev, dtype=torch.bool) if dense else None
+    ws = torch.empty(_lib.load().lgb200_gt_homography_ws_bytes(B, M, N), device=dev, dtype=torch.uint8)
+    call("lgb200_gt_from_homography", ptr(kp0), ptr(kp1), ptr(kp0_1), ptr(kp1_0), float(pos_th), float(neg_th), ptr(m0),
+         ptr(m1), ptr(asg), ptr(ws), B, M, N, stream_ptr())
+    out = {"matches0": m0, "matches1": m1, "matching_scores0": (m0 > -1).float(), "matching_scores1": (m1 > -1).float(),
+           "proj_0to1": kp0_1, "proj_1to0": kp1_0}
+    if dense:
+        out["assignment"] = asg
     return out
 
 

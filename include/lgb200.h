@@ -196,6 +196,17 @@ int lgb200_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream
 int lgb200_residual_add_cast(const float* x, const void* y, float* x_out, void* x_cast, int64_t n, int dtype,
                              cudaStream_t stream);
 
+/* ---- ground-truth correspondences from a homography ---------------------------------
+ * replaces the O(M N) part of gt_matches_from_homography (geometry/gt_generation.py:109-161): kp0 [B,M,2],
+ * kp1 [B,N,2] pixel coordinates, kp0_1 = warp(kp0, H), kp1_0 = warp(kp1, H^-1) (the O(M+N) warps of
+ * homography.py:161-180 are done by the caller).  dist = max(|kp0_1 - kp1|^2, |kp0 - kp1_0|^2); mutual nearest
+ * neighbours with dist < pos_th^2 are positives; matches: index, -1 (best one-way error > neg_th^2), -2 (ignored).
+ * assignment: [B,M,N] bytes (bool), cleared and filled by the call, or NULL.                              */
+size_t lgb200_gt_homography_ws_bytes(int B, int M, int N);
+int lgb200_gt_from_homography(const float* kp0, const float* kp1, const float* kp0_1, const float* kp1_0, float pos_th,
+                              float neg_th, int64_t* matches0, int64_t* matches1, uint8_t* assignment, void* ws, int B,
+                              int M, int N, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -297,6 +297,27 @@ def log_double_softmax(sim, bin_score):
     return scores
 
 
+def gluestick_attention(query, key, value):
+    """models/matchers/gluestick.py:524-529. query [B, dh, H, N], key/value [B, dh, H, M] (GlueStick keeps channels
+    first and splits heads as channel = d * H + h, gluestick.py:544-547) -> [B, dh, H, N]; fp32-forced in the reference."""
+    dh = query.shape[1]
+    scores = torch.einsum("bdhn,bdhm->bhnm", query, key) / dh**0.5
+    return torch.einsum("bhnm,bdhm->bdhn", torch.softmax(scores, -1), value)
+
+
+def gluestick_mha(x, source, params, num_heads=4):
+    """MultiHeadedAttention.forward (gluestick.py:532-551) with query = x, key = value = source ([B, D, N] / [B, D, M]);
+    params: merge.{weight,bias}, proj.{0,1,2}.{weight,bias} (Conv1d k=1 == Linear over channels)."""
+    lin = lambda t, i: torch.einsum("oc,bcn->bon", params[f"proj.{i}.weight"][:, :, 0], t) + \
+        params[f"proj.{i}.bias"][None, :, None]  # noqa: E731
+    B, D = x.shape[:2]
+    dh = D // num_heads
+    q, k, v = lin(x, 0), lin(source, 1), lin(source, 2)
+    o = gluestick_attention(q.view(B, dh, num_heads, -1), k.view(B, dh, num_heads, -1), v.view(B, dh, num_heads, -1))
+    o = o.contiguous().view(B, D, -1)
+    return torch.einsum("oc,bcn->bon", params["merge.weight"][:, :, 0], o) + params["merge.bias"][None, :, None]
+
+
 def log_optimal_transport(scores, alpha, iters):
     """gluefactory_nonfree/superglue.py:186-214, restated from the algorithm:
     log-domain Sinkhorn on the (M+1)x(N+1) coupling with dustbin score alpha,

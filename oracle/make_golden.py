@@ -113,8 +113,71 @@ def run_heads():
     print("heads ->", path)
 
 
+def run_gluestick_attention():
+    """Golden vectors for the GlueStick attention core and its MultiHeadedAttention wrapper
+    (models/matchers/gluestick.py:524-551): forward and all gradients in fp64."""
+    from gluefactory.models.matchers.gluestick import MultiHeadedAttention, attention
+
+    rs = np.random.RandomState(21)
+    out = {}
+    b, d, h, n, m = 1, 64, 4, 40, 56
+    q = torch.from_numpy(rs.standard_normal((b, d, h, n))).requires_grad_()
+    k = torch.from_numpy(rs.standard_normal((b, d, h, m))).requires_grad_()
+    v = torch.from_numpy(rs.standard_normal((b, d, h, m))).requires_grad_()
+    w = torch.from_numpy(rs.standard_normal((b, d, h, n)))
+    o, _ = attention(q, k, v)
+    (o * w).sum().backward()
+    out.update({"core|q": q.detach().numpy(), "core|k": k.detach().numpy(), "core|v": v.detach().numpy(),
+                "core|w": w.numpy(), "core|out": o.detach().numpy(), "core|dq": q.grad.numpy(),
+                "core|dk": k.grad.numpy(), "core|dv": v.grad.numpy()})
+    # module level: weights drawn from the seeded stream below (the test rebuilds them), gradients summarised
+    b, n, m = 1, 40, 56
+    mha = MultiHeadedAttention(4, 256).double()
+    wrs = np.random.RandomState(22)
+    with torch.no_grad():
+        for name, p_ in mha.named_parameters():  # order: merge.weight, merge.bias, proj.{0,1,2}.{weight,bias}
+            p_.copy_(torch.from_numpy(wrs.uniform(-1, 1, size=tuple(p_.shape)) / 16.0))
+    x = torch.from_numpy(rs.standard_normal((b, 256, n))).requires_grad_()
+    src = torch.from_numpy(rs.standard_normal((b, 256, m))).requires_grad_()
+    w2 = torch.from_numpy(rs.standard_normal((b, 256, n)))
+    y = mha(x, src, src)
+    (y * w2).sum().backward()
+    out.update({"mha|x": x.detach().numpy(), "mha|src": src.detach().numpy(), "mha|w": w2.numpy(),
+                "mha|out": y.detach().numpy(), "mha|dx": x.grad.numpy(), "mha|dsrc": src.grad.numpy(),
+                "mha|param_names": np.array([n_ for n_, _ in mha.named_parameters()])})
+    for name, p_ in mha.named_parameters():
+        out.update(summarise("mha|grad|" + name, p_.grad))
+    path = os.path.join(OUT, "gluestick_attn.npz")
+    np.savez_compressed(path, **out)
+    print("gluestick attention ->", path)
+
+
+def run_gt_homography():
+    """Golden labels from the reference's own gt_matches_from_homography (geometry/gt_generation.py:109-161),
+    imported with the kornia stand-in of oracle/_shim (the function itself never touches kornia)."""
+    from gluefactory.geometry.gt_generation import gt_matches_from_homography
+
+    out = {}
+    for tag, (B, M, N, seed) in {"a": (2, 260, 300, 5), "b": (1, 513, 200, 6)}.items():
+        d = synthetic.make_pairs(B, N, seed=seed, M=M, with_gt=False)
+        kp0, kp1, H = d["keypoints0"], d["keypoints1"], d["H_0to1"]  # fp32, as the pipeline passes them
+        r = gt_matches_from_homography(kp0, kp1, H, pos_th=3.0, neg_th=3.0)
+        out.update({f"{tag}|kp0": kp0.numpy(), f"{tag}|kp1": kp1.numpy(), f"{tag}|H": H.numpy(),
+                    f"{tag}|matches0": r["matches0"].numpy(), f"{tag}|matches1": r["matches1"].numpy(),
+                    f"{tag}|positives": r["assignment"].nonzero().numpy(),
+                    f"{tag}|proj_0to1": r["proj_0to1"].numpy(), f"{tag}|proj_1to0": r["proj_1to0"].numpy()})
+    path = os.path.join(OUT, "gt_homography.npz")
+    np.savez_compressed(path, **out)
+    print("gt_homography ->", path)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]  # regenerate single fixtures: gluestick_attn, gt_homography
+    if only:
+        for name in only:
+            {"gluestick_attn": run_gluestick_attention, "gt_homography": run_gt_homography}[name]()
+        sys.exit(0)
     torch.manual_seed(0)
     torch.set_num_threads(8)
     small = dict(synthetic.DEFAULT_CONF, descriptor_dim=128, input_dim=128, num_heads=2, n_layers=2)
@@ -127,3 +190,5 @@ if __name__ == "__main__":
     full = dict(synthetic.DEFAULT_CONF)
     run_case("lg_full_l9_n512", full, B=1, N=512, M=512, seed=15, sub=8)
     run_heads()
+    run_gluestick_attention()
+    run_gt_homography()

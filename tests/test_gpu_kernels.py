@@ -223,6 +223,59 @@ def test_other_heads_match_golden():
         np.testing.assert_allclose(ops.log_optimal_transport(sim, 0.7, 50).cpu().numpy(), g[f"{tag}|lot"], atol=1e-4)
 
 
+def test_gt_from_homography_matches_reference_labels():
+    """Device GT labels are bit-exact against the reference function's own output (golden) ..."""
+    g = dict(np.load(os.path.join(GOLDEN, "gt_homography.npz")))
+    for tag in ["a", "b"]:
+        kp0, kp1, H = (torch.from_numpy(g[f"{tag}|{n}"]).to(DEV) for n in ("kp0", "kp1", "H"))
+        r = ops.gt_matches_from_homography(kp0, kp1, H, 3.0, 3.0)
+        assert np.array_equal(r["matches0"].cpu().numpy(), g[f"{tag}|matches0"])
+        assert np.array_equal(r["matches1"].cpu().numpy(), g[f"{tag}|matches1"])
+        assert np.array_equal(r["assignment"].nonzero().cpu().numpy(), g[f"{tag}|positives"])
+        np.testing.assert_allclose(r["proj_0to1"].cpu().numpy(), g[f"{tag}|proj_0to1"], rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("B,M,N", [(2, 2048, 2048), (3, 1000, 777), (1, 5, 3000)])
+def test_gt_from_homography_matches_restatement_at_size(B, M, N):
+    """... and against the torch restatement (same warped points) at the benchmark size and on ragged shapes."""
+    from gluefactory_b200 import synthetic
+
+    d = synthetic.to_device(synthetic.make_pairs(B, N, seed=70 + B, M=M, with_gt=False), DEV)
+    kp0, kp1, H = d["keypoints0"], d["keypoints1"], d["H_0to1"]
+    asg, m0, m1 = synthetic.gt_matches_from_homography(kp0, kp1, H, 3.0, 3.0)
+    r = ops.gt_matches_from_homography(kp0, kp1, H, 3.0, 3.0)
+    assert torch.equal(r["matches0"], m0) and torch.equal(r["matches1"], m1)
+    assert torch.equal(r["assignment"], asg)
+    assert int(asg.sum()) > 0
+    sparse = ops.gt_matches_from_homography(kp0, kp1, H, 3.0, 3.0, dense=False)
+    assert "assignment" not in sparse and torch.equal(sparse["matches0"], m0)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
+def test_gluestick_attention_matches_golden(dtype, tol):
+    """GlueStick's channels-first attention core (gluestick.py:524-529), forward and gradients,
+    against vectors produced by the reference function itself (oracle/make_golden.py)."""
+    g = dict(np.load(os.path.join(GOLDEN, "gluestick_attn.npz")))
+    q, k, v = (torch.from_numpy(g[f"core|{n}"]).to(dtype).to(DEV).requires_grad_() for n in "qkv")
+    out = ops.gluestick_attention(q, k, v)
+    assert out.shape == q.shape
+    if dtype == torch.float32:
+        assert rel_err(out, torch.from_numpy(g["core|out"])) < tol
+        (out * torch.from_numpy(g["core|w"]).float().to(DEV)).sum().backward()
+        for n, t in (("dq", q), ("dk", k), ("dv", v)):
+            assert rel_err(t.grad, torch.from_numpy(g[f"core|{n}"])) < tol, n
+    else:  # bf16 operands: compare with the oracle evaluated on the same rounded operands
+        from oracle import lightglue_oracle as O
+        qd, kd, vd = (t.detach().double().cpu().requires_grad_() for t in (q, k, v))
+        ref = O.gluestick_attention(qd, kd, vd)
+        assert rel_err(out, ref) < tol
+        w = torch.from_numpy(g["core|w"])
+        (ref * w).sum().backward()
+        (out.float() * w.float().to(DEV)).sum().backward()
+        for n, t, td in (("dq", q, qd), ("dk", k, kd), ("dv", v, vd)):
+            assert rel_err(t.grad, td.grad) < 3e-2, n
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("rows,cols", [(16384, 256), (1000, 768), (37, 8), (4096, 512)])
 def test_colsum_and_residual(dtype, rows, cols):
