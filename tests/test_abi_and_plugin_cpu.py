@@ -90,5 +90,16 @@ def _dropin_checks():
     from gluefactory.models.two_view_pipeline import TwoViewPipeline
 
     pipe = TwoViewPipeline({"matcher": {"name": "gluefactory_b200.matchers.lightglue", "n_layers": 1},
+                            "ground_truth": {"name": "gluefactory_b200.matchers.homography_matcher", "th_positive": 2.0},
                             "extractor": {"name": None}, "allow_no_extract": True})
     assert isinstance(pipe.matcher, cls)
+    # the ground-truth component is discovered the same way (two_view_pipeline.py:54-56) and mirrors the reference's
+    gt_cls, ref_gt = get_model("gluefactory_b200.matchers.homography_matcher"), get_model("matchers.homography_matcher")
+    assert isinstance(pipe.ground_truth, gt_cls) and pipe.ground_truth.conf.th_positive == 2.0
+    assert sorted(gt_cls({}).required_data_keys) == sorted(ref_gt({}).required_data_keys)
+    for k, v in ref_gt.default_conf.items():
+        assert gt_cls.default_conf[k] == v, k
+    with pytest.raises(NotImplementedError):
+        gt_cls({}).loss({}, {})
+    with pytest.raises(Exception):  # no CUDA device here: the op refuses instead of falling back to the CPU
+        gt_cls({})({"H_0to1": torch.eye(3)[None], "keypoints0": torch.zeros(1, 4, 2), "keypoints1": torch.zeros(1, 4, 2)})

@@ -233,6 +233,11 @@ def test_gt_from_homography_matches_reference_labels():
         assert np.array_equal(r["matches1"].cpu().numpy(), g[f"{tag}|matches1"])
         assert np.array_equal(r["assignment"].nonzero().cpu().numpy(), g[f"{tag}|positives"])
         np.testing.assert_allclose(r["proj_0to1"].cpu().numpy(), g[f"{tag}|proj_0to1"], rtol=1e-5, atol=1e-3)
+        # the drop-in ground_truth component (mirror of matchers/homography_matcher.py) returns the same labels
+        from gluefactory_b200.matchers.homography_matcher import HomographyMatcher
+        pred = HomographyMatcher({"th_positive": 3.0, "th_negative": 3.0})({"keypoints0": kp0, "keypoints1": kp1, "H_0to1": H})
+        assert np.array_equal(pred["matches0"].cpu().numpy(), g[f"{tag}|matches0"])
+        assert pred["assignment"].dtype == torch.bool and set(pred) >= {"matches1", "matching_scores0", "proj_1to0"}
 
 
 @pytest.mark.parametrize("B,M,N", [(2, 2048, 2048), (3, 1000, 777), (1, 5, 3000)])
