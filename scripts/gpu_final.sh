@@ -9,3 +9,6 @@ timeout 200 python scripts/prof_step.py > gpurun_out/prof_step.log 2>&1; grep "t
 if [ "$1" = "ncu" ]; then
   timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 1300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --batch 8 --no-graph > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?" | tee -a gpurun_out/summary.txt
 fi
+if [ "$1" = "attn" ] || [ "$2" = "attn" ]; then
+  timeout 300 ncu --set full --clock-control none -k regex:attn_ -c 4 -o gpurun_out/attn_end python scripts/prof_attn.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn rc=$?" | tee -a gpurun_out/summary.txt
+fi
