@@ -53,6 +53,7 @@ SIGNATURES = {
     "lgb200_colsum_slabs": (_i, [_i64, _i]),
     "lgb200_colsum": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "lgb200_residual_add_cast": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "lgb200_residual_add_cast_pitched": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _vp]),
 }
 
 

@@ -484,9 +484,12 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ a, fl
 // x_out = x + y (fp32 residual stream) and its compute-dtype copy for the next GEMM, in one pass
 template <typename T>
 __global__ void __launch_bounds__(256) residual_add_cast_kernel(const float* __restrict__ x, const T* __restrict__ y,
-                                                               float* __restrict__ xo, T* __restrict__ xc, int64_t n) {
+                                                               float* __restrict__ xo, T* __restrict__ xc, int64_t n,
+                                                               int64_t cols, int64_t cast_pitch) {
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i0 >= n) return;
+  // the cast copy may be a column block of a wider matrix (row pitch cast_pitch > cols; cols % 8 == 0 then)
+  if (xc && cast_pitch != cols) xc += (i0 / cols) * cast_pitch + (i0 % cols) - i0;
   if (i0 + 8 <= n) {
     Vec8<float> a = Vec8<float>::load(x + i0);
     if (y) {
@@ -680,18 +683,30 @@ int lgb200_colsum(const void* a, float* out, float* ws, unsigned* counters, int6
   return check_launch("colsum");
 }
 
-int lgb200_residual_add_cast(const float* x, const void* y, float* x_out, void* x_cast, int64_t n, int dtype,
-                             cudaStream_t stream) {
-  LGB_REQUIRE(x && (x_out || x_cast) && n > 0, kErrInvalid, "residual_add_cast: bad arguments");
+int lgb200_residual_add_cast_pitched(const float* x, const void* y, float* x_out, void* x_cast, int64_t rows,
+                                     int64_t cols, int64_t cast_pitch, int dtype, cudaStream_t stream) {
+  LGB_REQUIRE(x && (x_out || x_cast) && rows > 0 && cols > 0, kErrInvalid, "residual_add_cast: bad arguments");
+  LGB_REQUIRE(cast_pitch >= cols, kErrInvalid, "residual_add_cast: cast pitch %lld < cols %lld", (long long)cast_pitch,
+              (long long)cols);
+  LGB_REQUIRE(cast_pitch == cols || (cols % 8 == 0 && cast_pitch % 8 == 0), kErrInvalid,
+              "residual_add_cast: a pitched cast output needs cols and pitch to be multiples of 8");
+  const int64_t n = rows * cols;
   const unsigned grid = (unsigned)(((n + 7) / 8 + 255) / 256);
   if (dtype == LGB200_F32)
-    residual_add_cast_kernel<float><<<grid, 256, 0, stream>>>(x, (const float*)y, x_out, (float*)x_cast, n);
+    residual_add_cast_kernel<float><<<grid, 256, 0, stream>>>(x, (const float*)y, x_out, (float*)x_cast, n, cols,
+                                                              cast_pitch);
   else if (dtype == LGB200_BF16)
     residual_add_cast_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, (const __nv_bfloat16*)y, x_out,
-                                                                      (__nv_bfloat16*)x_cast, n);
+                                                                      (__nv_bfloat16*)x_cast, n, cols, cast_pitch);
   else
     LGB_REQUIRE(false, kErrInvalid, "residual_add_cast: bad dtype %d", dtype);
   return check_launch("residual_add_cast");
+}
+
+int lgb200_residual_add_cast(const float* x, const void* y, float* x_out, void* x_cast, int64_t n, int dtype,
+                             cudaStream_t stream) {
+  LGB_REQUIRE(n > 0, kErrInvalid, "residual_add_cast: bad arguments");
+  return lgb200_residual_add_cast_pitched(x, y, x_out, x_cast, 1, n, n, dtype, stream);
 }
 
 int lgb200_rope_split_fwd(const void* qkv, const float* theta, void* q, void* k, void* v, int64_t ntok, int H,

@@ -123,30 +123,36 @@ class LayerFn(torch.autograd.Function):
          Wqk, bqk, Wv, bv, Wout, bout, W0c, b0c, g2, be2, W3c, b3c) = w
         D = x.shape[1]
         x = x.contiguous()
+        # The FFN input cat([x, msg], -1) (lightglue.py:162, 219) is never concatenated: the compute-dtype copy of x
+        # and the out-projection's result are written straight into the two halves of one [T, 2D] buffer, which
+        # then feeds ffn.0 as ONE K=2D GEMM (and, in backward, one [2D x 2D] weight-gradient GEMM).
+        T = x.shape[0]
         # ---- self block (lightglue.py:150-163)
-        _, x16 = ops.residual_add_cast(x, None, cdt)
+        cat1 = torch.empty(T, 2 * D, device=x.device, dtype=cdt)
+        x16, msg = cat1[:, :D], cat1[:, D:]
+        ops.residual_add_cast(x, None, cdt, out_cast=x16)
         qkv = torch.addmm(bqkv, x16, Wqkv.t())
         q, k, v = ops.rope_fwd(qkv, theta, H)
         del qkv
         att, lse1 = _attend_fwd(q, k, v, sizes, H, cross=False)
-        msg = torch.addmm(bo, att, Wo.t())
-        h = torch.addmm(b0, x16, W0[:, :D].t())
-        h.addmm_(msg, W0[:, D:].t())
+        torch.addmm(bo, att, Wo.t(), out=msg)
+        h = torch.addmm(b0, cat1, W0.t())
         g, mean1, rstd1 = ops.ln_gelu_fwd(h, g1, be1, eps)
         y = torch.addmm(b3, g, W3.t())
-        x1, x1_16 = ops.residual_add_cast(x, y, cdt)
+        cat2 = torch.empty(T, 2 * D, device=x.device, dtype=cdt)
+        x1_16, msg2 = cat2[:, :D], cat2[:, D:]
+        x1, _ = ops.residual_add_cast(x, y, cdt, out_cast=x1_16)
         del y
         # ---- cross block (lightglue.py:195-221)
         qk = torch.addmm(bqk, x1_16, Wqk.t())
         vv = torch.addmm(bv, x1_16, Wv.t())
         m, lse2 = _attend_fwd(qk, qk, vv, sizes, H, cross=True)
-        msg2 = torch.addmm(bout, m, Wout.t())
-        h2 = torch.addmm(b0c, x1_16, W0c[:, :D].t())
-        h2.addmm_(msg2, W0c[:, D:].t())
+        torch.addmm(bout, m, Wout.t(), out=msg2)
+        h2 = torch.addmm(b0c, cat2, W0c.t())
         gg, mean2, rstd2 = ops.ln_gelu_fwd(h2, g2, be2, eps)
         y2 = torch.addmm(b3c, gg, W3c.t())
         x2, _ = ops.residual_add_cast(x1, y2, None)
-        ctx.save_for_backward(theta, x16, q, k, v, att, msg, h, mean1, rstd1, g, x1_16, qk, vv, m, msg2, h2, mean2,
+        ctx.save_for_backward(theta, cat1, q, k, v, att, h, mean1, rstd1, g, cat2, qk, vv, m, h2, mean2,
                               rstd2, gg, *lse1, *lse2, *w)
         ctx.meta = (sizes, H, cdt, len(lse1), len(lse2), D)
         return x2
@@ -155,10 +161,11 @@ class LayerFn(torch.autograd.Function):
     def backward(ctx, dx):
         sizes, H, cdt, n1, n2, D = ctx.meta
         sv = ctx.saved_tensors
-        (theta, x16, q, k, v, att, msg, h, mean1, rstd1, g, x1_16, qk, vv, m, msg2, h2, mean2, rstd2, gg) = sv[:20]
-        lse1, lse2 = sv[20:20 + n1], sv[20 + n1:20 + n1 + n2]
+        (theta, cat1, q, k, v, att, h, mean1, rstd1, g, cat2, qk, vv, m, h2, mean2, rstd2, gg) = sv[:18]
+        x16, x1_16 = cat1[:, :D], cat2[:, :D]
+        lse1, lse2 = sv[18:18 + n1], sv[18 + n1:18 + n1 + n2]
         (Wqkv, bqkv, Wo, bo, W0, b0, g1, be1, W3, b3,
-         Wqk, bqk, Wv, bv, Wout, bout, W0c, b0c, g2, be2, W3c, b3c) = sv[20 + n1 + n2:]
+         Wqk, bqk, Wv, bv, Wout, bout, W0c, b0c, g2, be2, W3c, b3c) = sv[18 + n1 + n2:]
         dx = dx.contiguous()
         # ---- cross block
         dy2 = dx.to(cdt)
@@ -166,7 +173,7 @@ class LayerFn(torch.autograd.Function):
         dgg = torch.mm(dy2, W3c)
         dh2, dg2, dbe2, db0c = ops.ln_gelu_bwd(dgg, h2, g2, be2, mean2, rstd2, want_dxsum=True)
         del dgg
-        dW0c = torch.cat([_wgrad(dh2, x1_16), _wgrad(dh2, msg2)], 1)
+        dW0c = _wgrad(dh2, cat2)
         dmsg2 = torch.mm(dh2, W0c[:, D:])
         dx1 = _dgrad_acc(dx, dh2, W0c[:, :D])  # fp32 accumulation of the residual-stream gradient
         del dh2
@@ -184,7 +191,7 @@ class LayerFn(torch.autograd.Function):
         dg = torch.mm(dy, W3)
         dh, dg1, dbe1, db0 = ops.ln_gelu_bwd(dg, h, g1, be1, mean1, rstd1, want_dxsum=True)
         del dg
-        dW0 = torch.cat([_wgrad(dh, x16), _wgrad(dh, msg)], 1)
+        dW0 = _wgrad(dh, cat1)
         dmsg = torch.mm(dh, W0[:, D:])
         dx0 = _dgrad_acc(dx1, dh, W0[:, :D])
         del dh

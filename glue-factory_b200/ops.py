@@ -183,11 +183,19 @@ def colsum(a):
     return out
 
 
-def residual_add_cast(x, y, cdt, want_sum=True):
+def residual_add_cast(x, y, cdt, want_sum=True, out_cast=None):
     """x fp32 [.., D] + y (compute dtype or None) -> (x_new fp32 or None, cast(x_new) in cdt).
-    cdt None: only the fp32 sum is produced (y gives the kernel's element type)."""
+    cdt None: only the fp32 sum is produced (y gives the kernel's element type).
+    out_cast: optional destination for the cast copy, a [rows, D] column block (unit inner stride) of a wider matrix."""
     _chk(x, torch.float32)
     xo = torch.empty_like(x) if (want_sum and y is not None) else None
+    if out_cast is not None:
+        _chk(out_cast, cdt, strided_rows=True)
+        rows, cols = out_cast.shape
+        assert x.numel() == rows * cols
+        call("lgb200_residual_add_cast_pitched", ptr(x), ptr(y), ptr(xo), ptr(out_cast), rows, cols, out_cast.stride(0),
+             _code(cdt), stream_ptr())
+        return (xo if xo is not None else x), out_cast
     xc = torch.empty(x.shape, device=x.device, dtype=cdt) if cdt is not None else None
     call("lgb200_residual_add_cast", ptr(x), ptr(y), ptr(xo), ptr(xc), x.numel(),
          _code(cdt if cdt is not None else y.dtype), stream_ptr())

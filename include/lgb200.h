@@ -195,6 +195,10 @@ int lgb200_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream
  * x_out = x + y (y in `dtype`, may be NULL), x_cast = (dtype) x_out; either output may be NULL.   */
 int lgb200_residual_add_cast(const float* x, const void* y, float* x_out, void* x_cast, int64_t n, int dtype,
                              cudaStream_t stream);
+/* same over [rows, cols] with the cast copy written at row pitch cast_pitch >= cols (elements): the copy lands
+ * directly in the left / right half of the [x | msg] operand of ffn.0 (lightglue.py:162, 219), no torch.cat.   */
+int lgb200_residual_add_cast_pitched(const float* x, const void* y, float* x_out, void* x_cast, int64_t rows,
+                                     int64_t cols, int64_t cast_pitch, int dtype, cudaStream_t stream);
 
 /* ---- ground-truth correspondences from a homography ---------------------------------
  * replaces the O(M N) part of gt_matches_from_homography (geometry/gt_generation.py:109-161): kp0 [B,M,2],
