@@ -47,7 +47,7 @@ constexpr int FA_S_COL = 0, FA_O_COL = 128;
 // softmax warps never wait for Q K^T; P and the per-tile O = P V are double-buffered as well, so the P V of
 // tile j runs while the softmax of tile j+1 is being computed and is folded into the register accumulator
 // one iteration later.
-// Optional clock64 pipeline trace of CTA (0,0,0) (read back with lgb200_debug_read_trace / scripts/trace_dkv.py):
+// Optional clock64 pipeline trace of CTA (0,0,0) (read back with lgb200_debug_read_trace / scripts/trace_attn.py):
 // -DLGB_TRACE=1 traces the dKV kernel, -DLGB_TRACE=3 the forward kernel.
 // role 0 = producer, 1 = MMA issuer, 2 / 3 = two softmax warps; 4 time stamps per tile.
 #ifdef LGB_TRACE
