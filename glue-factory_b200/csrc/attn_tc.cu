@@ -277,6 +277,217 @@ __global__ void __launch_bounds__(192, 2)
 }
 
 // token-major [B, N, H, 64] bf16 -> 4-D tensor map {64, H, N, B}, box {64, 1, rows, 1}
+// ---------------------------------------------------------------------------------------------
+// FORWARD, variant 3 (NOT the default yet: select with LGB200_ATTN_FWD_V3=1; written at the end of round 1 from
+// the pipeline trace in profiles/r01_attention_pipeline_notes.md, to be validated on the first GPU call of round 2).
+// Differences from attn_fwd_tc_kernel:
+//   * P never goes through shared memory: the softmax warps write it (bf16, two keys per 32-bit column) over the
+//     first 32 columns of the S tile it was computed from, and P V is a TS-form MMA (A operand in TMEM) exactly like
+//     the accumulating MMAs of the backward kernels -- no st.shared, no fence.proxy.async, 32 KiB less smem;
+//   * O accumulates in TMEM across key tiles (accumulate flag) instead of being folded into 64 registers per thread
+//     every tile; a softmax warp rescales its O rows in TMEM only when one of its 32 rows outgrew the reference
+//     maximum by more than 2^8 (lazy rescaling: exponentials relative to a stale maximum, bounded by 256).
+// Per tile and thread this removes 64 FFMA + a 64-column tcgen05.ld + 8 st.shared + one barrier round trip.
+// ---------------------------------------------------------------------------------------------
+constexpr int FV_SMEM = FA_QBYTES + FA_STAGES * 2 * FA_KBYTES + 256;
+constexpr int FV_S_COL = 0, FV_O_COL = 128;  // TMEM: S0 [0,64) S1 [64,128) (P over their first 32 columns), O [128,192)
+
+__global__ void __launch_bounds__(192, 2)
+    attn_fwd_tc_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out,
+                          float* __restrict__ lse, int B, int Nq, int Nk, int H, int kv_shift, float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + FA_QBYTES;
+  uint8_t* sV = sK + FA_STAGES * FA_KBYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FA_STAGES * FA_KBYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;               // [FA_STAGES]
+  uint64_t* kv_empty = kv_full + FA_STAGES;   // [FA_STAGES]
+  uint64_t* s_full = kv_empty + FA_STAGES;    // [2]
+  uint64_t* p_full = s_full + 2;              // [2]
+  uint64_t* o_done = p_full + 2;              // one barrier, one phase per key tile (P V of tile j complete)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
+  const int kb = (b + kv_shift) % B;
+  const int ntiles = (Nk + FA_BN - 1) / FA_BN;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(q_full, 1);
+    for (int s = 0; s < FA_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 4);
+    }
+    mbar_init(o_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, FA_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, FA_QBYTES);
+      tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % FA_STAGES;
+        mbar_wait(&kv_empty[s], ((j / FA_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * FA_KBYTES);
+        tma_load_4d(sK + s * FA_KBYTES, &tmK, &kv_full[s], 0, h, j * FA_BN, kb);
+        tma_load_4d(sV + s * FA_KBYTES, &tmV, &kv_full[s], 0, h, j * FA_BN, kb);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer (warp-convergent, elected lane)
+    constexpr uint32_t idesc_s = make_idesc_bf16(FA_BM, FA_BN, 0, 0);  // Q (K-major) x K_j (K-major)
+    constexpr uint32_t idesc_o = make_idesc_bf16(FA_BM, FA_D, 0, 1);   // P (TMEM) x V_j (MN-major)
+    const uint64_t dQ0 = make_smem_desc(smem_u32(sQ), 16, 1024), dK0 = make_smem_desc(smem_u32(sK), 16, 1024);
+    const uint64_t dV0 = make_smem_desc(smem_u32(sV), 8192, 1024);
+    const bool leader = elect_one();
+    auto issue_s = [&](int j) {
+      const int s = j % FA_STAGES;
+      mbar_wait(&kv_full[s], (j / FA_STAGES) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint64_t dk = dK0 + (uint64_t)((s * FA_KBYTES) >> 4);
+        const uint32_t d = tmem_base + FV_S_COL + (j & 1) * FA_BN;
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16(d, dQ0 + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    if (ntiles > 1) issue_s(1);
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = j % FA_STAGES;
+      mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j written (and, if it was needed, O rescaled) by all 4 warps
+      tc_fence_after();
+      if (leader) {
+        const uint64_t dv = dV0 + (uint64_t)((s * FA_KBYTES) >> 4);
+        const uint32_t pcol = tmem_base + FV_S_COL + (j & 1) * FA_BN;  // keys [kk*16, +16) at P columns kk*8
+#pragma unroll
+        for (int kk = 0; kk < FA_BN / 16; ++kk)
+          umma_bf16_ts(tmem_base + FV_O_COL, pcol + kk * 8, dv + (uint64_t)(kk * 128), idesc_o,
+                       (j | kk) != 0 ? 1u : 0u);
+        umma_commit(&kv_empty[s]);
+        umma_commit(o_done);
+      }
+      __syncwarp();
+      if (j + 2 < ntiles) issue_s(j + 2);  // overwrites the S/P buffer of tile j: ordered behind its P V by the pipe
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroup
+    const int r = warp * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      const int kbase = j * FA_BN;
+      const bool tail = kbase + FA_BN > Nk;
+      const uint32_t sbuf = t_lane + FV_S_COL + (j & 1) * FA_BN;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      float sv[FA_BN];
+      tmem_ld32(sbuf, sv);
+      tmem_ld32(sbuf + 32, sv + 32);
+      tmem_ld_wait();
+      if (tail) {
+#pragma unroll
+        for (int e = 0; e < FA_BN; ++e)
+          if (kbase + e >= Nk) sv[e] = -INFINITY;
+      }
+      float mx = sv[0];
+#pragma unroll
+      for (int e = 1; e < FA_BN; ++e) mx = fmaxf(mx, sv[e]);
+      // Lazy reference maximum: the exponentials are taken relative to m, which is only raised (and O, l rescaled)
+      // when some row of this warp outgrew it by more than 2^8 -- p <= 256 stays harmless in bf16 / fp32, the result
+      // O / l does not depend on the reference, and after the first few tiles no rescaling happens at all.  (With the
+      // exact running maximum, one of a warp's 32 rows moves in most tiles and the skip would rarely trigger.)
+      const float m_cand = fmaxf(m, mx * scale_log2);
+      float alpha = 1.f, m_new = m;
+      if (__any_sync(0xffffffffu, m_cand - m > 8.f)) {  // first tile: m = -inf, always taken
+        m_new = m_cand;
+        alpha = fast_exp2(m - m_new);  // first tile: exp2(-inf) = 0 (O is overwritten by its P V anyway)
+        if (j > 0) {                   // the P V of tile j-1 must have landed before its result is rescaled
+          mbar_wait(o_done, (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < FA_D / 32; ++c) {
+            float v[32];
+            uint32_t w[32];
+            tmem_ld32(t_lane + FV_O_COL + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) w[e] = __float_as_uint(v[e] * alpha);
+            tmem_st16(t_lane + FV_O_COL + c * 32, w);
+            tmem_st16(t_lane + FV_O_COL + c * 32 + 16, w + 16);
+          }
+        }
+      }
+      float lsum = 0.f;
+      uint32_t pw[FA_BN / 2];
+#pragma unroll
+      for (int e = 0; e < FA_BN; e += 2) {
+        const float p0 = fast_exp2(fmaf(sv[e], scale_log2, -m_new));  // masked keys: exp2(-inf) = 0
+        const float p1 = fast_exp2(fmaf(sv[e + 1], scale_log2, -m_new));
+        lsum += p0 + p1;
+        pw[e >> 1] = pack_bf16(p0, p1);
+      }
+      tmem_st16(sbuf, pw);            // P_j over the first 32 columns of the S tile it came from
+      tmem_st16(sbuf + 16, pw + 16);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+      l = l * alpha + lsum;
+      m = m_new;
+    }
+    mbar_wait(o_done, (ntiles - 1) & 1);
+    tc_fence_after();
+    const int row = q0 + r;
+    const float inv = 1.f / l;
+    __nv_bfloat16* orow = out + (((int64_t)b * Nq + (row < Nq ? row : 0)) * H + h) * FA_D;
+#pragma unroll
+    for (int c = 0; c < FA_D / 32; ++c) {
+      float v[32];
+      tmem_ld32(t_lane + FV_O_COL + c * 32, v);
+      tmem_ld_wait();
+      if (row < Nq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16(v[g * 8 + 0] * inv, v[g * 8 + 1] * inv);
+          u.y = pack_bf16(v[g * 8 + 2] * inv, v[g * 8 + 3] * inv);
+          u.z = pack_bf16(v[g * 8 + 4] * inv, v[g * 8 + 5] * inv);
+          u.w = pack_bf16(v[g * 8 + 6] * inv, v[g * 8 + 7] * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = u;
+        }
+      }
+    }
+    if (row < Nq) lse[((int64_t)b * H + h) * Nq + row] = (m + log2f(l)) * 0.6931471805599453f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, FA_TMEM_COLS);
+}
+
 static int make_qkv_tmap(CUtensorMap* tm, const void* base, int B, int N, int H, int box_rows) {
   const uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)N, (uint64_t)B};
   const uint64_t str[3] = {64 * 2, (uint64_t)H * 64 * 2, (uint64_t)N * H * 64 * 2};
@@ -298,6 +509,18 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* l
     configured = true;
   }
   dim3 grid((Nq + FA_BM - 1) / FA_BM, H, B);
+  static const bool use_v3 = env_flag("LGB200_ATTN_FWD_V3");  // experimental variant, see attn_fwd_tc_v3_kernel
+  if (use_v3) {
+    static bool configured3 = false;
+    if (!configured3) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FV_SMEM);
+      LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_fwd_tc(v3): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      configured3 = true;
+    }
+    attn_fwd_tc_v3_kernel<<<grid, 192, FV_SMEM, stream>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), lse, B, Nq, Nk,
+                                                          H, kv_shift, scale * 1.4426950408889634f);
+    return check_launch("attn_fwd_tc(v3)");
+  }
   attn_fwd_tc_kernel<<<grid, 192, FA_SMEM, stream>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), lse, B, Nq, Nk, H,
                                                      kv_shift, scale * 1.4426950408889634f);
   return check_launch("attn_fwd_tc");
