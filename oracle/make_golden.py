@@ -113,6 +113,30 @@ def run_heads():
     print("heads ->", path)
 
 
+def run_heads_grad():
+    """Gradients of the two other assignment heads w.r.t. the similarity (and the bin / dustbin score), from the
+    reference functions under autograd -- the fixtures the backward kernels of rows a15 / a16 will be held to."""
+    from gluefactory.models.matchers.gluestick import log_double_softmax
+    from gluefactory_nonfree.superglue import log_optimal_transport
+
+    rs = np.random.RandomState(9)
+    out = {}
+    for tag, (B, M, N) in {"a": (2, 37, 53), "b": (1, 96, 80)}.items():
+        sim0 = rs.standard_normal((B, M, N)) * 3.0
+        w = torch.from_numpy(rs.standard_normal((B, M + 1, N + 1)))
+        out[f"{tag}|sim"], out[f"{tag}|w"] = sim0, w.numpy()
+        for name, fn in (("lds", lambda s_, b_: log_double_softmax(s_, b_)),
+                         ("lot", lambda s_, b_: log_optimal_transport(s_, b_, 50))):
+            sim = torch.from_numpy(sim0).requires_grad_()
+            beta = torch.tensor(0.7, dtype=torch.float64, requires_grad=True)
+            (fn(sim, beta) * w).sum().backward()
+            out[f"{tag}|{name}|dsim"] = sim.grad.numpy()
+            out[f"{tag}|{name}|dbin"] = beta.grad.numpy()
+    path = os.path.join(OUT, "heads_grad.npz")
+    np.savez_compressed(path, **out)
+    print("heads_grad ->", path)
+
+
 def run_gluestick_attention():
     """Golden vectors for the GlueStick attention core and its MultiHeadedAttention wrapper
     (models/matchers/gluestick.py:524-551): forward and all gradients in fp64."""
@@ -173,10 +197,11 @@ def run_gt_homography():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    only = [a for a in sys.argv[1:] if not a.startswith("-")]  # regenerate single fixtures: gluestick_attn, gt_homography
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]  # single fixtures: gluestick_attn, gt_homography, heads_grad
     if only:
         for name in only:
-            {"gluestick_attn": run_gluestick_attention, "gt_homography": run_gt_homography}[name]()
+            {"gluestick_attn": run_gluestick_attention, "gt_homography": run_gt_homography,
+             "heads_grad": run_heads_grad}[name]()
         sys.exit(0)
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -190,5 +215,6 @@ if __name__ == "__main__":
     full = dict(synthetic.DEFAULT_CONF)
     run_case("lg_full_l9_n512", full, B=1, N=512, M=512, seed=15, sub=8)
     run_heads()
+    run_heads_grad()
     run_gluestick_attention()
     run_gt_homography()
