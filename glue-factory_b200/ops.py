@@ -405,8 +405,7 @@ def filter_matches(rowmax, rowarg, colarg, th):
     return m0, m1, ms0, ms1
 
 
-def log_double_softmax(sim, bin_score):
-    """gluestick.py:772-783."""
+def _log_double_softmax_fwd(sim, bin_score):
     _chk(sim, torch.float32)
     B, M, N = sim.shape
     out = torch.empty(B, M + 1, N + 1, device=sim.device, dtype=torch.float32)
@@ -415,14 +414,32 @@ def log_double_softmax(sim, bin_score):
     return out
 
 
-def log_optimal_transport(sim, alpha, iters):
-    """gluefactory_nonfree/superglue.py:198-214 (forward)."""
+def log_double_softmax(sim, bin_score):
+    """gluestick.py:772-783.  Differentiable w.r.t. sim and a tensor bin_score (heads_grad.LogDoubleSoftmaxFn)."""
+    if torch.is_tensor(bin_score) and (sim.requires_grad or bin_score.requires_grad):
+        from .heads_grad import LogDoubleSoftmaxFn
+
+        return LogDoubleSoftmaxFn.apply(sim, bin_score)
+    return _log_double_softmax_fwd(sim, float(bin_score))
+
+
+def _log_optimal_transport_fwd(sim, alpha, iters):
     _chk(sim, torch.float32)
     B, M, N = sim.shape
     out = torch.empty(B, M + 1, N + 1, device=sim.device, dtype=torch.float32)
     ws = torch.empty(_lib.load().lgb200_heads_ws_bytes(B, M, N), device=sim.device, dtype=torch.uint8)
     call("lgb200_sinkhorn", ptr(sim), float(alpha), int(iters), ptr(out), ptr(ws), B, M, N, stream_ptr())
     return out
+
+
+def log_optimal_transport(sim, alpha, iters):
+    """gluefactory_nonfree/superglue.py:198-214.  Differentiable w.r.t. sim and a tensor alpha
+    (heads_grad.LogOptimalTransportFn: reverse Sinkhorn iterations, no dense autograd tape)."""
+    if torch.is_tensor(alpha) and (sim.requires_grad or alpha.requires_grad):
+        from .heads_grad import LogOptimalTransportFn
+
+        return LogOptimalTransportFn.apply(sim, alpha, int(iters))
+    return _log_optimal_transport_fwd(sim, float(alpha), iters)
 
 
 def adam_flat_(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0, lr_per_elem=None,

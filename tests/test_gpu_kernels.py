@@ -223,6 +223,22 @@ def test_other_heads_match_golden():
         np.testing.assert_allclose(ops.log_optimal_transport(sim, 0.7, 50).cpu().numpy(), g[f"{tag}|lot"], atol=1e-4)
 
 
+def test_other_heads_backward_matches_reference_autograd():
+    """GlueStick / SuperGlue heads are differentiable (forward kernels + heads_grad.py): gradients w.r.t. the
+    similarity and the bin score against the reference's autograd (tests/golden/heads_grad.npz)."""
+    g = dict(np.load(os.path.join(GOLDEN, "heads_grad.npz")))
+    for tag in ["a", "b"]:
+        w = torch.from_numpy(g[f"{tag}|w"]).float().to(DEV)
+        for name, fn in (("lds", lambda s_, b_: ops.log_double_softmax(s_, b_)),
+                         ("lot", lambda s_, b_: ops.log_optimal_transport(s_, b_, 50))):
+            sim = torch.from_numpy(g[f"{tag}|sim"]).float().to(DEV).requires_grad_()
+            beta = torch.tensor(0.7, device=DEV, requires_grad=True)
+            (fn(sim, beta) * w).sum().backward()
+            assert rel_err(sim.grad, torch.from_numpy(g[f"{tag}|{name}|dsim"])) < 1e-3, (tag, name)
+            ref = float(g[f"{tag}|{name}|dbin"])
+            assert abs(beta.grad.item() - ref) < 1e-3 * max(1.0, abs(ref)), (tag, name, beta.grad.item(), ref)
+
+
 def test_gt_from_homography_matches_reference_labels():
     """Device GT labels are bit-exact against the reference function's own output (golden) ..."""
     g = dict(np.load(os.path.join(GOLDEN, "gt_homography.npz")))
