@@ -1001,6 +1001,193 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
   if (warp == F3_SWARPS + 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// dQ kernel, variant 4 (NOT the default yet: select with LGB200_ATTN_DQ_V4=1; staged at the end of round 1 from
+// profiles/r01_attention_pipeline_notes.md, to be validated on the first GPU call of round 2).
+// Key tiles are 128 wide, so S = Q K^T and dP = dO V^T are N=128 MMAs (64 clk per K-step instead of 2 x 45), S is
+// double-buffered and dP single-buffered in TMEM, and the softmax is split in two phases: the exponentials need only
+// S and therefore overlap the dQ(j-1) -> dP(j) MMA chain; the short dS phase waits for dP.
+// TMEM: Q [0,32) dO [32,64) | S0 [64,192) S1 [192,320) | dP [320,448) (dS written over it, 16 packed columns per
+// 32-key slice) | dQ [448,512).  smem: 4 stages x (K 16 KiB + V 16 KiB).
+// ---------------------------------------------------------------------------------------------
+constexpr int F5_KT = 128;                        // keys per tile
+constexpr int F5_STAGES = 4;
+constexpr int F5_TBYTES = F5_KT * FA_D * 2;       // 16 KiB per K or V tile
+constexpr int F5_SMEM = F5_STAGES * 2 * F5_TBYTES + 256;
+constexpr int F5_S0 = 64, F5_DP = 320, F5_ACC = 448;
+constexpr int F5_SL = F5_KT / F3_NWG;             // 32 key columns per softmax warpgroup
+
+__global__ void __launch_bounds__(F3_THREADS, 1)
+    attn_bwd_dq_v4_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                          const __nv_bfloat16* __restrict__ qg, const __nv_bfloat16* __restrict__ dog,
+                          const float* __restrict__ lse, const float* __restrict__ delta,
+                          __nv_bfloat16* __restrict__ dq, int B, int Nq, int Nk, int H, int kv_shift, float scale,
+                          float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;                                // [F5_STAGES]
+  uint8_t* sV = sK + F5_STAGES * F5_TBYTES;          // [F5_STAGES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + F5_STAGES * F5_TBYTES);
+  uint64_t* a_ready = bars;
+  uint64_t* in_full = bars + 1;               // [F5_STAGES]
+  uint64_t* in_empty = in_full + F5_STAGES;   // [F5_STAGES]
+  uint64_t* s_full = in_empty + F5_STAGES;    // [2]
+  uint64_t* dp_full = s_full + 2;             // one phase per key tile
+  uint64_t* ds_full = dp_full + 1;            // one phase per key tile
+  uint64_t* acc_done = ds_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * FB_R, h = blockIdx.y, b = blockIdx.z;
+  const int kb = (b + kv_shift) % B;
+  const int ntiles = (Nk + F5_KT - 1) / F5_KT;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(a_ready, F3_SWARPS);
+    for (int s = 0; s < F5_STAGES; ++s) {
+      mbar_init(&in_full[s], 1);
+      mbar_init(&in_empty[s], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(dp_full, 1);
+    mbar_init(ds_full, F3_SWARPS);
+    mbar_init(acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == F3_SWARPS && lane == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == F3_SWARPS + 1) tmem_alloc(tmem_slot, FB_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == F3_SWARPS) {
+    if (lane == 0) {
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % F5_STAGES;
+        mbar_wait(&in_empty[s], ((j / F5_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&in_full[s], 2 * F5_TBYTES);
+        tma_load_4d(sK + s * F5_TBYTES, &tmK, &in_full[s], 0, h, j * F5_KT, kb);
+        tma_load_4d(sV + s * F5_TBYTES, &tmV, &in_full[s], 0, h, j * F5_KT, kb);
+      }
+    }
+  } else if (warp == F3_SWARPS + 1) {
+    constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, F5_KT, 0, 0);   // (Q|dO) in TMEM x (K|V) K-major, N = 128
+    constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // dS in TMEM x K_j MN-major
+    const uint64_t dKk = make_smem_desc(smem_u32(sK), 16, 1024), dVk = make_smem_desc(smem_u32(sV), 16, 1024);
+    const uint64_t dKm = make_smem_desc(smem_u32(sK), 8192, 1024);
+    const bool leader = elect_one();
+    auto wait_tile = [&](int j) {
+      mbar_wait(&in_full[j % F5_STAGES], (j / F5_STAGES) & 1);
+      tc_fence_after();
+    };
+    auto issue_s = [&](int j) {   // S_j = Q K_j^T into S buffer j & 1
+      if (leader) {
+        const uint64_t so = (uint64_t)(((j % F5_STAGES) * F5_TBYTES) >> 4);
+        const uint32_t d = tmem_base + F5_S0 + (j & 1) * F5_KT;
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16_ts(d, tmem_base + F3_A0 + kk * 8, dKk + so + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
+      }
+      __syncwarp();
+    };
+    auto issue_dp = [&](int j) {  // dP_j = dO V_j^T into the single dP buffer
+      if (leader) {
+        const uint64_t so = (uint64_t)(((j % F5_STAGES) * F5_TBYTES) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16_ts(tmem_base + F5_DP, tmem_base + F3_A1 + kk * 8, dVk + so + (uint64_t)(kk * 2), idesc_s,
+                       kk != 0 ? 1u : 0u);
+        umma_commit(dp_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    wait_tile(0);
+    issue_s(0);
+    issue_dp(0);
+    if (ntiles > 1) {
+      wait_tile(1);
+      issue_s(1);
+    }
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = j % F5_STAGES;
+      mbar_wait(ds_full, j & 1);  // dS_j sits in the dP buffer, S_j has been consumed
+      tc_fence_after();
+      if (leader) {
+        const uint64_t so = (uint64_t)((s * F5_TBYTES) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < F5_KT / 16; ++kk)  // keys [kk*16, +16): slice kk/2 wrote them at column (kk/2)*32 + (kk%2)*8
+          umma_bf16_ts(tmem_base + F5_ACC, tmem_base + F5_DP + (kk >> 1) * F5_SL + (kk & 1) * 8,
+                       dKm + so + (uint64_t)(kk * 128), idesc_acc, (j | kk) != 0 ? 1u : 0u);
+        umma_commit(&in_empty[s]);
+      }
+      __syncwarp();
+      if (j + 1 < ntiles) issue_dp(j + 1);  // behind dQ_j in the pipe, so dS_j has been read; its tile is loaded
+      if (j + 2 < ntiles) {
+        wait_tile(j + 2);
+        issue_s(j + 2);                     // into the buffer S_j occupied
+      }
+    }
+    if (leader) umma_commit(acc_done);
+    __syncwarp();
+  } else {
+    const int c = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const int row = q0 + r;
+    {
+      const int64_t o = (((int64_t)b * Nq + (row < Nq ? row : 0)) * H + h) * FA_D + c * F3_CW;
+      load_row_part_to_tmem(qg + o, row < Nq, t_lane + F3_A0 + c * (F3_CW / 2));
+      load_row_part_to_tmem(dog + o, row < Nq, t_lane + F3_A1 + c * (F3_CW / 2));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    }
+    const int64_t lo = ((int64_t)b * H + h) * Nq + (row < Nq ? row : 0);
+    const float lse2 = row < Nq ? lse[lo] * 1.4426950408889634f : INFINITY;
+    const float dl = row < Nq ? delta[lo] : 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      // phase 1: p = exp2(S c - lse) for this warpgroup's 32 key columns (runs under the dQ_{j-1}, dP_j MMAs)
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      float pv[F5_SL];
+      tmem_ld32(t_lane + F5_S0 + (j & 1) * F5_KT + c * F5_SL, pv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < F5_SL; ++e) pv[e] = fast_exp2(fmaf(pv[e], scale_log2, -lse2)) * scale;
+      // phase 2: dS = p (dP - delta) scale, written over the dP columns it came from
+      mbar_wait(dp_full, j & 1);
+      tc_fence_after();
+      float dp[F5_SL];
+      tmem_ld32(t_lane + F5_DP + c * F5_SL, dp);
+      tmem_ld_wait();
+      uint32_t dw[F5_SL / 2];
+#pragma unroll
+      for (int e = 0; e < F5_SL; e += 2) dw[e >> 1] = pack_bf16(pv[e] * (dp[e] - dl), pv[e + 1] * (dp[e + 1] - dl));
+      tmem_st16(t_lane + F5_DP + c * F5_SL, dw);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    store_out_cols16(dq + (((int64_t)b * Nq + (row < Nq ? row : 0)) * H + h) * FA_D + c * F3_CW,
+                     t_lane + F5_ACC + c * F3_CW, row < Nq);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == F3_SWARPS + 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
+}
+
 int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
                 void* dq, void* dk, void* dv, float* delta, int B, int Nq, int Nk, int H, int kv_shift, float scale,
                 cudaStream_t stream) {
@@ -1028,9 +1215,25 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, co
     CUtensorMap tq, tk, tv, tdo, tqx, tdox;
     if ((rc = make_qkv_tmap(&tk, k, B, Nk, H, FB_C))) return rc;
     if ((rc = make_qkv_tmap(&tv, v, B, Nk, H, FB_C))) return rc;
-    attn_bwd_dq_v3_kernel<<<dim3((Nq + FB_R - 1) / FB_R, H, B), F3_THREADS, F3_SMEM, stream>>>(
-        tk, tv, static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(dout), lse, delta,
-        static_cast<__nv_bfloat16*>(dq), B, Nq, Nk, H, kv_shift, scale, sl2);
+    static const bool dq_v4 = env_flag("LGB200_ATTN_DQ_V4");  // experimental 128-key variant, see attn_bwd_dq_v4_kernel
+    if (dq_v4) {
+      static bool configured4 = false;
+      if (!configured4) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F5_SMEM);
+        LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_bwd_tc(dq v4): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured4 = true;
+      }
+      CUtensorMap tk4, tv4;
+      if ((rc = make_qkv_tmap(&tk4, k, B, Nk, H, F5_KT))) return rc;
+      if ((rc = make_qkv_tmap(&tv4, v, B, Nk, H, F5_KT))) return rc;
+      attn_bwd_dq_v4_kernel<<<dim3((Nq + FB_R - 1) / FB_R, H, B), F3_THREADS, F5_SMEM, stream>>>(
+          tk4, tv4, static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(dout), lse, delta,
+          static_cast<__nv_bfloat16*>(dq), B, Nq, Nk, H, kv_shift, scale, sl2);
+    } else {
+      attn_bwd_dq_v3_kernel<<<dim3((Nq + FB_R - 1) / FB_R, H, B), F3_THREADS, F3_SMEM, stream>>>(
+          tk, tv, static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(dout), lse, delta,
+          static_cast<__nv_bfloat16*>(dq), B, Nq, Nk, H, kv_shift, scale, sl2);
+    }
     if ((rc = make_qkv_tmap(&tq, q, B, Nq, H, FB_C))) return rc;
     if ((rc = make_qkv_tmap(&tdo, dout, B, Nq, H, FB_C))) return rc;
     {
