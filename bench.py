@@ -15,7 +15,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import torch
@@ -87,8 +86,7 @@ class ClockSampler:
 
 
 def host_threads():
-    """Threads the CPU leg may really use: affinity mask and cgroup CPU quota, capped at 32 (the oracle's
-    N=2048 GEMMs are small; more threads only add synchronisation on a many-core host)."""
+    """Threads the CPU leg may use: affinity mask and cgroup CPU quota (LGB200_CPU_THREADS overrides)."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
         with open("/sys/fs/cgroup/cpu.max") as f:
@@ -97,7 +95,20 @@ def host_threads():
             n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
     except Exception:
         pass
-    return max(1, min(n, int(os.environ.get("LGB200_CPU_THREADS", "32"))))
+    if os.environ.get("LGB200_CPU_THREADS"):
+        n = min(n, int(os.environ["LGB200_CPU_THREADS"]))
+    return max(1, n)
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 def pin(data):
@@ -113,42 +124,101 @@ def nbytes(data):
 
 
 # ------------------------------------------------------------------------------------------------
+class CpuArm:
+    """The reference's own implementation of the path on the host CPU cores: the UNMODIFIED
+    reference matcher driven through its real TwoViewPipeline (oracle/reference_runner.py; installed under baseline/_ref
+    by the build, `kind: "reference"`), or, when that copy did not travel, the oracle port (`kind: "port"`).
+    One step = zero_grad + forward + loss + backward + Adam on `B` pairs of the N=2048 / 9-layer workload, fp32."""
+
+    def __init__(self, B=1, checkpointed=False, threads=None):
+        from gluefactory_b200 import synthetic
+        from oracle import reference_runner as R
+
+        self.B, self.checkpointed = B, checkpointed
+        torch.set_num_threads(threads or host_threads())
+        conf = dict(synthetic.DEFAULT_CONF)
+        w = synthetic.make_weights(conf, seed=0)
+        data = synthetic.make_pairs(B, N_KPTS, seed=1234)
+        if R.available():
+            self.kind = "reference"
+            self.tr = R.ReferenceTrainer(R.build_pipeline(conf, w, "cpu", checkpointed=checkpointed), lr=1e-4)
+            batch = R.pipeline_batch(data)
+            self.step = lambda: self.tr.step(batch)
+        else:
+            from oracle import lightglue_oracle as O
+
+            self.kind = "port"
+            ww = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+            state = {}
+
+            def step():
+                _, st = O.train_step_cpu(ww, data, conf, adam_state=state.get("s"))
+                state["s"] = st
+            self.step = step
+
+    def time_steps(self, steps, warmup):
+        for _ in range(warmup):
+            self.step()
+        t0 = time.time()
+        for _ in range(steps):
+            self.step()
+        return (time.time() - t0) / max(steps, 1)
+
+
+def pick_threads(budget_s=40.0):
+    """The oracle's / reference's N=2048 GEMMs are small: all cores is not always fastest.  Time ONE step at every
+    candidate thread count (bounded) and keep the best; the sweep is reported so the choice is visible."""
+    cand = sorted({host_threads(), min(host_threads(), 64), min(host_threads(), 32), min(host_threads(), 16)}, reverse=True)
+    sweep, t_start = {}, time.time()
+    for n in cand:
+        arm = CpuArm(B=1, threads=n)
+        arm.step()  # warm-up (allocator, thread pool)
+        t0 = time.time()
+        arm.step()
+        sweep[n] = time.time() - t0
+        if time.time() - t_start > budget_s:
+            break
+    best = min(sweep, key=sweep.get)
+    return best, {str(k): round(1.0 / v, 4) for k, v in sweep.items()}
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's algorithm for this path on the host CPU cores.  The reference is
-    Python and does not travel to the GPU box, so this times the oracle port (oracle/lightglue_oracle.py,
-    pinned to the reference by tests/golden) -- forward + loss + backward + Adam, fp32, all host threads.
-    A 'step' is a bounded sample of the workload: ONE pair of the same N=2048 / 9-layer configuration."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, same metric / unit.
+    A 'step' is a bounded sample of the workload (ONE pair of the same N=2048 / 9-layer configuration per step; the
+    variants object adds the reference YAML's per-GPU batch of 4 and activation checkpointing)."""
     if rank != 0:
         return
-    from gluefactory_b200 import synthetic
-    from oracle import lightglue_oracle as O
-
-    torch.set_num_threads(host_threads())
-    conf = dict(synthetic.DEFAULT_CONF)
-    w = {k: v.clone().requires_grad_(True) for k, v in synthetic.make_weights(conf, seed=0).items()}
-    data = synthetic.make_pairs(1, N_KPTS, seed=1234)
     budget = float(os.environ.get("LGB200_REF_BUDGET_S", "240"))
+    t_begin = time.time()
+    threads, sweep = pick_threads()
+    arm = CpuArm(B=1, checkpointed=False, threads=threads)
     t0 = time.time()
-    _, state = O.train_step_cpu(w, data, conf)  # warm-up 1 (allocator, thread pool)
+    arm.step()
     t_one = time.time() - t0
-    warm = max(0, min(args.warmup - 1, int(0.25 * budget / max(t_one, 1e-3))))
-    for _ in range(warm):
-        O.train_step_cpu(w, data, conf, adam_state=state)
-    steps = max(1, min(args.steps, int(0.7 * budget / max(t_one, 1e-3))))
-    t0 = time.time()
-    for _ in range(steps):
-        O.train_step_cpu(w, data, conf, adam_state=state)
-    dt = (time.time() - t0) / steps
+    left = lambda: budget - (time.time() - t_begin)  # noqa: E731
+    warm = max(0, min(args.warmup - 1, int(0.2 * left() / max(t_one, 1e-3))))
+    steps = max(1, min(args.steps, int(0.55 * left() / max(t_one, 1e-3)) - warm))
+    dt = arm.time_steps(steps, warm)
     val = 1.0 / dt
+    variants = []
+    for B, ckpt in ((4, False), (1, True)):
+        if left() < (B * t_one) * 3.5 or arm.kind != "reference" and ckpt:
+            continue
+        v = CpuArm(B=B, checkpointed=ckpt, threads=threads)
+        vdt = v.time_steps(2, 1)
+        variants.append({"pairs_per_step": B, "checkpointed": ckpt, "value": B / vdt, "steps": 2, "warmup": 1})
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "steps_requested": args.steps, "warmup": warm + 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"LightGlue train step N={N_KPTS} d={D_DESC} L={N_LAYERS} (configs[2]); one pair per step",
-                   "pairs_per_step": 1},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "host_cpus": os.cpu_count(),
-                         "sample": f"{steps} train steps of 1 pair (N={N_KPTS}, L={N_LAYERS}) after {warm + 1} warm-up"},
+                   "pairs_per_step": 1, "checkpointed": False, "flash": False, "variants": variants},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": arm.kind,
+                         "host_cpus": os.cpu_count(), "cpu_model": cpu_model(), "torch": torch.__version__,
+                         "thread_sweep_pairs_per_s": sweep,
+                         "sample": f"{steps} train steps of 1 pair (N={N_KPTS}, L={N_LAYERS}, fp32, "
+                                   f"{'unmodified reference through TwoViewPipeline' if arm.kind == 'reference' else 'oracle port'})"
+                                   f" after {warm + 1} warm-up"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -157,23 +227,54 @@ def run_reference(args, rank, world):
 
 def cpu_baseline_sample(seconds=25.0):
     """Bounded CPU sample for the default run's `cpu_baseline` object (rank 0, N=1 only)."""
-    from gluefactory_b200 import synthetic
-    from oracle import lightglue_oracle as O
-
-    torch.set_num_threads(host_threads())
-    conf = dict(synthetic.DEFAULT_CONF)
-    w = {k: v.clone().requires_grad_(True) for k, v in synthetic.make_weights(conf, seed=0).items()}
-    data = synthetic.make_pairs(1, N_KPTS, seed=1234)
+    threads = min(host_threads(), int(os.environ.get("LGB200_CPU_BASELINE_THREADS", "32")))
+    arm = CpuArm(B=1, threads=threads)
     t0 = time.time()
-    _, state = O.train_step_cpu(w, data, conf)
+    arm.step()
     t_one = time.time() - t0
     steps = max(1, min(4, int(seconds / max(t_one, 1e-3)) - 1))
-    t0 = time.time()
-    for _ in range(steps):
-        O.train_step_cpu(w, data, conf, adam_state=state)
-    dt = (time.time() - t0) / steps
-    return {"value": 1.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "host_cpus": os.cpu_count(),
-            "sample": f"{steps} train steps of 1 pair (N={N_KPTS}, L={N_LAYERS}, fp32, oracle port) after 1 warm-up"}
+    dt = arm.time_steps(steps, 0)
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": arm.kind, "host_cpus": os.cpu_count(),
+            "cpu_model": cpu_model(),
+            "sample": f"{steps} train steps of 1 pair (N={N_KPTS}, L={N_LAYERS}, fp32, "
+                      f"{'unmodified reference' if arm.kind == 'reference' else 'oracle port'}) after 1 warm-up; "
+                      "`--impl reference` runs the full-thread sweep, batch-4 and checkpointed variants"}
+
+
+def gpu_eager_baseline(dev, B=4, steps=5, warmup=3):
+    """The same-box GPU competitor: the reference ships no GPU kernels,
+    so its PyTorch modules on this B200 (`.cuda()`; fp32 and `--mp bfloat16` autocast) are what the plugin replaces.
+    Bounded: B pairs per step (the reference YAML's per-GPU batch), a few steps, rank 0 at N=1 only."""
+    from gluefactory_b200 import synthetic
+    from oracle import reference_runner as R
+
+    if not R.available():
+        return {"unavailable": "baseline/_ref did not travel (reference not installed)"}
+    conf = dict(synthetic.DEFAULT_CONF)
+    w = synthetic.make_weights(conf, seed=0)
+    batch = synthetic.to_device(R.pipeline_batch(synthetic.make_pairs(B, N_KPTS, seed=1234)), dev)
+    out = {"pairs_per_step": B, "steps": steps, "warmup": warmup, "unit": UNIT,
+           "what": "unmodified reference matcher through TwoViewPipeline on this GPU, PyTorch eager (train.py loop restated)"}
+    for tag, mp_dtype, ckpt in (("fp32", None, False), ("bf16_autocast", torch.bfloat16, False),
+                                ("bf16_autocast_checkpointed", torch.bfloat16, True)):
+        try:
+            tr = R.ReferenceTrainer(R.build_pipeline(conf, w, dev, checkpointed=ckpt), lr=1e-4, mp_dtype=mp_dtype)
+            for _ in range(warmup):
+                tr.step(batch)
+            torch.cuda.synchronize(dev)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(steps):
+                tr.step(batch)
+            e.record()
+            torch.cuda.synchronize(dev)
+            out[tag] = B * steps / (s.elapsed_time(e) / 1e3)
+            del tr
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001 -- a baseline must never take the bench down
+            out[tag] = None
+            out[tag + "_error"] = str(ex)[:200]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -215,10 +316,14 @@ def main():
     model = LightGlue(conf)
     model.load_state_dict(synthetic.make_weights(conf, seed=0), strict=False)
     model = model.to(dev)
-    trainer = MatcherTrainer(model, lr=1e-4)
+    # labels are generated on the device inside every step (gt.cu, the reference's ground_truth component): a batch
+    # is keypoints + descriptors + image sizes + the homography, nothing N x N crosses PCIe
+    from gluefactory_b200.matchers.homography_matcher import HomographyMatcher
+
+    trainer = MatcherTrainer(model, lr=1e-4, ground_truth=HomographyMatcher({"th_positive": 3.0, "th_negative": 3.0}))
 
     B = args.batch
-    pool = [pin(synthetic.make_pairs(B, N_KPTS, seed=1234 + 1000 * rank + i)) for i in range(2)]
+    pool = [pin(synthetic.make_pairs(B, N_KPTS, seed=1234 + 1000 * rank + i, with_gt=False)) for i in range(2)]
     pool_dev = [synthetic.to_device(p, dev) for p in pool]
     h2d = nbytes(pool[0])
 
@@ -286,7 +391,7 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": f"LightGlue matcher train step, N=M={N_KPTS} keypoints, d={D_DESC}, L={N_LAYERS}, H={N_HEADS} "
-                               "(BASELINE.json configs[2]); forward+loss+backward+all-reduce+Adam",
+                               "(BASELINE.json configs[2]); device GT labels+forward+loss+backward+all-reduce+Adam",
                    "pairs_per_gpu_per_step": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "launch": "cuda-graph replay of the whole step" if use_graph else "eager (host launches)",
                    "l2": "per-step working set (activations + N x N similarities, >1 GB) exceeds the 126 MB L2; inputs rotate",
@@ -299,6 +404,9 @@ def main():
     if roof is not None:
         line["roofline"] = roof
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del trainer, pool_dev
+        torch.cuda.empty_cache()
+        line["gpu_eager_baseline"] = gpu_eager_baseline(dev)
         line["cpu_baseline"] = cpu_baseline_sample()
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -313,38 +421,58 @@ def main():
 
 
 def kernel_roofline(trainer, pool_dev, B, dev):
-    """Average device time of the dominant kernel (the tcgen05 attention forward, 36 launches per
-    step) measured with CUDA events around each launch, vs its algorithmic FLOPs."""
+    """Device time of the attention kernels, measured live with CUDA events around every launch of the C-ABI entry
+    points inside two extra eager steps, against their ALGORITHMIC FLOPs (no recompute counted):
+    with C = 2 N^2 D per pair, one launch covers the 2B sequences of the batch and
+        forward : self 4C (2 images x {QK^T, PV}), cross 3C (S shared by the two directions; executed as 4C)
+        backward: self 8C, cross 6C.
+    The top-level object is the dominant group (attention backward, self and cross launches averaged with their own
+    FLOP counts); `kernels` lists forward / backward, self / cross separately."""
     from gluefactory_b200 import _lib
 
-    name = os.environ.get("LGB200_ROOFLINE_ENTRY", "lgb200_attn_bwd")
+    names = {"lgb200_attn_fwd", "lgb200_attn_bwd"}
     _lib.timed_events.clear()
-    _lib.timed_entry = name
+    _lib.timed_entry = names
+    # kv_shift (> 0 for the cross-attention launches) is argument 9 of attn_fwd and 14 of attn_bwd (include/lgb200.h)
+    _lib.timed_tagger = lambda name, a: "cross" if (a[9] if name == "lgb200_attn_fwd" else a[14]) else "self"
     for i in range(2):
         trainer.step(pool_dev[i % len(pool_dev)])
     torch.cuda.synchronize()
-    _lib.timed_entry = None
-    times = [s.elapsed_time(e) for s, e, _ in _lib.timed_events]
+    _lib.timed_entry, _lib.timed_tagger = None, None
+    groups = {}
+    for s, e, tag in _lib.timed_events:
+        groups.setdefault(tag, []).append(s.elapsed_time(e))
     _lib.timed_events.clear()
-    if not times:
+    if not groups:
         return None
-    avg_ms = sum(times) / len(times)
-    # one launch = all heads of the [image0; image1] batch: 2B sequences of N tokens, H heads.
-    # algorithmic FLOPs per launch (no recompute): fwd 2 GEMMs, bwd 4 GEMMs (5 for self-attention's dK);
-    # we count fwd = 4 N^2 d per (seq, head), bwd = 2x fwd.
-    per_head = 4 * N_KPTS * N_KPTS * 64
-    flops = per_head * N_HEADS * 2 * B * (2 if name == "lgb200_attn_bwd" else 1)
     peaks = measured_peaks()
-    achieved = flops / (avg_ms * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    C = 2 * N_KPTS * N_KPTS * D_DESC * B  # one all-heads contraction for every pair of the batch
+    alg = {("lgb200_attn_fwd", "self"): 4 * C, ("lgb200_attn_fwd", "cross"): 3 * C,
+           ("lgb200_attn_bwd", "self"): 8 * C, ("lgb200_attn_bwd", "cross"): 6 * C}
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            per_seq = json.load(f).get(name + "_per_sequence")
-        traffic = per_seq * 2 * B if per_seq else None  # one launch covers the 2B sequences of the batch
-    return {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tflops_sustained"], "traffic": traffic, "avg_launch_ms": avg_ms,
-            "launches_timed": len(times), "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)"}
+            tj = json.load(f)
+        if tj.get("sequences_per_launch") == 2 * B:  # only quote a capture taken at this run's batch size
+            traffic = tj.get("dram_bytes_per_launch", {})
+    kernels = {}
+    for (name, kind), ts in sorted(groups.items()):
+        avg_ms = sum(ts) / len(ts)
+        ach = alg[(name, kind)] / (avg_ms * 1e-3) / 1e12
+        kernels[f"{name[7:]}_{kind}"] = {"avg_launch_ms": avg_ms, "launches_timed": len(ts), "achieved": ach,
+                                         "frac": ach / peaks["tflops_sustained"], "algorithmic_gflop": alg[(name, kind)] / 1e9}
+    bw = [(k, v) for k, v in kernels.items() if k.startswith("attn_bwd")]
+    flops = sum(v["algorithmic_gflop"] * v["launches_timed"] for _, v in bw) * 1e9
+    secs = sum(v["avg_launch_ms"] * v["launches_timed"] for _, v in bw) * 1e-3
+    n = sum(v["launches_timed"] for _, v in bw)
+    achieved = flops / secs / 1e12
+    return {"kernel": "lgb200_attn_bwd (attn_bwd_prep + attn_bwd_dq + attn_bwd_dkv; self 8C and cross 6C launches)",
+            "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["tflops_sustained"], "traffic": traffic.get("lgb200_attn_bwd"),
+            "traffic_source": "profiles/r02_roofline_traffic.json (ncu --set full of this command at this batch size)" if traffic else None,
+            "avg_launch_ms": secs / n * 1e3, "launches_timed": n, "kernels": kernels,
+            "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)"}
 
 
 if __name__ == "__main__":

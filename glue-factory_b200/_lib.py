@@ -48,7 +48,9 @@ SIGNATURES = {
     "lgb200_sinkhorn": (_i, [_vp, _f, _i, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_gt_homography_ws_bytes": (_sz, [_i, _i, _i]),
     "lgb200_gt_from_homography": (_i, [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "lgb200_adam_flat": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _i, _vp, _f, _vp]),
+    "lgb200_adam_flat": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _i, _vp, _f, _vp, _vp, _vp, _vp]),
+    "lgb200_flat_grad_check": (_i, [_vp, _i64, _vp, _vp]),
+    "lgb200_amp_update": (_i, [_vp, _vp, _vp, _vp, _f, _f, _i, _vp]),
     "lgb200_cast_bf16": (_i, [_vp, _vp, _i64, _vp]),
     "lgb200_colsum_slabs": (_i, [_i64, _i]),
     "lgb200_colsum": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
@@ -74,7 +76,7 @@ def load(check_device=True):
             fn = getattr(lib, name)  # AttributeError if the symbol is missing
             fn.restype = res
             fn.argtypes = args
-        if lib.lgb200_abi_version() != 1:
+        if lib.lgb200_abi_version() != 2:
             raise Lgb200Error("liblgb200.so ABI version mismatch")
         _lib = lib
     if check_device and not _device_checked:
@@ -95,12 +97,13 @@ KERNELS_PER_CALL = {
     "lgb200_ln_gelu_fwd": 1, "lgb200_ln_gelu_bwd": 1, "lgb200_gemm_bf16": 1, "lgb200_assign_lse": 2,
     "lgb200_assign_scores": 2, "lgb200_assign_bwd": 1, "lgb200_filter_matches": 1, "lgb200_log_double_softmax": 3,
     "lgb200_adam_flat": 1, "lgb200_cast_bf16": 1, "lgb200_colsum": 1, "lgb200_residual_add_cast": 1,
-    "lgb200_gemm_bf16_splitk": 2, "lgb200_gt_from_homography": 3,
+    "lgb200_gemm_bf16_splitk": 2, "lgb200_gt_from_homography": 3, "lgb200_flat_grad_check": 1, "lgb200_amp_update": 1,
 }
 launch_count = 0          # running total of kernels launched through `call`
-timed_entry = None        # when set to an entry-point name, every call of it is bracketed by CUDA events
-timed_events = []         # [(start_event, end_event, tag)]
+timed_entry = None        # entry-point name or a set of names: every call of them is bracketed by CUDA events
+timed_events = []         # [(start_event, end_event, tag)]; tag = (name, timed_tagger(name, args)) when a tagger is set
 timed_tag = None
+timed_tagger = None       # optional callable (name, args) -> hashable, e.g. to tell self- from cross-attention launches
 
 
 def call(name, *args):
@@ -108,14 +111,14 @@ def call(name, *args):
     library's message (reference convention: Python exceptions / asserts, lightglue.py:413-414)."""
     global launch_count
     lib = load()
-    if timed_entry == name:
+    if timed_entry is not None and (timed_entry == name or (isinstance(timed_entry, (set, frozenset)) and name in timed_entry)):
         import torch
 
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         rc = getattr(lib, name)(*args)
         e.record()
-        timed_events.append((s, e, timed_tag))
+        timed_events.append((s, e, (name, timed_tagger(name, args)) if timed_tagger is not None else timed_tag))
     else:
         rc = getattr(lib, name)(*args)
     if rc != 0:

@@ -79,6 +79,41 @@ int make_tmap(CUtensorMap* out, const void* base, bool fp32, int rank, const uin
   return 0;
 }
 
+int ensure_dyn_smem(const void* func, int bytes) {
+  constexpr int kMaxFuncs = 64, kMaxDevs = 16;
+  static const void* funcs[kMaxFuncs];
+  static unsigned done[kMaxFuncs];  // bit d: configured on device d
+  static int nfuncs = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  LGB_REQUIRE(e == cudaSuccess, kErrCuda, "cudaGetDevice: %s", cudaGetErrorString(e));
+  int slot = -1;
+  for (int i = 0; i < nfuncs; ++i)
+    if (funcs[i] == func) slot = i;
+  if (slot >= 0 && dev < kMaxDevs && (done[slot] >> dev & 1u)) return 0;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  LGB_REQUIRE(e == cudaSuccess, kErrCuda, "cudaFuncSetAttribute(%d bytes): %s", bytes, cudaGetErrorString(e));
+  if (slot < 0 && nfuncs < kMaxFuncs) {
+    slot = nfuncs++;
+    funcs[slot] = func;
+    done[slot] = 0;
+  }
+  if (slot >= 0 && dev < kMaxDevs) done[slot] |= 1u << dev;
+  return 0;
+}
+
+int device_sm_count() {
+  static int counts[16];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 16 && counts[dev]) return counts[dev];
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev >= 0 && dev < 16) counts[dev] = n;
+  return n;
+}
+
 bool env_flag(const char* name) {
   const char* v = getenv(name);
   return v && v[0] && strcmp(v, "0") != 0;

@@ -20,33 +20,16 @@
 
 namespace lgb {
 
-// 32 consecutive columns [c*32, c*32+32) of a 64-column bf16 row (128 B, swizzled 16-byte chunks)
-__device__ __forceinline__ void store_row_chunk32_fwd(uint8_t* row_base, int sw, int c, const float* v) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    uint4 u;
-    u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-    u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-    const int chunk = c * 4 + g;
-    *reinterpret_cast<uint4*>(row_base + ((chunk ^ sw) << 4)) = u;
-  }
-}
-
 constexpr int FA_BM = 128;     // queries per CTA
 constexpr int FA_BN = 64;      // keys per iteration
 constexpr int FA_D = 64;
 constexpr int FA_STAGES = 4;
 constexpr int FA_QBYTES = FA_BM * FA_D * 2;   // 16 KiB
 constexpr int FA_KBYTES = FA_BN * FA_D * 2;   // 8 KiB
-constexpr int FA_PBYTES = FA_BM * FA_BN * 2;  // 16 KiB (one 128-byte swizzle row per query)
-constexpr int FA_SMEM = FA_QBYTES + FA_STAGES * 2 * FA_KBYTES + 2 * FA_PBYTES + 256;
-constexpr int FA_TMEM_COLS = 256;             // S0 [0,64) S1 [64,128) O0 [128,192) O1 [192,256)
+constexpr int FA_SMEM = FA_QBYTES + FA_STAGES * 2 * FA_KBYTES + 256;
+constexpr int FA_TMEM_COLS = 256;             // S0 [0,64) S1 [64,128) (P over their first 32 columns), O [128,192)
 constexpr int FA_S_COL = 0, FA_O_COL = 128;
 
-// Software pipeline (per CTA):  the MMA thread keeps TWO S tiles in flight (double-buffered in TMEM) so the
-// softmax warps never wait for Q K^T; P and the per-tile O = P V are double-buffered as well, so the P V of
-// tile j runs while the softmax of tile j+1 is being computed and is folded into the register accumulator
-// one iteration later.
 // Optional clock64 pipeline trace of CTA (0,0,0) (read back with lgb200_debug_read_trace / scripts/trace_attn.py):
 // -DLGB_TRACE=1 traces the dKV kernel, -DLGB_TRACE=3 the forward kernel.
 // role 0 = producer, 1 = MMA issuer, 2 / 3 = two softmax warps; 4 time stamps per tile.
@@ -83,217 +66,19 @@ __device__ long long g_trace[4 * 64 * 4];
 #define LGB_TR_LIFE(k) do {} while (0)
 #endif
 
-__global__ void __launch_bounds__(192, 2)
-    attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                       const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out,
-                       float* __restrict__ lse, int B, int Nq, int Nk, int H, int kv_shift, float scale_log2) {
-  LGB_TRF_LIFE(0);
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + FA_QBYTES;
-  uint8_t* sV = sK + FA_STAGES * FA_KBYTES;
-  uint8_t* sP = sV + FA_STAGES * FA_KBYTES;  // [2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_PBYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;               // [FA_STAGES]
-  uint64_t* kv_empty = kv_full + FA_STAGES;   // [FA_STAGES]
-  uint64_t* s_full = kv_empty + FA_STAGES;    // [2]
-  uint64_t* p_full = s_full + 2;              // [2]
-  uint64_t* o_full = p_full + 2;              // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
-  const int kb = (b + kv_shift) % B;
-  const int ntiles = (Nk + FA_BN - 1) / FA_BN;
-
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(q_full, 1);
-    for (int s = 0; s < FA_STAGES; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 4);
-      mbar_init(&o_full[s], 1);
-    }
-    mbar_fence_init();
-  }
-  if (warp == 4 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 5) tmem_alloc(tmem_slot, FA_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 4) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(q_full, FA_QBYTES);
-      tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % FA_STAGES;
-        mbar_wait(&kv_empty[s], ((j / FA_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[s], 2 * FA_KBYTES);
-        tma_load_4d(sK + s * FA_KBYTES, &tmK, &kv_full[s], 0, h, j * FA_BN, kb);
-        tma_load_4d(sV + s * FA_KBYTES, &tmV, &kv_full[s], 0, h, j * FA_BN, kb);
-      }
-    }
-  } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    // The whole warp runs the loop (waits, descriptor arithmetic stay warp-uniform -> uniform registers);
-    // one elected lane issues the tcgen05 instructions.
-    constexpr uint32_t idesc_s = make_idesc_bf16(FA_BM, FA_BN, 0, 0);  // Q (K-major) x K_j (K-major)
-    constexpr uint32_t idesc_o = make_idesc_bf16(FA_BM, FA_D, 0, 1);   // P (K-major) x V_j (MN-major)
-    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
-    const uint64_t dQ0 = make_smem_desc(aQ, 16, 1024), dK0 = make_smem_desc(aK, 16, 1024);
-    const uint64_t dP0 = make_smem_desc(aP, 16, 1024), dV0 = make_smem_desc(aV, 8192, 1024);
-    const bool leader = elect_one();
-    auto issue_s = [&](int j) {
-      const int s = j % FA_STAGES;
-      mbar_wait(&kv_full[s], (j / FA_STAGES) & 1);
-      tc_fence_after();
-      if (leader) {
-        const uint64_t dk = dK0 + (uint64_t)((s * FA_KBYTES) >> 4);
-        const uint32_t d = tmem_base + FA_S_COL + (j & 1) * FA_BN;
-#pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk) umma_bf16(d, dQ0 + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(&s_full[j & 1]);
-      }
-      __syncwarp();
-    };
-    mbar_wait(q_full, 0);
-    issue_s(0);
-    if (ntiles > 1) issue_s(1);
-    for (int j = 0; j < ntiles; ++j) {
-      const int s = j % FA_STAGES;
-      mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      if (leader) LGB_TRF(1, j, 0);
-      if (leader) {
-        const uint64_t dp = dP0 + (uint64_t)(((j & 1) * FA_PBYTES) >> 4);
-        const uint64_t dv = dV0 + (uint64_t)((s * FA_KBYTES) >> 4);
-        const uint32_t d = tmem_base + FA_O_COL + (j & 1) * FA_D;
-#pragma unroll
-        for (int kk = 0; kk < FA_BN / 16; ++kk)
-          umma_bf16(d, dp + (uint64_t)(kk * 2), dv + (uint64_t)(kk * 128), idesc_o, kk != 0 ? 1u : 0u);
-        umma_commit(&kv_empty[s]);
-        umma_commit(&o_full[j & 1]);
-      }
-      if (leader) LGB_TRF(1, j, 1);
-      __syncwarp();
-      if (j + 2 < ntiles) issue_s(j + 2);
-      if (leader) LGB_TRF(1, j, 2);
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax warpgroup
-    const int r = warp * 32 + lane;  // query row within the tile == TMEM lane
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    float o_acc[FA_D];
-#pragma unroll
-    for (int d = 0; d < FA_D; ++d) o_acc[d] = 0.f;
-    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    const int sw = r & 7;
-    auto fold_o = [&](int jj, float a) {  // o_acc = o_acc * a + O_jj
-      mbar_wait(&o_full[jj & 1], (jj >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < FA_D / 32; ++c) {
-        float v[32];
-        tmem_ld32(t_lane + FA_O_COL + (jj & 1) * FA_D + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o_acc[c * 32 + e] = fmaf(o_acc[c * 32 + e], a, v[e]);
-      }
-    };
-    for (int j = 0; j < ntiles; ++j) {
-      const int kbase = j * FA_BN;
-      const bool tail = kbase + FA_BN > Nk;
-      uint8_t* prow = sP + (j & 1) * FA_PBYTES + r * 128;
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      if (lane == 0 && (warp == 0 || warp == 3)) LGB_TRF(2 + (warp == 3), j, 0);
-      float sv[FA_BN];
-      tmem_ld32(t_lane + FA_S_COL + (j & 1) * FA_BN, sv);
-      tmem_ld32(t_lane + FA_S_COL + (j & 1) * FA_BN + 32, sv + 32);
-      tmem_ld_wait();
-      if (lane == 0 && (warp == 0 || warp == 3)) LGB_TRF(2 + (warp == 3), j, 1);
-      if (tail) {
-#pragma unroll
-        for (int e = 0; e < FA_BN; ++e)
-          if (kbase + e >= Nk) sv[e] = -INFINITY;
-      }
-      float mx = sv[0];
-#pragma unroll
-      for (int e = 1; e < FA_BN; ++e) mx = fmaxf(mx, sv[e]);
-      const float m_new = fmaxf(m, mx * scale_log2);
-      const float alpha = fast_exp2(m - m_new);  // first tile: exp2(-inf) = 0
-      float lsum = 0.f;
-#pragma unroll
-      for (int e = 0; e < FA_BN; ++e) {
-        sv[e] = fast_exp2(fmaf(sv[e], scale_log2, -m_new));  // masked keys: exp2(-inf) = 0
-        lsum += sv[e];
-      }
-      store_row_chunk32_fwd(prow, sw, 0, sv);
-      store_row_chunk32_fwd(prow, sw, 1, sv + 32);
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[j & 1]);
-      if (lane == 0 && (warp == 0 || warp == 3)) LGB_TRF(2 + (warp == 3), j, 2);
-      if (j > 0) fold_o(j - 1, alpha_prev);
-      if (lane == 0 && (warp == 0 || warp == 3)) LGB_TRF(2 + (warp == 3), j, 3);  // the P V of the previous tile ran under this tile's softmax
-      l = l * alpha + lsum;
-      m = m_new;
-      alpha_prev = alpha;
-    }
-    fold_o(ntiles - 1, alpha_prev);
-    const int row = q0 + r;
-    if (row < Nq) {
-      const float inv = 1.f / l;
-      __nv_bfloat16* orow = out + (((int64_t)b * Nq + row) * H + h) * FA_D;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 u;
-        u.x = pack_bf16(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
-        u.y = pack_bf16(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
-        u.z = pack_bf16(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv);
-        u.w = pack_bf16(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(orow + g * 8) = u;
-      }
-      lse[((int64_t)b * H + h) * Nq + row] = (m + log2f(l)) * 0.6931471805599453f;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, FA_TMEM_COLS);
-  LGB_TRF_LIFE(1);
-}
-
 // token-major [B, N, H, 64] bf16 -> 4-D tensor map {64, H, N, B}, box {64, 1, rows, 1}
 // ---------------------------------------------------------------------------------------------
-// FORWARD, variant 3 (NOT the default yet: select with LGB200_ATTN_FWD_V3=1; written at the end of round 1 from
-// the pipeline trace in profiles/r01_attention_pipeline_notes.md, to be validated on the first GPU call of round 2).
-// Differences from attn_fwd_tc_kernel:
+// FORWARD kernel (round 2: the round-1 kernel handed P to the second MMA through shared memory and folded O into 64
+// registers per thread every tile; 226 -> 188 us at 32 sequences, profiles/r02_stage_check.md):
 //   * P never goes through shared memory: the softmax warps write it (bf16, two keys per 32-bit column) over the
 //     first 32 columns of the S tile it was computed from, and P V is a TS-form MMA (A operand in TMEM) exactly like
-//     the accumulating MMAs of the backward kernels -- no st.shared, no fence.proxy.async, 32 KiB less smem;
-//   * O accumulates in TMEM across key tiles (accumulate flag) instead of being folded into 64 registers per thread
-//     every tile; a softmax warp rescales its O rows in TMEM only when one of its 32 rows outgrew the reference
-//     maximum by more than 2^8 (lazy rescaling: exponentials relative to a stale maximum, bounded by 256).
-// Per tile and thread this removes 64 FFMA + a 64-column tcgen05.ld + 8 st.shared + one barrier round trip.
+//     the accumulating MMAs of the backward kernels -- no st.shared, no fence.proxy.async;
+//   * O accumulates in TMEM across key tiles (accumulate flag); a softmax warp rescales its O rows in TMEM only when
+//     one of its 32 rows outgrew the reference maximum by more than 2^8 (lazy rescaling: exponentials relative to a
+//     stale maximum, bounded by 256, so after the first few tiles O is never touched again).
 // ---------------------------------------------------------------------------------------------
-constexpr int FV_SMEM = FA_QBYTES + FA_STAGES * 2 * FA_KBYTES + 256;
-constexpr int FV_S_COL = 0, FV_O_COL = 128;  // TMEM: S0 [0,64) S1 [64,128) (P over their first 32 columns), O [128,192)
-
 __global__ void __launch_bounds__(192, 2)
-    attn_fwd_tc_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+    attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                           const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out,
                           float* __restrict__ lse, int B, int Nq, int Nk, int H, int kv_shift, float scale_log2) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -365,7 +150,7 @@ __global__ void __launch_bounds__(192, 2)
       tc_fence_after();
       if (leader) {
         const uint64_t dk = dK0 + (uint64_t)((s * FA_KBYTES) >> 4);
-        const uint32_t d = tmem_base + FV_S_COL + (j & 1) * FA_BN;
+        const uint32_t d = tmem_base + FA_S_COL + (j & 1) * FA_BN;
 #pragma unroll
         for (int kk = 0; kk < FA_D / 16; ++kk)
           umma_bf16(d, dQ0 + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
@@ -382,10 +167,10 @@ __global__ void __launch_bounds__(192, 2)
       tc_fence_after();
       if (leader) {
         const uint64_t dv = dV0 + (uint64_t)((s * FA_KBYTES) >> 4);
-        const uint32_t pcol = tmem_base + FV_S_COL + (j & 1) * FA_BN;  // keys [kk*16, +16) at P columns kk*8
+        const uint32_t pcol = tmem_base + FA_S_COL + (j & 1) * FA_BN;  // keys [kk*16, +16) at P columns kk*8
 #pragma unroll
         for (int kk = 0; kk < FA_BN / 16; ++kk)
-          umma_bf16_ts(tmem_base + FV_O_COL, pcol + kk * 8, dv + (uint64_t)(kk * 128), idesc_o,
+          umma_bf16_ts(tmem_base + FA_O_COL, pcol + kk * 8, dv + (uint64_t)(kk * 128), idesc_o,
                        (j | kk) != 0 ? 1u : 0u);
         umma_commit(&kv_empty[s]);
         umma_commit(o_done);
@@ -401,7 +186,7 @@ __global__ void __launch_bounds__(192, 2)
     for (int j = 0; j < ntiles; ++j) {
       const int kbase = j * FA_BN;
       const bool tail = kbase + FA_BN > Nk;
-      const uint32_t sbuf = t_lane + FV_S_COL + (j & 1) * FA_BN;
+      const uint32_t sbuf = t_lane + FA_S_COL + (j & 1) * FA_BN;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       float sv[FA_BN];
@@ -432,12 +217,12 @@ __global__ void __launch_bounds__(192, 2)
           for (int c = 0; c < FA_D / 32; ++c) {
             float v[32];
             uint32_t w[32];
-            tmem_ld32(t_lane + FV_O_COL + c * 32, v);
+            tmem_ld32(t_lane + FA_O_COL + c * 32, v);
             tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 32; ++e) w[e] = __float_as_uint(v[e] * alpha);
-            tmem_st16(t_lane + FV_O_COL + c * 32, w);
-            tmem_st16(t_lane + FV_O_COL + c * 32 + 16, w + 16);
+            tmem_st16(t_lane + FA_O_COL + c * 32, w);
+            tmem_st16(t_lane + FA_O_COL + c * 32 + 16, w + 16);
           }
         }
       }
@@ -467,7 +252,7 @@ __global__ void __launch_bounds__(192, 2)
 #pragma unroll
     for (int c = 0; c < FA_D / 32; ++c) {
       float v[32];
-      tmem_ld32(t_lane + FV_O_COL + c * 32, v);
+      tmem_ld32(t_lane + FA_O_COL + c * 32, v);
       tmem_ld_wait();
       if (row < Nq) {
 #pragma unroll
@@ -502,25 +287,8 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* l
   if ((rc = make_qkv_tmap(&tq, q, B, Nq, H, FA_BM))) return rc;  // K/V boxes: FA_BN rows
   if ((rc = make_qkv_tmap(&tk, k, B, Nk, H, FA_BN))) return rc;
   if ((rc = make_qkv_tmap(&tv, v, B, Nk, H, FA_BN))) return rc;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
-    LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_tc_kernel), FA_SMEM))) return rc;
   dim3 grid((Nq + FA_BM - 1) / FA_BM, H, B);
-  static const bool use_v3 = env_flag("LGB200_ATTN_FWD_V3");  // experimental variant, see attn_fwd_tc_v3_kernel
-  if (use_v3) {
-    static bool configured3 = false;
-    if (!configured3) {
-      cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FV_SMEM);
-      LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_fwd_tc(v3): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      configured3 = true;
-    }
-    attn_fwd_tc_v3_kernel<<<grid, 192, FV_SMEM, stream>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), lse, B, Nq, Nk,
-                                                          H, kv_shift, scale * 1.4426950408889634f);
-    return check_launch("attn_fwd_tc(v3)");
-  }
   attn_fwd_tc_kernel<<<grid, 192, FA_SMEM, stream>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), lse, B, Nq, Nk, H,
                                                      kv_shift, scale * 1.4426950408889634f);
   return check_launch("attn_fwd_tc");
@@ -1001,193 +769,6 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
   if (warp == F3_SWARPS + 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
 }
 
-// ---------------------------------------------------------------------------------------------
-// dQ kernel, variant 4 (NOT the default yet: select with LGB200_ATTN_DQ_V4=1; staged at the end of round 1 from
-// profiles/r01_attention_pipeline_notes.md, to be validated on the first GPU call of round 2).
-// Key tiles are 128 wide, so S = Q K^T and dP = dO V^T are N=128 MMAs (64 clk per K-step instead of 2 x 45), S is
-// double-buffered and dP single-buffered in TMEM, and the softmax is split in two phases: the exponentials need only
-// S and therefore overlap the dQ(j-1) -> dP(j) MMA chain; the short dS phase waits for dP.
-// TMEM: Q [0,32) dO [32,64) | S0 [64,192) S1 [192,320) | dP [320,448) (dS written over it, 16 packed columns per
-// 32-key slice) | dQ [448,512).  smem: 4 stages x (K 16 KiB + V 16 KiB).
-// ---------------------------------------------------------------------------------------------
-constexpr int F5_KT = 128;                        // keys per tile
-constexpr int F5_STAGES = 4;
-constexpr int F5_TBYTES = F5_KT * FA_D * 2;       // 16 KiB per K or V tile
-constexpr int F5_SMEM = F5_STAGES * 2 * F5_TBYTES + 256;
-constexpr int F5_S0 = 64, F5_DP = 320, F5_ACC = 448;
-constexpr int F5_SL = F5_KT / F3_NWG;             // 32 key columns per softmax warpgroup
-
-__global__ void __launch_bounds__(F3_THREADS, 1)
-    attn_bwd_dq_v4_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                          const __nv_bfloat16* __restrict__ qg, const __nv_bfloat16* __restrict__ dog,
-                          const float* __restrict__ lse, const float* __restrict__ delta,
-                          __nv_bfloat16* __restrict__ dq, int B, int Nq, int Nk, int H, int kv_shift, float scale,
-                          float scale_log2) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sK = smem;                                // [F5_STAGES]
-  uint8_t* sV = sK + F5_STAGES * F5_TBYTES;          // [F5_STAGES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + F5_STAGES * F5_TBYTES);
-  uint64_t* a_ready = bars;
-  uint64_t* in_full = bars + 1;               // [F5_STAGES]
-  uint64_t* in_empty = in_full + F5_STAGES;   // [F5_STAGES]
-  uint64_t* s_full = in_empty + F5_STAGES;    // [2]
-  uint64_t* dp_full = s_full + 2;             // one phase per key tile
-  uint64_t* ds_full = dp_full + 1;            // one phase per key tile
-  uint64_t* acc_done = ds_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * FB_R, h = blockIdx.y, b = blockIdx.z;
-  const int kb = (b + kv_shift) % B;
-  const int ntiles = (Nk + F5_KT - 1) / F5_KT;
-
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(a_ready, F3_SWARPS);
-    for (int s = 0; s < F5_STAGES; ++s) {
-      mbar_init(&in_full[s], 1);
-      mbar_init(&in_empty[s], 1);
-    }
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
-    mbar_init(dp_full, 1);
-    mbar_init(ds_full, F3_SWARPS);
-    mbar_init(acc_done, 1);
-    mbar_fence_init();
-  }
-  if (warp == F3_SWARPS && lane == 0) {
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == F3_SWARPS + 1) tmem_alloc(tmem_slot, FB_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == F3_SWARPS) {
-    if (lane == 0) {
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % F5_STAGES;
-        mbar_wait(&in_empty[s], ((j / F5_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&in_full[s], 2 * F5_TBYTES);
-        tma_load_4d(sK + s * F5_TBYTES, &tmK, &in_full[s], 0, h, j * F5_KT, kb);
-        tma_load_4d(sV + s * F5_TBYTES, &tmV, &in_full[s], 0, h, j * F5_KT, kb);
-      }
-    }
-  } else if (warp == F3_SWARPS + 1) {
-    constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, F5_KT, 0, 0);   // (Q|dO) in TMEM x (K|V) K-major, N = 128
-    constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // dS in TMEM x K_j MN-major
-    const uint64_t dKk = make_smem_desc(smem_u32(sK), 16, 1024), dVk = make_smem_desc(smem_u32(sV), 16, 1024);
-    const uint64_t dKm = make_smem_desc(smem_u32(sK), 8192, 1024);
-    const bool leader = elect_one();
-    auto wait_tile = [&](int j) {
-      mbar_wait(&in_full[j % F5_STAGES], (j / F5_STAGES) & 1);
-      tc_fence_after();
-    };
-    auto issue_s = [&](int j) {   // S_j = Q K_j^T into S buffer j & 1
-      if (leader) {
-        const uint64_t so = (uint64_t)(((j % F5_STAGES) * F5_TBYTES) >> 4);
-        const uint32_t d = tmem_base + F5_S0 + (j & 1) * F5_KT;
-#pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16_ts(d, tmem_base + F3_A0 + kk * 8, dKk + so + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(&s_full[j & 1]);
-      }
-      __syncwarp();
-    };
-    auto issue_dp = [&](int j) {  // dP_j = dO V_j^T into the single dP buffer
-      if (leader) {
-        const uint64_t so = (uint64_t)(((j % F5_STAGES) * F5_TBYTES) >> 4);
-#pragma unroll
-        for (int kk = 0; kk < FA_D / 16; ++kk)
-          umma_bf16_ts(tmem_base + F5_DP, tmem_base + F3_A1 + kk * 8, dVk + so + (uint64_t)(kk * 2), idesc_s,
-                       kk != 0 ? 1u : 0u);
-        umma_commit(dp_full);
-      }
-      __syncwarp();
-    };
-    mbar_wait(a_ready, 0);
-    tc_fence_after();
-    wait_tile(0);
-    issue_s(0);
-    issue_dp(0);
-    if (ntiles > 1) {
-      wait_tile(1);
-      issue_s(1);
-    }
-    for (int j = 0; j < ntiles; ++j) {
-      const int s = j % F5_STAGES;
-      mbar_wait(ds_full, j & 1);  // dS_j sits in the dP buffer, S_j has been consumed
-      tc_fence_after();
-      if (leader) {
-        const uint64_t so = (uint64_t)((s * F5_TBYTES) >> 4);
-#pragma unroll
-        for (int kk = 0; kk < F5_KT / 16; ++kk)  // keys [kk*16, +16): slice kk/2 wrote them at column (kk/2)*32 + (kk%2)*8
-          umma_bf16_ts(tmem_base + F5_ACC, tmem_base + F5_DP + (kk >> 1) * F5_SL + (kk & 1) * 8,
-                       dKm + so + (uint64_t)(kk * 128), idesc_acc, (j | kk) != 0 ? 1u : 0u);
-        umma_commit(&in_empty[s]);
-      }
-      __syncwarp();
-      if (j + 1 < ntiles) issue_dp(j + 1);  // behind dQ_j in the pipe, so dS_j has been read; its tile is loaded
-      if (j + 2 < ntiles) {
-        wait_tile(j + 2);
-        issue_s(j + 2);                     // into the buffer S_j occupied
-      }
-    }
-    if (leader) umma_commit(acc_done);
-    __syncwarp();
-  } else {
-    const int c = warp >> 2;
-    const int r = (warp & 3) * 32 + lane;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const int row = q0 + r;
-    {
-      const int64_t o = (((int64_t)b * Nq + (row < Nq ? row : 0)) * H + h) * FA_D + c * F3_CW;
-      load_row_part_to_tmem(qg + o, row < Nq, t_lane + F3_A0 + c * (F3_CW / 2));
-      load_row_part_to_tmem(dog + o, row < Nq, t_lane + F3_A1 + c * (F3_CW / 2));
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready);
-    }
-    const int64_t lo = ((int64_t)b * H + h) * Nq + (row < Nq ? row : 0);
-    const float lse2 = row < Nq ? lse[lo] * 1.4426950408889634f : INFINITY;
-    const float dl = row < Nq ? delta[lo] : 0.f;
-    for (int j = 0; j < ntiles; ++j) {
-      // phase 1: p = exp2(S c - lse) for this warpgroup's 32 key columns (runs under the dQ_{j-1}, dP_j MMAs)
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      float pv[F5_SL];
-      tmem_ld32(t_lane + F5_S0 + (j & 1) * F5_KT + c * F5_SL, pv);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < F5_SL; ++e) pv[e] = fast_exp2(fmaf(pv[e], scale_log2, -lse2)) * scale;
-      // phase 2: dS = p (dP - delta) scale, written over the dP columns it came from
-      mbar_wait(dp_full, j & 1);
-      tc_fence_after();
-      float dp[F5_SL];
-      tmem_ld32(t_lane + F5_DP + c * F5_SL, dp);
-      tmem_ld_wait();
-      uint32_t dw[F5_SL / 2];
-#pragma unroll
-      for (int e = 0; e < F5_SL; e += 2) dw[e >> 1] = pack_bf16(pv[e] * (dp[e] - dl), pv[e + 1] * (dp[e + 1] - dl));
-      tmem_st16(t_lane + F5_DP + c * F5_SL, dw);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
-    }
-    mbar_wait(acc_done, 0);
-    tc_fence_after();
-    store_out_cols16(dq + (((int64_t)b * Nq + (row < Nq ? row : 0)) * H + h) * FA_D + c * F3_CW,
-                     t_lane + F5_ACC + c * F3_CW, row < Nq);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == F3_SWARPS + 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
-}
-
 int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
                 void* dq, void* dk, void* dv, float* delta, int B, int Nq, int Nk, int H, int kv_shift, float scale,
                 cudaStream_t stream) {
@@ -1204,36 +785,14 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, co
   }
   const float sl2 = scale * 1.4426950408889634f;
   {
-    static bool configured3 = false;
-    if (!configured3) {
-      cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM);
-      LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      e = cudaFuncSetAttribute(attn_bwd_dq_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
-      LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      configured3 = true;
-    }
+    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_dkv_v3_kernel), F4_SMEM))) return rc;
+    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_dq_v3_kernel), F3_SMEM))) return rc;
     CUtensorMap tq, tk, tv, tdo, tqx, tdox;
     if ((rc = make_qkv_tmap(&tk, k, B, Nk, H, FB_C))) return rc;
     if ((rc = make_qkv_tmap(&tv, v, B, Nk, H, FB_C))) return rc;
-    static const bool dq_v4 = env_flag("LGB200_ATTN_DQ_V4");  // experimental 128-key variant, see attn_bwd_dq_v4_kernel
-    if (dq_v4) {
-      static bool configured4 = false;
-      if (!configured4) {
-        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F5_SMEM);
-        LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_bwd_tc(dq v4): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured4 = true;
-      }
-      CUtensorMap tk4, tv4;
-      if ((rc = make_qkv_tmap(&tk4, k, B, Nk, H, F5_KT))) return rc;
-      if ((rc = make_qkv_tmap(&tv4, v, B, Nk, H, F5_KT))) return rc;
-      attn_bwd_dq_v4_kernel<<<dim3((Nq + FB_R - 1) / FB_R, H, B), F3_THREADS, F5_SMEM, stream>>>(
-          tk4, tv4, static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(dout), lse, delta,
-          static_cast<__nv_bfloat16*>(dq), B, Nq, Nk, H, kv_shift, scale, sl2);
-    } else {
-      attn_bwd_dq_v3_kernel<<<dim3((Nq + FB_R - 1) / FB_R, H, B), F3_THREADS, F3_SMEM, stream>>>(
-          tk, tv, static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(dout), lse, delta,
-          static_cast<__nv_bfloat16*>(dq), B, Nq, Nk, H, kv_shift, scale, sl2);
-    }
+    attn_bwd_dq_v3_kernel<<<dim3((Nq + FB_R - 1) / FB_R, H, B), F3_THREADS, F3_SMEM, stream>>>(
+        tk, tv, static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(dout), lse, delta,
+        static_cast<__nv_bfloat16*>(dq), B, Nq, Nk, H, kv_shift, scale, sl2);
     if ((rc = make_qkv_tmap(&tq, q, B, Nq, H, FB_C))) return rc;
     if ((rc = make_qkv_tmap(&tdo, dout, B, Nq, H, FB_C))) return rc;
     {

@@ -365,19 +365,28 @@ __global__ void __launch_bounds__(256, 2)
 // Adam on the flat buffer.  g is multiplied by grad_scale (1/world for the summed all-reduce, or the
 // inverse AMP loss scale).  Matches torch.optim.Adam (no amsgrad, L2 weight decay added to the grad).
 // ---------------------------------------------------------------------------------------------
+struct AdamDev {  // optional device-resident controls (all may be null); see lgb200_adam_flat in lgb200.h
+  const int* step;          // 1-based step count (CUDA-graph replay)
+  const float* lr;          // learning rate (so a scheduler can change it between graph replays)
+  const float* loss_scale;  // GradScaler scale: gradients are multiplied by 1 / *loss_scale (GradScaler.unscale_)
+  const float* found_inf;   // != 0: skip the update entirely (GradScaler.step / the NaN guard of train.py:477-480)
+};
+
 __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                                       const float* __restrict__ lr_per_elem_or_null, float lr,
+                                                       const float* __restrict__ lr_scale_or_null, float lr,
                                                        float beta1, float beta2, float eps, float wd, float bc1,
-                                                       float bc2_sqrt, float grad_scale,
-                                                       const int* __restrict__ step_dev) {
+                                                       float bc2_sqrt, float grad_scale, AdamDev dev) {
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i0 >= n) return;
-  if (step_dev) {  // step count lives in device memory (CUDA-graph replay): bias corrections computed here
-    const float t = (float)(*step_dev);
+  if (dev.found_inf && *dev.found_inf != 0.f) return;  // whole grid takes the same branch
+  if (dev.step) {  // step count lives in device memory (CUDA-graph replay): bias corrections computed here
+    const float t = (float)(*dev.step);
     bc1 = 1.f - powf(beta1, t);
     bc2_sqrt = sqrtf(1.f - powf(beta2, t));
   }
+  if (dev.lr) lr = *dev.lr;
+  if (dev.loss_scale) grad_scale *= 1.f / *dev.loss_scale;
   if (i0 + 4 <= n) {
     float4 pp = *reinterpret_cast<float4*>(p + i0), gg = *reinterpret_cast<const float4*>(g + i0);
     float4 mm = *reinterpret_cast<float4*>(m + i0), vv = *reinterpret_cast<float4*>(v + i0);
@@ -385,7 +394,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
     float Mm[4] = {mm.x, mm.y, mm.z, mm.w}, V[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float l = lr_per_elem_or_null ? lr_per_elem_or_null[i0 + e] : lr;
+      const float l = lr_scale_or_null ? lr * lr_scale_or_null[i0 + e] : lr;
       float gr = G[e] * grad_scale + wd * P[e];
       Mm[e] = beta1 * Mm[e] + (1.f - beta1) * gr;
       V[e] = beta2 * V[e] + (1.f - beta2) * gr * gr;
@@ -397,12 +406,54 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
     *reinterpret_cast<float4*>(v + i0) = make_float4(V[0], V[1], V[2], V[3]);
   } else {
     for (int64_t i = i0; i < n; ++i) {
-      const float l = lr_per_elem_or_null ? lr_per_elem_or_null[i] : lr;
+      const float l = lr_scale_or_null ? lr * lr_scale_or_null[i] : lr;
       float gr = g[i] * grad_scale + wd * p[i];
       m[i] = beta1 * m[i] + (1.f - beta1) * gr;
       v[i] = beta2 * v[i] + (1.f - beta2) * gr * gr;
       const float denom = sqrtf(v[i]) / bc2_sqrt + eps;
       p[i] -= (l / bc1) * (m[i] / denom);
+    }
+  }
+}
+
+// found_inf = 1 when any of g[0..n) is non-finite (the flat gradient after the all-reduce; the trainer appends the
+// loss as one more element), else 0 -- GradScaler.unscale_'s inf check (train.py:490-512) without the host sync.
+// Grid-stride, 128-bit loads; a CTA that sees a non-finite value writes the flag (benign race: all write 1).
+__global__ void __launch_bounds__(256) grad_check_kernel(const float* __restrict__ g, int64_t n,
+                                                        float* __restrict__ found_inf) {
+  bool bad = false;
+  const int64_t nv = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 x = reinterpret_cast<const float4*>(g)[i];
+    // finite <=> x - x == 0
+    bad |= !((x.x - x.x) == 0.f) | !((x.y - x.y) == 0.f) | !((x.z - x.z) == 0.f) | !((x.w - x.w) == 0.f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float x = g[nv * 4 + threadIdx.x];
+    bad |= !((x - x) == 0.f);
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) *found_inf = 1.f;
+}
+
+// One thread: advance the step count unless the step is skipped, and update the loss scale like
+// torch.amp.GradScaler.update (backoff on overflow, growth after `growth_interval` clean steps).
+__global__ void amp_update_kernel(const float* __restrict__ found_inf, int* __restrict__ step,
+                                  float* __restrict__ loss_scale, int* __restrict__ growth_tracker,
+                                  float growth_factor, float backoff_factor, int growth_interval) {
+  const bool inf = *found_inf != 0.f;
+  if (step && !inf) *step += 1;
+  if (loss_scale) {
+    if (inf) {
+      *loss_scale *= backoff_factor;
+      if (growth_tracker) *growth_tracker = 0;
+    } else if (growth_tracker) {
+      const int t = *growth_tracker + 1;
+      if (t == growth_interval) {
+        *loss_scale *= growth_factor;
+        *growth_tracker = 0;
+      } else {
+        *growth_tracker = t;
+      }
     }
   }
 }
@@ -810,9 +861,10 @@ int lgb200_ln_gelu_bwd(const void* dy, const void* x, const float* gamma, const 
   LGB_REQUIRE(false, kErrInvalid, "ln_gelu_bwd: bad dtype %d", dtype);
 }
 
-int lgb200_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_per_elem, float lr,
+int lgb200_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_scale_per_elem, float lr,
                      float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
-                     float grad_scale, cudaStream_t stream) {
+                     float grad_scale, const float* lr_dev, const float* loss_scale_dev, const float* found_inf_dev,
+                     cudaStream_t stream) {
   LGB_REQUIRE(p && g && m && v, kErrInvalid, "adam_flat: null pointer");
   LGB_REQUIRE(n > 0 && (step >= 1 || step_dev), kErrInvalid, "adam_flat: bad n/step");
   LGB_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -821,9 +873,29 @@ int lgb200_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, co
   const float bc1 = step >= 1 ? 1.f - powf(beta1, (float)step) : 1.f;
   const float bc2s = step >= 1 ? sqrtf(1.f - powf(beta2, (float)step)) : 1.f;
   const unsigned grid = (unsigned)(((n + 3) / 4 + 255) / 256);
-  adam_flat_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n, lr_per_elem, lr, beta1, beta2, eps, weight_decay, bc1, bc2s,
-                                             grad_scale, step_dev);
+  AdamDev dev{step_dev, lr_dev, loss_scale_dev, found_inf_dev};
+  adam_flat_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n, lr_scale_per_elem, lr, beta1, beta2, eps, weight_decay, bc1,
+                                             bc2s, grad_scale, dev);
   return check_launch("adam_flat");
+}
+
+int lgb200_flat_grad_check(const float* g, int64_t n, float* found_inf, cudaStream_t stream) {
+  LGB_REQUIRE(g && found_inf && n > 0, kErrInvalid, "flat_grad_check: bad arguments");
+  LGB_REQUIRE(reinterpret_cast<uintptr_t>(g) % 16 == 0, kErrInvalid, "flat_grad_check: g must be 16-byte aligned");
+  cudaError_t e = cudaMemsetAsync(found_inf, 0, sizeof(float), stream);
+  LGB_REQUIRE(e == cudaSuccess, kErrCuda, "flat_grad_check: memset: %s", cudaGetErrorString(e));
+  int64_t blocks = (n / 4 + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < 1 ? 1 : (blocks > 1184 ? 1184 : blocks));
+  grad_check_kernel<<<grid, 256, 0, stream>>>(g, n, found_inf);
+  return check_launch("flat_grad_check");
+}
+
+int lgb200_amp_update(const float* found_inf, int* step_dev, float* loss_scale, int* growth_tracker,
+                      float growth_factor, float backoff_factor, int growth_interval, cudaStream_t stream) {
+  LGB_REQUIRE(found_inf, kErrInvalid, "amp_update: null found_inf");
+  amp_update_kernel<<<1, 1, 0, stream>>>(found_inf, step_dev, loss_scale, growth_tracker, growth_factor,
+                                         backoff_factor, growth_interval);
+  return check_launch("amp_update");
 }
 
 int lgb200_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream) {

@@ -214,17 +214,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, in
     if (rc) return rc;
   }
   auto kern = gemm_bf16_kernel<A_MN, B_MN, OutT>;
-  static bool configured = false;
-  static int num_sms = 0;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
-    LGB_REQUIRE(e == cudaSuccess, kErrCuda, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    LGB_REQUIRE(e == cudaSuccess && num_sms > 0, kErrCuda, "gemm: cannot query the SM count");
-    configured = true;
+  {
+    int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), G_SMEM);
+    if (rc) return rc;
   }
+  const int num_sms = device_sm_count();
   const int tiles_m = (M + GB_M - 1) / GB_M, tiles_n = (N + GB_N - 1) / GB_N;
   const int64_t ntiles = (int64_t)tiles_m * tiles_n * batch;
   LGB_REQUIRE(ntiles < (1ll << 31), kErrUnsupported, "gemm: too many tiles");
@@ -257,22 +251,11 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
-static int num_sms_cached() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
 // split-K plan for a [M,N] = sum_K product: as many splits as idle SMs allow, at least 4 k-blocks each
 static void splitk_plan(int M, int N, int K, int* splits, int* kps) {
   const int tiles = ((M + GB_M - 1) / GB_M) * ((N + GB_N - 1) / GB_N);
   const int nk = (K + GB_K - 1) / GB_K;
-  int s = num_sms_cached() / tiles;
+  int s = device_sm_count() / tiles;
   if (s > nk / 4) s = nk / 4;
   if (s < 1) s = 1;
   *kps = (nk + s - 1) / s;

@@ -17,6 +17,17 @@ __device__ __forceinline__ float sqdist(float2 a, float2 b) {
   return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
 }
 
+// torch.min order on (value, index): a NaN is the minimum (it propagates, first NaN wins), otherwise the smaller
+// value, and the lower index among equals -- so an all-inf / NaN row still yields a valid index (degenerate H).
+__device__ __forceinline__ bool gt_better(float d, int i, float bd, int bi) {
+  const bool dn = d != d, bn = bd != bd;
+  if (dn != bn) return dn;
+  if (!dn && d != bd) return d < bd;
+  return i < bi;
+}
+// running minimum that propagates NaN like torch.min
+__device__ __forceinline__ float gt_min(float a, float b) { return (a != a || b != b) ? NAN : fminf(a, b); }
+
 // rows: min_j dist, argmin_j dist, min_j d0.  columns: the same over this strip's rows, one partial per strip.
 __global__ void __launch_bounds__(256) gt_h_scan_kernel(const float2* __restrict__ kp0, const float2* __restrict__ kp1,
                                                        const float2* __restrict__ kp0_1,
@@ -47,19 +58,22 @@ __global__ void __launch_bounds__(256) gt_h_scan_kernel(const float2* __restrict
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const float d0 = sqdist(a0[t], c1), d1 = sqdist(a1[t], c10);
-        const float d = fmaxf(d0, d1);
-        if (d < bd[t]) { bd[t] = d; bi[t] = j; }  // j ascends per lane: first minimum kept
-        bd0[t] = fminf(bd0[t], d0);
+        const float d = (d0 != d0 || d1 != d1) ? NAN : fmaxf(d0, d1);  // torch.max propagates NaN
+        if (d < bd[t] || (d != d && bd[t] == bd[t])) { bd[t] = d; bi[t] = j; }  // j ascends per lane: first minimum kept
+        bd0[t] = gt_min(bd0[t], d0);
       }
     }
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      if (bi[t] == 0x7fffffff && lane < N) bi[t] = lane;  // every distance of this lane was +inf: its first column
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
 #pragma unroll
       for (int o = 16; o; o >>= 1) {
         const float od = __shfl_xor_sync(0xffffffffu, bd[t], o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi[t], o);
-        if (od < bd[t] || (od == bd[t] && oi < bi[t])) { bd[t] = od; bi[t] = oi; }
-        bd0[t] = fminf(bd0[t], __shfl_xor_sync(0xffffffffu, bd0[t], o));
+        if (gt_better(od, oi, bd[t], bi[t])) { bd[t] = od; bi[t] = oi; }
+        bd0[t] = gt_min(bd0[t], __shfl_xor_sync(0xffffffffu, bd0[t], o));
       }
       const int i = r_base + warp * 8 + t;
       if (lane == 0 && i < M) {
@@ -84,10 +98,11 @@ __global__ void __launch_bounds__(256) gt_h_scan_kernel(const float2* __restrict
     int bi = 0x7fffffff;
     for (int t = 0; t < nrows; ++t) {
       const float d0 = sqdist(s_a0[t], c1), d1 = sqdist(s_a1[t], c10);
-      const float d = fmaxf(d0, d1);
-      if (d < bd) { bd = d; bi = r_base + t; }
-      bd1 = fminf(bd1, d1);
+      const float d = (d0 != d0 || d1 != d1) ? NAN : fmaxf(d0, d1);
+      if (d < bd || (d != d && bd == bd)) { bd = d; bi = r_base + t; }
+      bd1 = gt_min(bd1, d1);
     }
+    if (bi == 0x7fffffff) bi = r_base;  // all +inf: first row of the strip (nrows >= 1)
     const int64_t o = ((int64_t)b * nstrips + strip) * N + j;
     part_dist[o] = bd;
     part_arg[o] = bi;
@@ -108,8 +123,8 @@ __global__ void __launch_bounds__(256) gt_h_colmerge_kernel(const float* __restr
   for (int s = 0; s < nstrips; ++s) {
     const int64_t o = ((int64_t)b * nstrips + s) * N + j;
     const float d = part_dist[o];
-    if (d < bd) { bd = d; bi = part_arg[o]; }
-    bd1 = fminf(bd1, part_d1[o]);
+    if (gt_better(d, part_arg[o], bd, bi)) { bd = d; bi = part_arg[o]; }
+    bd1 = gt_min(bd1, part_d1[o]);
   }
   col_dist[(int64_t)b * N + j] = bd;
   col_arg[(int64_t)b * N + j] = bi;
@@ -130,7 +145,7 @@ __global__ void __launch_bounds__(256) gt_h_label_kernel(const float* __restrict
   if (t < M) {
     const int64_t o = (int64_t)b * M + t;
     const int j = row_arg[o];
-    const bool pos = col_arg[(int64_t)b * N + j] == t && row_dist[o] < pos2;
+    const bool pos = (unsigned)j < (unsigned)N && col_arg[(int64_t)b * N + j] == t && row_dist[o] < pos2;
     int64_t m = pos ? (int64_t)j : -2;
     if (row_d0[o] > neg2) m = -1;
     m0[o] = m;
@@ -139,7 +154,7 @@ __global__ void __launch_bounds__(256) gt_h_label_kernel(const float* __restrict
   if (t < N) {
     const int64_t o = (int64_t)b * N + t;
     const int i = col_arg[o];
-    const bool pos = row_arg[(int64_t)b * M + i] == t && col_dist[o] < pos2;
+    const bool pos = (unsigned)i < (unsigned)M && row_arg[(int64_t)b * M + i] == t && col_dist[o] < pos2;
     int64_t m = pos ? (int64_t)i : -2;
     if (col_d1[o] > neg2) m = -1;
     m1[o] = m;

@@ -12,6 +12,11 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 int make_tmap(CUtensorMap* out, const void* base, bool fp32, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 bool env_flag(const char* name);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel, device), not once
+// per process.  Returns 0 or kErrCuda.
+int ensure_dyn_smem(const void* func, int bytes);
+// SM count of the CURRENT device (cached per device ordinal)
+int device_sm_count();
 
 // fp32 / bf16 CUDA-core attention (attn_simt.cu)
 template <typename T>

@@ -273,6 +273,15 @@ class LightGlue(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def forward(self, data):
+        """lightglue.py:412-543.  The caller may be inside torch.autocast (train.py:468-472 `--mp bfloat16|float16`):
+        the numeric mode here is chosen by conf.precision, not by the ambient autocast state, so the body runs with
+        autocast disabled (fp32 keypoint normalisation / rotary angles / residual stream as in the reference's
+        custom_fwd(cast_inputs=float32) regions, bf16 tensor-core operands inside the kernels) and every input is
+        converted explicitly -- descriptors may arrive in fp16, cf. the `.half()` quirk of lightglue.py:451-453."""
+        with torch.autocast(device_type="cuda", enabled=False):
+            return self._forward(data)
+
+    def _forward(self, data):
         for key in self.required_data_keys:
             assert key in data, f"Missing key {key} in data"
         _lib.load()  # raises unless the CUDA library is built and the device is a B200 (no CPU fallback)
@@ -295,7 +304,7 @@ class LightGlue(nn.Module):
             x = self._lin(x, self.input_proj).float()
         # rotary angles, cached for all layers (lightglue.py:456-458); cos/sin are taken in-kernel
         kp = torch.cat([kpts0.reshape(B * M, 2), kpts1.reshape(B * N, 2)], 0)
-        theta = F.linear(kp, self.posenc.Wr.weight.float()).contiguous()
+        theta = F.linear(kp, self.posenc.Wr.weight.float()).float().contiguous()
         sizes = (B, M, N)
         all0, all1, layers_x = [], [], []
         L = conf.n_layers
@@ -362,8 +371,11 @@ class LightGlue(nn.Module):
                    la[:, :, :-1].max(-2).indices.to(torch.int32).contiguous())
 
         def head(i):
-            la_i = self.log_assignment[i]
-            pre = f"log_assignment.{i}.final_proj."
+            # the last stacked state always belongs to the LAST layer's head (lightglue.py:588 `loss_params(pred, -1)`):
+            # in eval mode only that state is stacked (lightglue.py:485), so L == 1 while the head index is n_layers - 1
+            hi = conf.n_layers - 1 if i == L - 1 else i
+            la_i = self.log_assignment[hi]
+            pre = f"log_assignment.{hi}.final_proj."
             tok = self.token_confidence[i].token[0] if (i < L - 1 and self.training) else None
             return engine.HeadFn.apply(layers_x[i], (B, M, N), self._cdt, gtd, conf.loss.nll_balancing, fin,
                                        self._shadow[pre + "weight"], self._shadow[pre + "bias"],
@@ -405,7 +417,12 @@ class LightGlue(nn.Module):
         return torch.where(dust > val, torch.full_like(arg, width), arg)
 
     def loss(self, pred, data):
-        """lightglue.py:578-627 without materialising any of the per-layer log-assignment matrices."""
+        """lightglue.py:578-627 without materialising any of the per-layer log-assignment matrices.  Like forward, runs
+        with the ambient autocast disabled; its backward is linear in the incoming gradient (GradScaler, train.py:490)."""
+        with torch.autocast(device_type="cuda", enabled=False):
+            return self._loss(pred, data)
+
+    def _loss(self, pred, data):
         conf = self.conf
         ref0, ref1 = pred.get("ref_descriptors0"), pred.get("ref_descriptors1")
         if ref0 is not None:
@@ -415,8 +432,10 @@ class LightGlue(nn.Module):
             (B, M, N), L = pred["_b200_sizes"], len(pred["_b200_layers"])
         gt = data["gt_assignment"]
         gt_u8 = gt.contiguous().view(torch.uint8) if gt.dtype == torch.bool else gt.to(torch.uint8).contiguous()
-        rowcnt = gt.sum(2).float()
-        colcnt = gt.sum(1).float()
+        # counts with an fp32 accumulator inside the reduction (exact below 2^24); `gt.sum(2)` would first upcast the
+        # 4.2 MB/pair boolean mask to int64 (1.1 ms per step at 32 pairs, profiles/r01_roofline_table.md)
+        rowcnt = gt_u8.sum(2, dtype=torch.float32)
+        colcnt = gt_u8.sum(1, dtype=torch.float32)
         neg0 = (data["gt_matches0"] == -1).float()
         neg1 = (data["gt_matches1"] == -1).float()
         num_pos = rowcnt.sum(1).clamp(min=1.0)
@@ -425,7 +444,7 @@ class LightGlue(nn.Module):
 
         def head(i):
             d0, d1 = ref0[:, i], ref1[:, i]
-            md0, md1, z0, z1 = self._head_inputs(d0, d1, i)
+            md0, md1, z0, z1 = self._head_inputs(d0, d1, conf.n_layers - 1 if i == L - 1 else i)  # lightglue.py:588
             ls0, ls1, du0, du1 = F.logsigmoid(z0), F.logsigmoid(z1), F.logsigmoid(-z0), F.logsigmoid(-z1)
             s_pos, rmax, rarg, cmax, carg = ops.AssignPositives.apply(md0, md1, ls0, ls1, du0, du1, gt_u8, rowcnt,
                                                                       colcnt, self._bf16)

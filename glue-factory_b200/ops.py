@@ -442,11 +442,25 @@ def log_optimal_transport(sim, alpha, iters):
     return _log_optimal_transport_fwd(sim, float(alpha), iters)
 
 
-def adam_flat_(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0, lr_per_elem=None,
-               step_dev=None):
-    """In-place Adam on flat fp32 buffers (train.py:358-361, 513).  `step_dev` (int32 device scalar) replaces
-    the host step count when the call is captured in a CUDA graph."""
+def adam_flat_(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0, lr_scale_per_elem=None,
+               step_dev=None, lr_dev=None, loss_scale_dev=None, found_inf_dev=None):
+    """In-place Adam on flat fp32 buffers (train.py:358-361, 513).  The *_dev device scalars replace the host values
+    when the call is captured in a CUDA graph: step count, learning rate, GradScaler scale, skip flag (lgb200.h)."""
     for t in (p, g, m, v):
         _chk(t, torch.float32)
-    call("lgb200_adam_flat", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), ptr(lr_per_elem), float(lr), float(betas[0]),
-         float(betas[1]), float(eps), float(weight_decay), int(step), ptr(step_dev), float(grad_scale), stream_ptr())
+    call("lgb200_adam_flat", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), ptr(lr_scale_per_elem), float(lr),
+         float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), ptr(step_dev), float(grad_scale),
+         ptr(lr_dev), ptr(loss_scale_dev), ptr(found_inf_dev), stream_ptr())
+
+
+def flat_grad_check(g, found_inf):
+    """found_inf[0] <- 1.0 if any element of the flat fp32 buffer g is non-finite else 0.0 (no host sync)."""
+    _chk(g, torch.float32), _chk(found_inf, torch.float32)
+    call("lgb200_flat_grad_check", ptr(g), g.numel(), ptr(found_inf), stream_ptr())
+
+
+def amp_update(found_inf, step_dev=None, loss_scale=None, growth_tracker=None, growth_factor=2.0, backoff_factor=0.5,
+               growth_interval=2000):
+    """Device-side bookkeeping of one optimiser step: step count (unless skipped) + GradScaler.update rule."""
+    call("lgb200_amp_update", ptr(found_inf), ptr(step_dev), ptr(loss_scale), ptr(growth_tracker), float(growth_factor),
+         float(backoff_factor), int(growth_interval), stream_ptr())

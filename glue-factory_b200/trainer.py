@@ -38,7 +38,11 @@ class FlatParams:
             n += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         self.numel = n
         self.flat = torch.zeros(n, device=dev, dtype=dt)
-        self.grad = torch.zeros(n, device=dev, dtype=dt)
+        # one extra aligned slot behind the gradients carries the step's loss through the SAME all-reduce, so that
+        # every rank sees a non-finite loss of any rank and skips the update together (train.py:477-488)
+        self.grad_ext = torch.zeros(n + _ALIGN, device=dev, dtype=dt)
+        self.grad = self.grad_ext[:n]
+        self.loss_slot = self.grad_ext[n:n + 1]
         for p, off in zip(self.params, self.offsets):
             self.flat[off:off + p.numel()].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + p.numel()].view_as(p)
@@ -59,6 +63,23 @@ class FlatParams:
         ops.call("lgb200_cast_bf16", ops.ptr(self.flat), ops.ptr(self.flat16), self.numel, ops.stream_ptr())
         return self._views16
 
+    def lr_scale_per_elem(self, lr_scaling):
+        """The reference's LR groups (train.py:177-196 pack_lr_parameters, :353-361): `lr_scaling` is a list of
+        (factor, [name substrings]); a parameter whose name contains one of the substrings trains at factor x lr
+        (first matching group wins, as the reference's filter loop).  Returns the per-element multiplier vector for
+        lgb200_adam_flat, or None when every factor is 1."""
+        scale = torch.ones(self.numel, device=self.flat.device, dtype=torch.float32)
+        hit = False
+        for p, off in zip(self.params, self.offsets):
+            name = self._names[id(p)]
+            for factor, filters in lr_scaling:
+                if any(f in name for f in filters):
+                    if factor != 1:
+                        scale[off:off + p.numel()] = float(factor)
+                        hit = True
+                    break
+        return scale if hit else None
+
     def zero_grad(self):
         """Detach the .grad views: autograd then hands each freshly computed gradient over by reference
         (no per-parameter accumulate kernel); `gather_grads` packs them into the flat buffer."""
@@ -77,40 +98,98 @@ class FlatParams:
 
 
 class MatcherTrainer:
-    """model: a matcher with forward(data)->pred and loss(pred, data)->(losses, metrics)."""
+    """model: a matcher with forward(data)->pred and loss(pred, data)->(losses, metrics).
 
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None):
+    Every per-step control lives in device memory, so the eager step and the CUDA-graph replay run the SAME
+    sequence with no host synchronisation:
+        loss -> backward -> flat gradients (+ the loss in the extra slot) -> ONE all-reduce
+             -> lgb200_flat_grad_check (any non-finite value on any rank?) -> lgb200_amp_update (step count)
+             -> lgb200_adam_flat (skipped on the device when the check fired: train.py:477-480, 503-512).
+    `loss_scale`: None (default; bf16 needs no loss scaling) or an initial GradScaler scale (train.py:456, 490):
+    the loss is multiplied by the device-resident scale, the gradients are un-scaled inside the Adam kernel and the
+    scale follows torch.amp.GradScaler.update.  `lr_scaling`: the reference's LR groups (train.py:353-361).
+    `ground_truth`: device label generator, so a batch needs only keypoints, descriptors and H."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None,
+                 loss_scale=None, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, lr_scaling=None,
+                 ground_truth=None):
         self.model = model.train()
+        # optional label generator run at the top of every step on the device (two_view_pipeline.py:98-100 runs the
+        # `ground_truth` component inside loss()): a module data -> {matches0, matches1, assignment, ...}, e.g.
+        # gluefactory_b200.matchers.homography_matcher; its outputs are merged into the batch under the `gt_` prefix
+        self.ground_truth = ground_truth
         self.fp = FlatParams(model)
+        dev = self.fp.flat.device
         self.m = torch.zeros_like(self.fp.flat)
         self.v = torch.zeros_like(self.fp.flat)
-        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
-        self.t = 0
+        self.betas, self.eps, self.wd = betas, eps, weight_decay
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self._lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
+        self._t_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._found_inf = torch.zeros(1, device=dev, dtype=torch.float32)
+        self._scale_dev = None if loss_scale is None else torch.full((1,), float(loss_scale), device=dev)
+        self._growth = None if loss_scale is None else torch.zeros(1, device=dev, dtype=torch.int32)
+        self._amp = (growth_factor, backoff_factor, growth_interval)
+        self._lr_scale = self.fp.lr_scale_per_elem(lr_scaling) if lr_scaling else None
+        self._lr_host = float(lr)
+        self.calls = 0  # optimiser-step attempts (skipped steps included)
+
+    # ---- controls (device scalars: changing them never invalidates a captured graph)
+    @property
+    def lr(self):
+        return self._lr_host
+
+    @lr.setter
+    def lr(self, value):
+        """Scheduler hook (train.py `lr_scheduler.step()`): takes effect on the next step, eager or replayed."""
+        self._lr_host = float(value)
+        self._lr_dev.fill_(float(value))
+
+    @property
+    def t(self):
+        """Number of optimiser updates actually applied (reads the device counter: synchronises)."""
+        return int(self._t_dev.item())
+
+    def skipped_last_step(self):
+        return bool(self._found_inf.item() != 0)
+
+    def loss_scale(self):
+        return None if self._scale_dev is None else float(self._scale_dev.item())
 
     def exchange_gradients(self):
-        """The ONE collective of the step: sum-all-reduce of the flat gradient buffer."""
+        """The ONE collective of the step: sum-all-reduce of the flat gradient buffer (+ the loss slot)."""
         if self.world > 1:
-            dist.all_reduce(self.fp.grad, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.fp.grad_ext, op=dist.ReduceOp.SUM, group=self.group)
 
     # ---- CUDA-graph replay of the whole step (removes the ~2500 per-step launch calls from the host)
     def capture(self, example, device, warmup=3):
         """Capture forward + loss + backward + all-reduce + Adam into one CUDA graph.  `example` fixes the
-        shapes; later batches are copied into the captured static input buffers."""
+        shapes; later batches are copied into the captured static input buffers.  The warm-up steps run on the
+        example batch but leave no trace: parameters, Adam moments, step count and loss scale are restored."""
         # private static inputs: to_device() returns device tensors as they are, and step_graphed() overwrites these
         self._static = _clone(to_device(example, device))
+        keep = [t.clone() for t in self._state_tensors()]
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 self._step_impl(self._static)
         torch.cuda.current_stream().wait_stream(side)
-        self._t_dev = torch.full((1,), self.t, device=device, dtype=torch.int32)
+        for t, k in zip(self._state_tensors(), keep):
+            t.copy_(k)
+        self.calls -= warmup
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
-            self._static_loss, self._static_losses = self._step_impl(self._static, graphed=True)
+            self._static_loss, self._static_losses = self._step_impl(self._static)
+        self.calls -= 1  # the capture itself executes nothing
         return self
+
+    def _state_tensors(self):
+        ts = [self.fp.flat, self.m, self.v, self._t_dev]
+        if self._scale_dev is not None:
+            ts += [self._scale_dev, self._growth]
+        return ts
 
     def step_graphed(self, data, prefetch=None):
         """Replay the captured step on a new batch (host or device tensors of the captured shapes).
@@ -139,7 +218,7 @@ class MatcherTrainer:
                 _copy_into(self._staged, prefetch)
                 self._staged_ready.record(self._copy_stream)
             self._staged_src = prefetch
-        self.t += 1
+        self.calls += 1
         return self._static_loss, self._static_losses
 
     def step(self, data, device=None):
@@ -148,24 +227,27 @@ class MatcherTrainer:
             data = to_device(data, device, non_blocking=True)
         return self._step_impl(data)
 
-    def _step_impl(self, data, graphed=False):
+    def _step_impl(self, data):
         self.fp.zero_grad()
+        if self.ground_truth is not None:
+            data = {**data, **{f"gt_{k}": v for k, v in self.ground_truth(data).items()}}
         pred = self.model(data)
         losses, _ = self.model.loss(pred, data)
         loss = losses["total"].mean()
-        loss.backward()
+        (loss if self._scale_dev is None else loss * self._scale_dev[0]).backward()
         self.fp.gather_grads()
+        self.fp.loss_slot.copy_(loss.detach().reshape(1))
         self.exchange_gradients()
-        if graphed:
-            # the bias-correction terms depend on the step count, which must not be baked into the graph:
-            # the count lives in device memory and is incremented inside the graph.
-            self._t_dev.add_(1)
-            ops.adam_flat_(self.fp.flat, self.fp.grad, self.m, self.v, 0, self.lr, self.betas, self.eps, self.wd,
-                           grad_scale=1.0 / self.world, step_dev=self._t_dev)
-        else:
-            self.t += 1
-            ops.adam_flat_(self.fp.flat, self.fp.grad, self.m, self.v, self.t, self.lr, self.betas, self.eps, self.wd,
-                           grad_scale=1.0 / self.world)
+        # non-finite loss or gradient on ANY rank -> every rank skips this update (and backs the loss scale off)
+        ops.flat_grad_check(self.fp.grad_ext[:self.fp.numel + 4], self._found_inf)
+        ops.amp_update(self._found_inf, step_dev=self._t_dev)  # ++step unless skipped (Adam's bias correction reads it)
+        ops.adam_flat_(self.fp.flat, self.fp.grad, self.m, self.v, 0, self._lr_host, self.betas, self.eps, self.wd,
+                       grad_scale=1.0 / self.world, lr_scale_per_elem=self._lr_scale, step_dev=self._t_dev,
+                       lr_dev=self._lr_dev, loss_scale_dev=self._scale_dev, found_inf_dev=self._found_inf)
+        if self._scale_dev is not None:  # GradScaler.update AFTER the step: the gradients carry the old scale
+            g, b, i = self._amp
+            ops.amp_update(self._found_inf, None, self._scale_dev, self._growth, g, b, i)
+        self.calls += 1
         return loss.detach(), losses
 
 

@@ -34,7 +34,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define LGB200_ABI_VERSION 1
+#define LGB200_ABI_VERSION 2
 
 #define LGB200_F32 0
 #define LGB200_BF16 1
@@ -185,11 +185,24 @@ int lgb200_colsum(const void* a, float* out, float* ws, unsigned* counters, int6
                   cudaStream_t stream);
 
 /* ---- flat-buffer optimiser (train.py:358-361, 513) and casts --------------------------------------- */
-/* step: 1-based step count for the bias correction; when step_dev != NULL the count is read from device
- * memory instead (so a CUDA graph of the whole training step can be replayed).                       */
-int lgb200_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_per_elem, float lr,
+/* Adam over the flat buffers, one launch.  g is multiplied by grad_scale (1/world for the summed all-reduce).
+ * step: 1-based step count for the bias correction; the four *_dev pointers (each may be NULL) move the per-step
+ * controls into device memory so that ONE captured CUDA graph of the whole training step stays valid while they
+ * change:  step_dev (count), lr_dev (scheduler, train.py:347-367), loss_scale_dev (GradScaler scale: gradients are
+ * additionally multiplied by 1 / *loss_scale_dev, train.py:490), found_inf_dev (!= 0: the update is skipped --
+ * GradScaler.step on overflow and the NaN guard of train.py:477-480, 503-512).
+ * lr_scale_per_elem (may be NULL): per-element LR multiplier = the reference's lr_scaling groups (train.py:353-361). */
+int lgb200_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_scale_per_elem, float lr,
                      float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
-                     float grad_scale, cudaStream_t stream);
+                     float grad_scale, const float* lr_dev, const float* loss_scale_dev, const float* found_inf_dev,
+                     cudaStream_t stream);
+/* found_inf[0] = 1.0f if any of g[0..n) is non-finite, else 0.0f (GradScaler.unscale_'s check, no host sync). */
+int lgb200_flat_grad_check(const float* g, int64_t n, float* found_inf, cudaStream_t stream);
+/* One step of bookkeeping on the device: ++*step_dev unless *found_inf, and the GradScaler.update rule on
+ * *loss_scale / *growth_tracker (both may be NULL): x backoff_factor on overflow, x growth_factor after
+ * growth_interval consecutive clean steps. */
+int lgb200_amp_update(const float* found_inf, int* step_dev, float* loss_scale, int* growth_tracker,
+                      float growth_factor, float backoff_factor, int growth_interval, cudaStream_t stream);
 int lgb200_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream);
 /* residual update of the fp32 stream fused with the cast for the next GEMM (lightglue.py:163, 219-220):
  * x_out = x + y (y in `dtype`, may be NULL), x_cast = (dtype) x_out; either output may be NULL.   */

@@ -38,6 +38,62 @@ def bf16_round(x):
     return x.to(torch.bfloat16).to(x.dtype)
 
 
+class _RoundBoth(torch.autograd.Function):
+    """bf16 round trip in forward AND of the incoming gradient in backward: models a tensor that the CUDA path
+    stores in bf16 and whose gradient it also produces in bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return bf16_round(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return bf16_round(g)
+
+
+class _RoundGrad(torch.autograd.Function):
+    """identity in forward, bf16 round trip of the gradient in backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return bf16_round(g)
+
+
+class Bf16Mirror:
+    """Rounding model of the CUDA `precision: bf16` path (glue-factory_b200/engine.py), for tight parity tests of
+    the tensor-core kernels at sizes where comparing with fp64 only measures bf16 noise.  Passed as `rnd=`:
+
+      operand(x): GEMM / attention operand taken from an fp32 tensor (the residual stream, weights) -- rounded in
+                  forward, gradient left in fp32 (the CUDA path accumulates the residual-stream gradient in fp32);
+      store(x):   a tensor the CUDA path keeps in bf16 (every Linear output, rotated q / k, attention output,
+                  LayerNorm+GELU output) -- rounded in forward and its gradient rounded in backward;
+      bias(b):    Linear biases are read from the bf16 weight shadow;
+      grad(x):    fp32 in forward, gradient produced in bf16 (the similarity matrix: dsim is bf16).
+
+    Not mirrored (second-order): P is rounded after normalisation here and before it in the kernels; the shared
+    to_qk gradient is rounded per direction before the sum in the CUDA path; final_proj's input gradient."""
+
+    def __call__(self, x):  # plain operand rounding, so the object can be passed wherever `rnd` is a callable
+        return bf16_round(x)
+
+    operand = staticmethod(bf16_round)
+    bias = staticmethod(bf16_round)
+    store = staticmethod(_RoundBoth.apply)
+    grad = staticmethod(_RoundGrad.apply)
+
+
+def _hook(rnd, name):
+    """`rnd` is either a plain callable (operand rounding only; the round-1 hook) or a Bf16Mirror-like object."""
+    f = getattr(rnd, name, None)
+    if f is not None:
+        return f
+    return rnd if name == "operand" else _id
+
+
 # ----------------------------------------------------------------------------
 # positional encoding / rotary
 # ----------------------------------------------------------------------------
@@ -72,7 +128,8 @@ def rope(t, theta):
 # transformer blocks
 # ----------------------------------------------------------------------------
 def _linear(x, w, name, rnd=_id):
-    return rnd(x) @ rnd(w[name + ".weight"]).t() + w[name + ".bias"]
+    op = _hook(rnd, "operand")
+    return _hook(rnd, "store")(op(x) @ op(w[name + ".weight"]).t() + _hook(rnd, "bias")(w[name + ".bias"]))
 
 
 def _ffn(x, msg, w, pre, rnd=_id):
@@ -80,15 +137,16 @@ def _ffn(x, msg, w, pre, rnd=_id):
     (lightglue.py:143-148, 178-183)."""
     h = _linear(torch.cat([x, msg], -1), w, pre + ".ffn.0", rnd)
     h = F.layer_norm(h, h.shape[-1:], w[pre + ".ffn.1.weight"], w[pre + ".ffn.1.bias"], 1e-5)
-    h = F.gelu(h)
+    h = _hook(rnd, "store")(F.gelu(h))
     return _linear(h, w, pre + ".ffn.3", rnd)
 
 
 def _attend(q, k, v, scale, rnd=_id):
     """softmax(q k^T * scale) v  over [B,H,N,dh]  (lightglue.py:118-121, 207-216)."""
-    s = (rnd(q) @ rnd(k).transpose(-1, -2)) * scale
+    op = _hook(rnd, "operand")
+    s = (op(q) @ op(k).transpose(-1, -2)) * scale
     p = torch.softmax(s, -1)
-    return rnd(p) @ rnd(v)
+    return _hook(rnd, "store")(op(p) @ op(v))
 
 
 def self_block(x, theta, w, pre, H, rnd=_id):
@@ -97,7 +155,8 @@ def self_block(x, theta, w, pre, H, rnd=_id):
     dh = D // H
     qkv = _linear(x, w, pre + ".Wqkv", rnd).view(B, N, H, dh, 3).permute(0, 2, 1, 3, 4)
     q, k, v = qkv[..., 0], qkv[..., 1], qkv[..., 2]
-    q, k = rope(q, theta), rope(k, theta)
+    st = _hook(rnd, "store")
+    q, k = st(rope(q, theta)), st(rope(k, theta))
     ctx = _attend(q, k, v, dh**-0.5, rnd)
     msg = _linear(ctx.transpose(1, 2).reshape(B, N, D), w, pre + ".out_proj", rnd)
     return x + _ffn(x, msg, w, pre, rnd)
@@ -149,7 +208,8 @@ def match_assignment(d0, d1, w, i, rnd=_id):
     D = d0.shape[-1]
     md0 = _linear(d0, w, pre + ".final_proj", rnd) / D**0.25
     md1 = _linear(d1, w, pre + ".final_proj", rnd) / D**0.25
-    sim = rnd(md0) @ rnd(md1).transpose(1, 2)
+    op = _hook(rnd, "operand")
+    sim = _hook(rnd, "grad")(op(md0) @ op(md1).transpose(1, 2))
     z0 = (d0 @ w[pre + ".matchability.weight"].t() + w[pre + ".matchability.bias"]).squeeze(-1)
     z1 = (d1 @ w[pre + ".matchability.weight"].t() + w[pre + ".matchability.bias"]).squeeze(-1)
     return sigmoid_log_double_softmax(sim, z0, z1), sim

@@ -95,6 +95,70 @@ def run_case(name, conf, B, N, M, seed, dtype=torch.float64, sub=1):
           f"({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+def _err_stats(prefix, got, ref):
+    """rel. L2 error of `got` against the fp64 reference tensor `ref` (whole tensor)."""
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    return {prefix: np.array(((got - ref).norm() / ref.norm().clamp(min=1e-300)).item())}
+
+
+def run_case_autocast(name, conf, B, N, M, seed):
+    """How far does the UNMODIFIED reference itself move when it is run the way `train.py --mp bfloat16`
+    runs it (train.py:468-472: fp32 module under torch.autocast(dtype=bfloat16))?  Both the fp64 run and the
+    autocast run are the reference module on identical weights / inputs; the fixture stores, per output, per loss
+    entry and per parameter gradient, the error of the autocast run against the fp64 run, measured exactly as
+    tests/test_gpu_parity_bf16.py measures the CUDA bf16 path against the fp64 golden of the same case:
+        whole-tensor rel. L2 for log_assignment / losses / small gradients,
+        rel. L2 over the 512 probe entries (and the probe projection) for big gradient matrices.
+    The CUDA bf16 path (bf16 operands, fp32 accumulate, fp32 residual stream) is required to be at least this
+    close to fp64 -- the 'same autocast dtype' contract of SURVEY.md section 7, hard part 1(b)."""
+    weights = synthetic.make_weights(conf, seed=seed)
+    out = {"meta|B": np.array(B), "meta|N": np.array(N), "meta|M": np.array(M), "meta|seed": np.array(seed),
+           "meta|conf": np.array(repr(conf)), "meta|autocast": np.array("cpu/bfloat16")}
+    runs = {}
+    for tag, dtype in (("f64", torch.float64), ("ac", torch.float32)):
+        data = synthetic.make_pairs(B, N, seed=seed + 1, D=conf["input_dim"], M=M, dtype=dtype)
+        model = build_reference(conf, weights, dtype)
+        if tag == "ac":
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                pred = model(data)
+                losses, _ = model.loss(pred, data)
+                loss = losses["total"].mean()
+        else:
+            pred = model(data)
+            losses, _ = model.loss(pred, data)
+            loss = losses["total"].mean()
+        loss.backward()
+        runs[tag] = (pred, losses, {k: p.grad.detach().double() for k, p in model.named_parameters()})
+    (p64, l64, g64), (pac, lac, gac) = runs["f64"], runs["ac"]
+    la64, laac = p64["log_assignment"].detach().double(), pac["log_assignment"].detach().double()
+    out.update(_err_stats("err|log_assignment", laac, la64))
+    out["err|log_assignment_maxabs"] = np.array((laac - la64).abs().max().item())
+    inner64, innerac = la64[:, :-1, :-1], laac[:, :-1, :-1]
+    top2 = inner64.topk(2, dim=2).values
+    margin = top2[..., 0] - top2[..., 1]
+    agree = innerac.max(2).indices == inner64.max(2).indices
+    out["idx|row_agree_frac"] = np.array(agree.double().mean().item())
+    # smallest margin above which the autocast reference keeps every row argmax
+    out["idx|row_safe_margin"] = np.array(margin[~agree].max().item() if (~agree).any() else 0.0)
+    out["idx|matches0_agree_frac"] = np.array((pac["matches0"] == p64["matches0"]).double().mean().item())
+    for k in ["total", "last", "assignment_nll", "nll_pos", "nll_neg", "confidence", "row_norm"]:
+        out.update(_err_stats("err|loss|" + k, lac[k], l64[k]))
+    for k in g64:
+        a, r = gac[k], g64[k]
+        if r.numel() <= 4096:
+            out.update(_err_stats("err|grad|" + k, a, r))
+        else:
+            idx = probe_index(r.numel())
+            out.update(_err_stats("err|grad|" + k, a.reshape(-1)[idx], r.reshape(-1)[idx]))
+        out["err|gradnorm|" + k] = np.array(abs(a.norm().item() - r.norm().item()) / max(r.norm().item(), 1e-300))
+    path = os.path.join(OUT, "ac_" + name + ".npz")
+    np.savez_compressed(path, **out)
+    worst = max(float(v) for k_, v in out.items() if k_.startswith("err|grad|"))
+    print(f"ac_{name}: log_assignment rel {float(out['err|log_assignment']):.3e} (max abs "
+          f"{float(out['err|log_assignment_maxabs']):.3e}), loss rel {float(out['err|loss|total']):.3e}, worst grad rel "
+          f"{worst:.3e}, row argmax agreement {float(out['idx|row_agree_frac']):.4f} -> {path}")
+
+
 def run_heads():
     """Golden vectors for the two other assignment heads on the path."""
     from gluefactory.models.matchers.gluestick import log_double_softmax
@@ -195,13 +259,44 @@ def run_gt_homography():
     print("gt_homography ->", path)
 
 
+def run_eval_loss():
+    """Validation-mode loss of the reference (train.py:92-93 do_evaluation: model.eval(), loss on the last layer only,
+    lightglue.py:485 keeps one stacked layer and :588 uses log_assignment[-1]) + the matcher metrics."""
+    conf = dict(synthetic.DEFAULT_CONF, n_layers=3, filter_threshold=0.1)
+    B, N, seed = 2, 160, 13
+    weights = synthetic.make_weights(conf, seed=seed)
+    data = synthetic.make_pairs(B, N, seed=seed + 1, D=conf["input_dim"], dtype=torch.float64)
+    model = build_reference(conf, weights, torch.float64).eval()
+    with torch.no_grad():
+        pred = model(data)
+        losses, metrics = model.loss(pred, data)
+    out = {"meta|conf": np.array(repr(conf)), "meta|B": np.array(B), "meta|N": np.array(N), "meta|M": np.array(N),
+           "meta|seed": np.array(seed)}
+    for k, v in losses.items():
+        out["loss|" + k] = v.detach().cpu().numpy() if torch.is_tensor(v) else np.array(v)
+    for k, v in metrics.items():
+        out["metric|" + k] = v.detach().cpu().numpy()
+    path = os.path.join(OUT, "eval_loss.npz")
+    np.savez_compressed(path, **out)
+    print("eval_loss ->", path, {k: v for k, v in out.items() if k.startswith("loss|total")})
+
+
+def run_autocast_cases():
+    torch.manual_seed(0)
+    mid = dict(synthetic.DEFAULT_CONF, n_layers=3, filter_threshold=0.1)
+    run_case_autocast("lg_d256_l3_n160", mid, B=2, N=160, M=160, seed=13)
+    disk = dict(synthetic.DEFAULT_CONF, n_layers=2, input_dim=128)
+    run_case_autocast("lg_disk_d256_l2_n128", disk, B=1, N=128, M=128, seed=14)
+    run_case_autocast("lg_full_l9_n512", dict(synthetic.DEFAULT_CONF), B=1, N=512, M=512, seed=15)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     only = [a for a in sys.argv[1:] if not a.startswith("-")]  # single fixtures: gluestick_attn, gt_homography, heads_grad
     if only:
         for name in only:
             {"gluestick_attn": run_gluestick_attention, "gt_homography": run_gt_homography,
-             "heads_grad": run_heads_grad}[name]()
+             "heads_grad": run_heads_grad, "autocast": run_autocast_cases, "eval_loss": run_eval_loss}[name]()
         sys.exit(0)
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -218,3 +313,5 @@ if __name__ == "__main__":
     run_heads_grad()
     run_gluestick_attention()
     run_gt_homography()
+    run_autocast_cases()
+    run_eval_loss()

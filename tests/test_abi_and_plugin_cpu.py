@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(built):
     lib = _lib.load(check_device=False)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.lgb200_abi_version() == 1
+    assert lib.lgb200_abi_version() == 2
     # pure host queries are callable without a GPU
     assert lib.lgb200_assign_ws_bytes(2, 64, 64) == 2 * 2 * 64 * 8
     assert lib.lgb200_ln_gelu_bwd_parts(1000) == 125

@@ -272,6 +272,24 @@ def test_gt_from_homography_matches_restatement_at_size(B, M, N):
     assert "assignment" not in sparse and torch.equal(sparse["matches0"], m0)
 
 
+def test_gt_from_homography_degenerate_rows():
+    """Rows / columns whose distances are all +inf or NaN (overflowing or NaN keypoints, a point on the homography's
+    line at infinity) must behave like torch's min (valid first index, NaN propagates), never index out of bounds."""
+    from gluefactory_b200 import synthetic
+
+    d = synthetic.to_device(synthetic.make_pairs(2, 300, seed=91, M=260, with_gt=False), DEV)
+    kp0, kp1, H = d["keypoints0"].clone(), d["keypoints1"].clone(), d["H_0to1"]
+    kp0[0, 7] = 3e30                      # squared distances overflow to +inf for the whole row
+    kp1[0, 11] = float("nan")             # a NaN column
+    kp1[1, 5] = float("inf")
+    kp0[1, 0] = float("nan")
+    asg, m0, m1 = synthetic.gt_matches_from_homography(kp0, kp1, H, 3.0, 3.0)
+    r = ops.gt_matches_from_homography(kp0, kp1, H, 3.0, 3.0)
+    torch.cuda.synchronize()
+    assert torch.equal(r["matches0"], m0) and torch.equal(r["matches1"], m1)
+    assert torch.equal(r["assignment"], asg)
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
 def test_gluestick_attention_matches_golden(dtype, tol):
     """GlueStick's channels-first attention core (gluestick.py:524-529), forward and gradients,

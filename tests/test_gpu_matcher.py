@@ -133,6 +133,31 @@ def test_training_reduces_loss_and_eval_metrics():
     assert "confidence" not in losses
 
 
+@pytest.mark.parametrize("engine", ["fused", "autograd"])
+def test_eval_mode_loss_uses_last_head(engine):
+    """Validation loss (train.py:92-93): in eval mode only the last layer's state is stacked (lightglue.py:485) and
+    the loss must still apply the LAST assignment head (lightglue.py:588), not head 0.  Golden = the reference in
+    eval mode (tests/golden/eval_loss.npz)."""
+    import ast
+    import os
+
+    from tests.util import GOLDEN
+
+    g = dict(np.load(os.path.join(GOLDEN, "eval_loss.npz")))
+    conf = ast.literal_eval(str(g["meta|conf"]))
+    B, N, seed = int(g["meta|B"]), int(g["meta|N"]), int(g["meta|seed"])
+    model = _build(conf, synthetic.make_weights(conf, seed=seed), "fp32", engine).eval()
+    d = _f32(synthetic.make_pairs(B, N, seed=seed + 1, dtype=torch.float64))
+    with torch.no_grad():
+        pred = model(d)
+        losses, metrics = model.loss(pred, d)
+    for k in ["total", "last", "assignment_nll", "nll_pos", "nll_neg", "num_matchable", "num_unmatchable", "row_norm"]:
+        np.testing.assert_allclose(losses[k].cpu().numpy(), g["loss|" + k], rtol=1e-3, err_msg=k)
+    assert "confidence" not in losses
+    for k in ["match_recall", "match_precision", "accuracy", "average_precision"]:
+        np.testing.assert_allclose(metrics[k].cpu().numpy(), g["metric|" + k], rtol=1e-3, atol=1e-6, err_msg=k)
+
+
 def test_nan_propagates_to_loss():
     """train.py:477-480 skips the step on a NaN loss; the kernels must not trap or hide it."""
     conf = dict(synthetic.DEFAULT_CONF, n_layers=1)
