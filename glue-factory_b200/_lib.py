@@ -32,10 +32,14 @@ SIGNATURES = {
     "lgb200_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i, _f, _vp]),
     "lgb200_gemm_splitk_ws_floats": (_i64, [_i, _i, _i]),
     "lgb200_gemm_bf16_splitk": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _vp]),
+    "lgb200_linear": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i, _f, _i, _vp]),
     "lgb200_assign_ws_bytes": (_sz, [_i, _i, _i]),
     "lgb200_assign_lse": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_assign_scores": (_i, [_vp] * 16 + [_i, _i, _i, _vp]),
     "lgb200_assign_bwd": (_i, [_vp] * 8 + [_i, _i, _i, _i, _vp]),
+    "lgb200_assign_fused_lse": (_i, [_vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "lgb200_assign_fused_stats": (_i, [_vp, _vp, _f] + [_vp] * 10 + [_i, _i, _i, _i, _vp]),
+    "lgb200_assign_fused_bwd": (_i, [_vp, _vp, _f] + [_vp] * 9 + [_i, _i, _i, _i, _vp]),
     "lgb200_filter_matches": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_head_logsig": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "lgb200_head_token_bwd_ws_floats": (_i, [_i]),

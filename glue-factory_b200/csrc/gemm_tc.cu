@@ -19,19 +19,23 @@ namespace lgb {
 constexpr int GB_M = 128, GB_N = 128, GB_K = 64, G_STAGES = 4;
 constexpr int G_TILE = GB_M * GB_K * 2;  // 16 KiB per operand per stage
 constexpr int G_EPI = 4 * 2 * 4096;      // per-warp staging: two 32-row x 128-byte blocks
-constexpr int G_SMEM = G_STAGES * 2 * G_TILE + G_EPI + 256;
+constexpr int G_BIAS = 4 * GB_N * 4;     // per-warp copy of the tile's 128 bias values
+constexpr int G_SMEM = G_STAGES * 2 * G_TILE + G_EPI + G_BIAS + 256;
 
 template <bool A_MN, bool B_MN, typename OutT>
 __global__ void __launch_bounds__(192, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, OutT* __restrict__ C, int M, int N, int K, int64_t ldc,
                      int64_t strideC, float alpha, int tiles_m, int tiles_n, int ntiles, int use_tma_store,
-                     int kps /* split-K: k-blocks per split (0 = off); the tile's batch index is then the split */) {
+                     int kps /* split-K: k-blocks per split (0 = off); the tile's batch index is then the split */,
+                     const float* __restrict__ bias /* [N] added to every row, or null */,
+                     int reduce_add /* fp32 C only: C += alpha A B (+ bias) through TMA reduce-add */) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + G_STAGES * G_TILE;
   float* sE = reinterpret_cast<float*>(smem + 2 * G_STAGES * G_TILE);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * G_STAGES * G_TILE + G_EPI);
+  float* sBias = reinterpret_cast<float*>(smem + 2 * G_STAGES * G_TILE + G_EPI);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * G_STAGES * G_TILE + G_EPI + G_BIAS);
   uint64_t* empty = full + G_STAGES;
   uint64_t* acc_full = empty + G_STAGES;  // [2]
   uint64_t* acc_empty = acc_full + 2;     // [2]
@@ -132,6 +136,22 @@ __global__ void __launch_bounds__(192, 1)
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
       const int n0 = (t % tiles_n) * GB_N, m0 = ((t / tiles_n) % tiles_m) * GB_M, b = t / (tiles_n * tiles_m);
       const int acc = lt & 1;
+      float* sb = sBias + warp * GB_N;
+      if (bias) {  // this warp's copy of the tile's bias slice (lane l holds columns 4l .. 4l+3)
+        __syncwarp();
+        const int col = n0 + lane * 4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col + 3 < N && (reinterpret_cast<uintptr_t>(bias + col) & 15) == 0) {
+          bv = *reinterpret_cast<const float4*>(bias + col);
+        } else {
+          if (col < N) bv.x = bias[col];
+          if (col + 1 < N) bv.y = bias[col + 1];
+          if (col + 2 < N) bv.z = bias[col + 2];
+          if (col + 3 < N) bv.w = bias[col + 3];
+        }
+        *reinterpret_cast<float4*>(sb + lane * 4) = bv;
+        __syncwarp();
+      }
       mbar_wait(&acc_full[acc], (lt >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -151,17 +171,28 @@ __global__ void __launch_bounds__(192, 1)
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
+        if (bias) {
+#pragma unroll
+          for (int q4 = 0; q4 < CW / 4; ++q4) {
+            const float4 bq = *reinterpret_cast<const float4*>(sb + c * CW + q4 * 4);  // same address in every lane
+            v[4 * q4] = fmaf(v[4 * q4], alpha, bq.x); v[4 * q4 + 1] = fmaf(v[4 * q4 + 1], alpha, bq.y);
+            v[4 * q4 + 2] = fmaf(v[4 * q4 + 2], alpha, bq.z); v[4 * q4 + 3] = fmaf(v[4 * q4 + 3], alpha, bq.w);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) v[i] *= alpha;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {  // 16-byte chunk j of this thread's row, XOR-swizzled by the row (== SWIZZLE_128B)
           uint4 u;
           if constexpr (sizeof(OutT) == 4) {
-            u.x = __float_as_uint(v[4 * j] * alpha); u.y = __float_as_uint(v[4 * j + 1] * alpha);
-            u.z = __float_as_uint(v[4 * j + 2] * alpha); u.w = __float_as_uint(v[4 * j + 3] * alpha);
+            u.x = __float_as_uint(v[4 * j]); u.y = __float_as_uint(v[4 * j + 1]);
+            u.z = __float_as_uint(v[4 * j + 2]); u.w = __float_as_uint(v[4 * j + 3]);
           } else {
-            u.x = pack_bf16(v[8 * j] * alpha, v[8 * j + 1] * alpha);
-            u.y = pack_bf16(v[8 * j + 2] * alpha, v[8 * j + 3] * alpha);
-            u.z = pack_bf16(v[8 * j + 4] * alpha, v[8 * j + 5] * alpha);
-            u.w = pack_bf16(v[8 * j + 6] * alpha, v[8 * j + 7] * alpha);
+            u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+            u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+            u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+            u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
           }
           *reinterpret_cast<uint4*>(blk + lane * 128 + ((j ^ (lane & 7)) << 4)) = u;
         }
@@ -169,7 +200,8 @@ __global__ void __launch_bounds__(192, 1)
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tmC, blk, n0 + c * CW, m0 + warp * 32, b);
+            if (reduce_add) tma_reduce_add_3d(&tmC, blk, n0 + c * CW, m0 + warp * 32, b);
+            else tma_store_3d(&tmC, blk, n0 + c * CW, m0 + warp * 32, b);
             tma_store_commit();
           }
         } else {
@@ -200,7 +232,8 @@ __global__ void __launch_bounds__(192, 1)
 
 template <bool A_MN, bool B_MN, typename OutT>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int batch, int M, int N, int K,
-                       int64_t ldc, int64_t strideC, float alpha, cudaStream_t stream, int kps = 0) {
+                       int64_t ldc, int64_t strideC, float alpha, cudaStream_t stream, int kps = 0,
+                       const float* bias = nullptr, int reduce_add = 0) {
   constexpr int ES = (int)sizeof(OutT);
   CUtensorMap tc;
   memset(&tc, 0, sizeof(tc));
@@ -213,6 +246,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, in
     int rc = make_tmap(&tc, C, ES == 4, 3, dims, str, box);
     if (rc) return rc;
   }
+  LGB_REQUIRE(!reduce_add || (tma_ok && ES == 4), kErrInvalid,
+              "gemm: accumulate-into-C needs an fp32 C with 16-byte aligned base / row pitch");
   auto kern = gemm_bf16_kernel<A_MN, B_MN, OutT>;
   {
     int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), G_SMEM);
@@ -224,7 +259,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, in
   LGB_REQUIRE(ntiles < (1ll << 31), kErrUnsupported, "gemm: too many tiles");
   const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);
   kern<<<grid, 192, G_SMEM, stream>>>(ta, tb, tc, static_cast<OutT*>(C), M, N, K, ldc, strideC, alpha, tiles_m, tiles_n,
-                                      (int)ntiles, tma_ok ? 1 : 0, kps);
+                                      (int)ntiles, tma_ok ? 1 : 0, kps, bias, reduce_add);
   return check_launch("gemm_bf16");
 }
 
@@ -344,4 +379,31 @@ extern "C" int lgb200_gemm_bf16(const void* A, const void* B, void* C, int batch
   LGB_GEMM_CASE(1, 1)
 #undef LGB_GEMM_CASE
   LGB_REQUIRE(false, kErrInvalid, "gemm_bf16: bad major/dtype flags");
+}
+
+// y = alpha * op(A) op(B)^T + bias (+ C when beta != 0): the nn.Linear-shaped projections of the layer
+// (lightglue.py:139-148, 156-163, 174-183, 195-221, 280) and their input-gradient GEMMs, single problem (no batch).
+extern "C" int lgb200_linear(const void* A, const void* B, void* C, const float* bias, int M, int N, int K,
+                             int a_mn_major, int b_mn_major, int64_t lda, int64_t ldb, int64_t ldc, int c_dtype,
+                             float alpha, int accumulate, cudaStream_t stream) {
+  LGB_REQUIRE(A && B && C, kErrInvalid, "linear: null pointer");
+  LGB_REQUIRE(M > 0 && N > 0 && K > 0, kErrInvalid, "linear: empty problem %dx%dx%d", M, N, K);
+  LGB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, kErrInvalid, "linear: lda/ldb must be multiples of 8 elements");
+  LGB_REQUIRE(!accumulate || c_dtype == LGB200_F32, kErrInvalid, "linear: accumulate needs an fp32 C");
+  CUtensorMap ta, tb;
+  int rc = make_ab_maps(&ta, &tb, A, B, 1, M, N, K, a_mn_major, b_mn_major, lda, ldb, 0, 0);
+  if (rc) return rc;
+#define LGB_LIN_CASE(AM, BMJ)                                                                                       \
+  if (a_mn_major == AM && b_mn_major == BMJ) {                                                                      \
+    if (c_dtype == LGB200_F32)                                                                                      \
+      return launch_gemm<AM, BMJ, float>(ta, tb, C, 1, M, N, K, ldc, 0, alpha, stream, 0, bias, accumulate ? 1 : 0); \
+    if (c_dtype == LGB200_BF16)                                                                                     \
+      return launch_gemm<AM, BMJ, __nv_bfloat16>(ta, tb, C, 1, M, N, K, ldc, 0, alpha, stream, 0, bias, 0);       \
+  }
+  LGB_LIN_CASE(0, 0)
+  LGB_LIN_CASE(0, 1)
+  LGB_LIN_CASE(1, 0)
+  LGB_LIN_CASE(1, 1)
+#undef LGB_LIN_CASE
+  LGB_REQUIRE(false, kErrInvalid, "linear: bad major/dtype flags");
 }

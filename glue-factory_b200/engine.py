@@ -12,34 +12,41 @@ shadow refreshed once per step, weight gradients are produced in fp32 directly b
 (`out_dtype`), the residual update emits the next GEMM's operand in the same pass, and nothing
 N x N is ever kept besides `sim`.
 
-All dense projections are plain cuBLAS GEMMs (`torch.mm/addmm`); everything else is an lgb200 kernel.
+In `precision: bf16` every GEMM of the layer and of the head -- the nine nn.Linear projections, their input-gradient
+and weight-gradient contractions -- runs on the library's own persistent tcgen05 GEMM (`ops.linear`: bias and
+fp32 accumulate-into-dx epilogues; `ops.wgrad_bf16`: split-K, fp32 out); no cuBLAS kernel is launched.  The fp32
+parity mode keeps fp32 cuBLAS (`torch.addmm/mm`) for the projections.
 """
 import torch
 import torch.nn.functional as F
 
 from . import ops
 
-_OUT_DTYPE_OK = True
-_ADDMM_DTYPE_OK = True
 _head_counters = {}
+# fused GEMM + assignment kernels (csrc/assign_tc.cu) for bf16 descriptors; False = the round-1 path (sim written to HBM)
+FUSED_ASSIGN = True
+
+
+def _lin(x, W, b, out=None):
+    """y = x W^T + b.  bf16: own tcgen05 GEMM with the fp32 bias added in the epilogue (W = bf16 shadow, b = the fp32
+    parameter); fp32 parity mode: cuBLAS."""
+    if x.dtype == torch.bfloat16:
+        return ops.linear(x, W, b, out=out)
+    return torch.addmm(b, x, W.t()) if out is None else torch.addmm(b, x, W.t(), out=out)
+
+
+def _dgrad(dy, W):
+    """dx = dy W (compute dtype)."""
+    if dy.dtype == torch.bfloat16:
+        return ops.linear(dy, W, w_is_kn=True)
+    return torch.mm(dy, W)
 
 
 def _wgrad(dy, a):
-    """dW [out, in] fp32 = dy^T a for compute-dtype dy [T, out], a [T, in]."""
-    global _OUT_DTYPE_OK
+    """dW [out, in] fp32 = dy^T a for compute-dtype dy [T, out], a [T, in] (row-strided views allowed)."""
     if dy.dtype == torch.float32:
         return torch.mm(dy.t(), a)
-    # the split-K tcgen05 GEMM beats cuBLAS only while one 128x128 tile grid leaves most SMs to the K splits
-    # (256x256: 38 vs 46 us at T = 131072; wider outputs re-read the operands through L2 and tie at ~50 us)
-    if (dy.dtype == torch.bfloat16 and dy.shape[1] * a.shape[1] <= 256 * 256 and dy.stride(1) == 1 and a.stride(1) == 1
-            and dy.stride(0) % 8 == 0 and a.stride(0) % 8 == 0 and dy.data_ptr() % 16 == 0 and a.data_ptr() % 16 == 0):
-        return ops.wgrad_bf16(dy, a)
-    if _OUT_DTYPE_OK:
-        try:
-            return torch.mm(dy.t(), a, out_dtype=torch.float32)
-        except (TypeError, RuntimeError):
-            _OUT_DTYPE_OK = False
-    return torch.mm(dy.t(), a).float()
+    return ops.wgrad_bf16(dy, a)
 
 
 def _bgrad(dy):
@@ -47,19 +54,12 @@ def _bgrad(dy):
 
 
 def _dgrad_acc(acc, dy, w):
-    """acc (fp32 [T, in]) += dy (compute dtype [T, out]) @ w ([out, in]), IN PLACE, in the GEMM epilogue when
-    torch exposes addmm(out_dtype=..., out=acc) for bf16 operands, else GEMM + mixed-dtype add.  Every `acc`
-    handed in is a gradient buffer this engine owns (HeadFn's fresh dx or autograd's accumulation result), so
-    overwriting it saves the 134 MB copy an out-of-place addmm starts with."""
-    global _ADDMM_DTYPE_OK
+    """acc (fp32 [T, in]) += dy (compute dtype [T, out]) @ w ([out, in]), IN PLACE: the GEMM's epilogue adds its tile
+    into acc with a TMA reduce (bf16 operands), so the residual-stream gradient is accumulated in fp32 and never
+    re-read by an SM.  Every `acc` handed in is a gradient buffer this engine owns."""
     if dy.dtype == torch.float32:
         return acc.addmm_(dy, w)
-    if _ADDMM_DTYPE_OK:
-        try:
-            return torch.addmm(acc, dy, w, out_dtype=torch.float32, out=acc)
-        except (TypeError, RuntimeError):
-            _ADDMM_DTYPE_OK = False
-    return acc.add_(torch.mm(dy, w))
+    return ops.linear(dy, w, out=acc, w_is_kn=True, accumulate=True)
 
 
 def _attend_fwd(q, k, v, sizes, H, cross):
@@ -121,6 +121,8 @@ class LayerFn(torch.autograd.Function):
     def forward(ctx, x, theta, sizes, H, cdt, eps, w, *params):
         (Wqkv, bqkv, Wo, bo, W0, b0, g1, be1, W3, b3,
          Wqk, bqk, Wv, bv, Wout, bout, W0c, b0c, g2, be2, W3c, b3c) = w
+        if cdt == torch.bfloat16:  # biases are added in fp32 in the GEMM epilogue: take the master parameters
+            bqkv, bo, b0, b3, bqk, bv, bout, b0c, b3c = (params[i].detach() for i in (1, 3, 5, 9, 11, 13, 15, 17, 21))
         D = x.shape[1]
         x = x.contiguous()
         # The FFN input cat([x, msg], -1) (lightglue.py:162, 219) is never concatenated: the compute-dtype copy of x
@@ -131,26 +133,26 @@ class LayerFn(torch.autograd.Function):
         cat1 = torch.empty(T, 2 * D, device=x.device, dtype=cdt)
         x16, msg = cat1[:, :D], cat1[:, D:]
         ops.residual_add_cast(x, None, cdt, out_cast=x16)
-        qkv = torch.addmm(bqkv, x16, Wqkv.t())
+        qkv = _lin(x16, Wqkv, bqkv)
         q, k, v = ops.rope_fwd(qkv, theta, H)
         del qkv
         att, lse1 = _attend_fwd(q, k, v, sizes, H, cross=False)
-        torch.addmm(bo, att, Wo.t(), out=msg)
-        h = torch.addmm(b0, cat1, W0.t())
+        _lin(att, Wo, bo, out=msg)
+        h = _lin(cat1, W0, b0)
         g, mean1, rstd1 = ops.ln_gelu_fwd(h, g1, be1, eps)
-        y = torch.addmm(b3, g, W3.t())
+        y = _lin(g, W3, b3)
         cat2 = torch.empty(T, 2 * D, device=x.device, dtype=cdt)
         x1_16, msg2 = cat2[:, :D], cat2[:, D:]
         x1, _ = ops.residual_add_cast(x, y, cdt, out_cast=x1_16)
         del y
         # ---- cross block (lightglue.py:195-221)
-        qk = torch.addmm(bqk, x1_16, Wqk.t())
-        vv = torch.addmm(bv, x1_16, Wv.t())
+        qk = _lin(x1_16, Wqk, bqk)
+        vv = _lin(x1_16, Wv, bv)
         m, lse2 = _attend_fwd(qk, qk, vv, sizes, H, cross=True)
-        torch.addmm(bout, m, Wout.t(), out=msg2)
-        h2 = torch.addmm(b0c, cat2, W0c.t())
+        _lin(m, Wout, bout, out=msg2)
+        h2 = _lin(cat2, W0c, b0c)
         gg, mean2, rstd2 = ops.ln_gelu_fwd(h2, g2, be2, eps)
-        y2 = torch.addmm(b3c, gg, W3c.t())
+        y2 = _lin(gg, W3c, b3c)
         x2, _ = ops.residual_add_cast(x1, y2, None)
         ctx.save_for_backward(theta, cat1, q, k, v, att, h, mean1, rstd1, g, cat2, qk, vv, m, h2, mean2,
                               rstd2, gg, *lse1, *lse2, *w)
@@ -170,15 +172,15 @@ class LayerFn(torch.autograd.Function):
         # ---- cross block
         dy2 = dx.to(cdt)
         dW3c, db3c = _wgrad(dy2, gg), _bgrad(dy2)
-        dgg = torch.mm(dy2, W3c)
+        dgg = _dgrad(dy2, W3c)
         dh2, dg2, dbe2, db0c = ops.ln_gelu_bwd(dgg, h2, g2, be2, mean2, rstd2, want_dxsum=True)
         del dgg
         dW0c = _wgrad(dh2, cat2)
-        dmsg2 = torch.mm(dh2, W0c[:, D:])
+        dmsg2 = _dgrad(dh2, W0c[:, D:])
         dx1 = _dgrad_acc(dx, dh2, W0c[:, :D])  # fp32 accumulation of the residual-stream gradient
         del dh2
         dWout, dbout = _wgrad(dmsg2, m), _bgrad(dmsg2)
-        dm = torch.mm(dmsg2, Wout)
+        dm = _dgrad(dmsg2, Wout)
         dq_, dk_, dvv = _attend_bwd(qk, qk, vv, m, lse2, dm, sizes, H, cross=True)
         dqk = dq_.add_(dk_)  # the shared to_qk projection is query in one direction and key in the other
         dWqk, dbqk = _wgrad(dqk, x1_16), _bgrad(dqk)
@@ -188,15 +190,15 @@ class LayerFn(torch.autograd.Function):
         # ---- self block
         dy = dx1.to(cdt)
         dW3, db3 = _wgrad(dy, g), _bgrad(dy)
-        dg = torch.mm(dy, W3)
+        dg = _dgrad(dy, W3)
         dh, dg1, dbe1, db0 = ops.ln_gelu_bwd(dg, h, g1, be1, mean1, rstd1, want_dxsum=True)
         del dg
         dW0 = _wgrad(dh, cat1)
-        dmsg = torch.mm(dh, W0[:, D:])
+        dmsg = _dgrad(dh, W0[:, D:])
         dx0 = _dgrad_acc(dx1, dh, W0[:, :D])
         del dh
         dWo, dbo = _wgrad(dmsg, att), _bgrad(dmsg)
-        datt = torch.mm(dmsg, Wo)
+        datt = _dgrad(dmsg, Wo)
         dq, dk, dv = _attend_bwd(q, k, v, att, lse1, datt, sizes, H, cross=False)
         dqkv, dtheta = ops.rope_bwd(dq, dk, dv, q, k, theta, H)
         dWqkv, dbqkv = _wgrad(dqkv, x16), _bgrad(dqkv)
@@ -222,15 +224,21 @@ class HeadFn(torch.autograd.Function):
         # compute-dtype x for final_proj + [matchability logit, token-confidence logit] per token, one pass over x
         x16, zt, ls, du = ops.head_token_fwd(x, wm.view(-1), bm, wt.view(-1) if has_tok else None,
                                              bt if has_tok else None, cdt)
-        md = torch.addmm(bfp, x16, wfp.t())  # final_proj, un-scaled; d^-1/2 is folded into sim
+        md = _lin(x16, wfp, bfp_p.detach() if cdt == torch.bfloat16 else bfp)  # final_proj, un-scaled; d^-1/2 is folded into sim
         md0, md1 = md[:t0].view(B, M, D), md[t0:].view(B, N, D)
         alpha = float(D) ** -0.5
-        if cdt == torch.bfloat16:
-            sim = ops.gemm_bf16(md0, md1, alpha=alpha)
-        else:
-            sim = torch.bmm(md0, md1.transpose(1, 2)).mul_(alpha)
         ls0, ls1, du0, du1 = ls[:t0].view(B, M), ls[t0:].view(B, N), du[:t0].view(B, M), du[t0:].view(B, N)
-        st = ops.assign_stats(sim, ls0, ls1, du0, du1, gt_u8=gt["u8"], dense=False)
+        fused = FUSED_ASSIGN and ops.assign_fused_ok(md, D) and gt.get("u8_t") is not None
+        if fused:
+            # GEMM + LSE, then GEMM + scores / argmax / positives: the similarity matrix stays in tensor memory
+            sim = None
+            st = ops.assign_fused_stats(md0, md1, alpha, ls0, ls1, gt_u8=gt["u8"])
+        else:
+            if cdt == torch.bfloat16:
+                sim = ops.gemm_bf16(md0, md1, alpha=alpha)
+            else:
+                sim = torch.bmm(md0, md1.transpose(1, 2)).mul_(alpha)
+            st = ops.assign_stats(sim, ls0, ls1, du0, du1, gt_u8=gt["u8"], dense=False)
         out = torch.empty(4, B, device=dev, dtype=torch.float32)
         f0, f1 = (fin if (fin is not None and has_tok) else (None, None))
         hws = torch.empty(4 * B * ((M + N + 255) // 256), device=dev, dtype=torch.float32)
@@ -244,13 +252,13 @@ class HeadFn(torch.autograd.Function):
                  ops.ptr(gt["num_pos"]), ops.ptr(gt["num_neg"]), float(bal), ops.ptr(out[0]), ops.ptr(out[1]),
                  ops.ptr(out[2]), ops.ptr(out[3]), ops.ptr(hws), ops.ptr(cnt), B, M, N, ops.stream_ptr())
         nll, nll_pos, nll_neg, conf = out[0], out[1], out[2], out[3]
-        saved = [x, x16, md, sim, st["lse_row"], st["lse_col"], zt, st["rowmax"], st["rowarg"], st["colmax"],
-                 st["colarg"], wfp, wm, gt["u8"], gt["rowcnt"], gt["colcnt"], gt["neg0"], gt["neg1"], gt["num_pos"],
-                 gt["num_neg"]]
+        saved = [x, x16, md, sim if sim is not None else gt["u8_t"], st["lse_row"], st["lse_col"], zt, st["rowmax"],
+                 st["rowarg"], st["colmax"], st["colarg"], wfp, wm, gt["u8"], gt["rowcnt"], gt["colcnt"], gt["neg0"],
+                 gt["neg1"], gt["num_pos"], gt["num_neg"]]
         if f0 is not None:
             saved += [f0, f1]
         ctx.save_for_backward(*saved)
-        ctx.meta = (sizes, cdt, bal, alpha, has_tok, f0 is not None)
+        ctx.meta = (sizes, cdt, bal, alpha, has_tok, f0 is not None, fused)
         ctx.mark_non_differentiable(nll_pos, nll_neg)
         return nll, conf, nll_pos, nll_neg
 
@@ -259,7 +267,7 @@ class HeadFn(torch.autograd.Function):
         sv = ctx.saved_tensors
         (x, x16, md, sim, lse_row, lse_col, zt, rowmax, rowarg, colmax, colarg, wfp, wm, gt_u8, rowcnt, colcnt, neg0,
          neg1, num_pos, num_neg) = sv[:20]
-        (B, M, N), cdt, bal, alpha, has_tok, has_fin = ctx.meta
+        (B, M, N), cdt, bal, alpha, has_tok, has_fin, fused = ctx.meta
         f0, f1 = (sv[20], sv[21]) if has_fin else (None, None)
         D = x.shape[1]
         t0 = B * M
@@ -272,20 +280,25 @@ class HeadFn(torch.autograd.Function):
                  ops.stream_ptr())
         # similarity: dsim = gc (2 gt - softmax_row * rowcnt - softmax_col * colcnt), gc includes d^-1/2
         gc = (g_nll * (-bal * alpha) / num_pos).contiguous()
-        tc = cdt == torch.bfloat16 and N % 8 == 0 and M % 8 == 0
-        dsim = torch.empty(B, M, N, device=x.device, dtype=torch.bfloat16 if tc else torch.float32)
-        ops.call("lgb200_assign_bwd", ops.ptr(sim), ops.ptr(lse_row), ops.ptr(lse_col), ops.ptr(gt_u8), ops.ptr(gc),
-                 ops.ptr(rowcnt), ops.ptr(colcnt), ops.ptr(dsim), ops._code(dsim.dtype), B, M, N, ops.stream_ptr())
         md0, md1 = md[:t0].view(B, M, D), md[t0:].view(B, N, D)
-        if tc:
-            dmd0 = ops.gemm_bf16(dsim, md1, a_mn_major=False, b_mn_major=True, out_dtype=cdt)  # dsim   md1
-            dmd1 = ops.gemm_bf16(dsim, md0, a_mn_major=True, b_mn_major=True, out_dtype=cdt)   # dsim^T md0
+        if fused:
+            # dsim is recomputed tile by tile and contracted with the other image's descriptors in the same kernel
+            dmd = torch.empty(t0 + B * N, D, device=x.device, dtype=cdt)
+            ops.assign_fused_bwd(md0, md1, alpha, lse_row, lse_col, gt_u8, sim, gc, rowcnt, colcnt, dmd[:t0], dmd[t0:])
         else:
-            dmd0 = torch.bmm(dsim, md1.float()).to(cdt)
-            dmd1 = torch.bmm(dsim.transpose(1, 2), md0.float()).to(cdt)
-        dmd = torch.cat([dmd0.reshape(t0, D), dmd1.reshape(B * N, D)], 0)
+            tc = cdt == torch.bfloat16 and N % 8 == 0 and M % 8 == 0
+            dsim = torch.empty(B, M, N, device=x.device, dtype=torch.bfloat16 if tc else torch.float32)
+            ops.call("lgb200_assign_bwd", ops.ptr(sim), ops.ptr(lse_row), ops.ptr(lse_col), ops.ptr(gt_u8), ops.ptr(gc),
+                     ops.ptr(rowcnt), ops.ptr(colcnt), ops.ptr(dsim), ops._code(dsim.dtype), B, M, N, ops.stream_ptr())
+            if tc:
+                dmd0 = ops.gemm_bf16(dsim, md1, a_mn_major=False, b_mn_major=True, out_dtype=cdt)  # dsim   md1
+                dmd1 = ops.gemm_bf16(dsim, md0, a_mn_major=True, b_mn_major=True, out_dtype=cdt)   # dsim^T md0
+            else:
+                dmd0 = torch.bmm(dsim, md1.float()).to(cdt)
+                dmd1 = torch.bmm(dsim.transpose(1, 2), md0.float()).to(cdt)
+            dmd = torch.cat([dmd0.reshape(t0, D), dmd1.reshape(B * N, D)], 0)
         dWfp, dbfp = _wgrad(dmd, x16), _bgrad(dmd)
         # dx = dmd W_fp + dzt[:,0] wm (the token-confidence head reads a detached x, lightglue.py:82-83), dW2, db2
-        dx, dW2, db2 = ops.head_token_bwd(x, torch.mm(dmd, wfp), dzt, wm.view(-1))
+        dx, dW2, db2 = ops.head_token_bwd(x, _dgrad(dmd, wfp), dzt, wm.view(-1))
         dwt, dbt = (dW2[1:2], db2[1:2]) if has_tok else (None, None)
         return dx, None, None, None, None, None, None, None, dWfp, dbfp, dW2[0:1], db2[0:1], dwt, dbt

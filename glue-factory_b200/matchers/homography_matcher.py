@@ -51,6 +51,12 @@ class HomographyMatcher(nn.Module):
             assert key in data, f"Missing key {key} in data"
         if not self.conf.use_points:
             return {}
+        # label generation is geometry in pixel units: always fp32, whatever autocast region the caller is in
+        # (the pipeline runs ground_truth inside loss(), i.e. inside train.py's autocast block, :468-475)
+        with torch.autocast(device_type="cuda", enabled=False):
+            return self._labels(data)
+
+    def _labels(self, data):
         return ops.gt_matches_from_homography(data["keypoints0"], data["keypoints1"], data["H_0to1"],
                                               pos_th=self.conf.th_positive, neg_th=self.conf.th_negative,
                                               dense=bool(self.conf.dense_assignment))

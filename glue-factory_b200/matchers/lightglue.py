@@ -215,9 +215,12 @@ class LightGlue(nn.Module):
         return w, params
 
     def _lin(self, x, layer):
-        """nn.Linear through cuBLAS; bf16 operands in bf16 mode (fp32 accumulate inside cuBLAS)."""
+        """nn.Linear: bf16 mode -> the library's tcgen05 GEMM (bf16 operands, fp32 accumulate, fp32 bias epilogue);
+        fp32 parity mode -> fp32 cuBLAS."""
         if self._bf16:
-            return F.linear(x.to(torch.bfloat16), layer.weight.to(torch.bfloat16), layer.bias.to(torch.bfloat16))
+            shp = x.shape
+            y = ops.LinearFn.apply(x.reshape(-1, shp[-1]).to(torch.bfloat16).contiguous(), layer.weight, layer.bias)
+            return y.view(*shp[:-1], y.shape[-1])
         return F.linear(x, layer.weight, layer.bias)
 
     def _ffn(self, x, msg, ffn):
@@ -364,6 +367,9 @@ class LightGlue(nn.Module):
         L = len(layers_x)
         gtd = {"u8": gt_u8, "rowcnt": rowcnt.contiguous(), "colcnt": colcnt.contiguous(), "neg0": neg0.contiguous(),
                "neg1": neg1.contiguous(), "num_pos": num_pos.contiguous(), "num_neg": (num_neg0 + num_neg1).contiguous()}
+        if self._bf16 and engine.FUSED_ASSIGN and torch.is_grad_enabled():
+            # the fused backward walks the mask by columns as well: one transposed copy per step, shared by all layers
+            gtd["u8_t"] = gt_u8.transpose(1, 2).contiguous()
         la = pred["log_assignment"].detach()
         fin = pred.get("_b200_final_arg")
         if fin is None and L > 1:

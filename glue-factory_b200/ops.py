@@ -230,6 +230,50 @@ def gemm_bf16(a, b, a_mn_major=False, b_mn_major=False, out_dtype=torch.float32,
     return c
 
 
+def linear(a, w, bias=None, out=None, out_dtype=torch.bfloat16, w_is_kn=False, accumulate=False, alpha=1.0):
+    """The nn.Linear-shaped GEMMs of the layer on the persistent tcgen05 kernel (lgb200_linear, include/lgb200.h):
+        out[M, N] (=|+=) alpha * a[M, K] @ W^T + bias,   W = w[N, K]  (forward: y = x W^T + b)
+                                                     or  W^T = w[K, N] when w_is_kn (dgrad: dx = dy W, w = the [out, in] weight)
+    a, w bf16 2-D with unit inner stride (row-strided views are fine: column blocks of wider matrices);
+    bias fp32 [N]; out may be a row-strided view; accumulate=True adds into an fp32 `out` (TMA reduce-add)."""
+    _chk(a, torch.bfloat16, strided_rows=True), _chk(w, torch.bfloat16, strided_rows=True)
+    M, K = a.shape
+    N = w.shape[1] if w_is_kn else w.shape[0]
+    assert (w.shape[0] if w_is_kn else w.shape[1]) == K, (a.shape, w.shape, w_is_kn)
+    if out is None:
+        assert not accumulate
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype)
+    else:
+        assert out.shape == (M, N) and out.stride(1) == 1
+    if accumulate:
+        assert out.dtype == torch.float32
+    if bias is not None:
+        _chk(bias, torch.float32)
+        assert bias.numel() == N
+    call("lgb200_linear", ptr(a), ptr(w), ptr(out), ptr(bias), M, N, K, 0, int(w_is_kn), a.stride(0), w.stride(0),
+         out.stride(0), _code(out.dtype), float(alpha), int(accumulate), stream_ptr())
+    return out
+
+
+class LinearFn(torch.autograd.Function):
+    """nn.Linear on the library's GEMMs with autograd: x [T, in] bf16, weight [out, in] / bias [out] fp32 parameters.
+    forward y = x W^T + b (bf16 out, fp32 bias in the epilogue); backward dgrad (bf16), split-K wgrad (fp32), bias
+    gradient by the column-sum kernel.  Used by the op-by-op `engine: autograd` composition and for input_proj."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        w16 = weight.detach().to(torch.bfloat16)
+        ctx.save_for_backward(x, w16)
+        return linear(x, w16, bias.detach().float().contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w16 = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = linear(dy, w16, w_is_kn=True) if ctx.needs_input_grad[0] else None
+        return dx, wgrad_bf16(dy, x), colsum(dy)
+
+
 # ------------------------------------------------------------------------------------------------
 # assignment head (lightglue.py:256-290, losses.py)
 # ------------------------------------------------------------------------------------------------
@@ -262,6 +306,45 @@ def assign_stats(sim, ls0, ls1, dust0, dust1, gt_u8=None, dense=False):
          ptr(pos_row_sum), ptr(row_expsum), ptr(ws), B, M, N, stream_ptr())
     out.update(scores=scores, row_expsum=row_expsum, pos_row_sum=pos_row_sum)
     return out
+
+
+def assign_fused_ok(md, D):
+    """The fused GEMM + assignment kernels take bf16 descriptors of width 64..256 (multiple of 64)."""
+    return md.dtype == torch.bfloat16 and D % 64 == 0 and 64 <= D <= 256
+
+
+def assign_fused_stats(md0, md1, alpha, ls0, ls1, gt_u8=None):
+    """md0 [B,M,D], md1 [B,N,D] bf16 -> the same dict as assign_stats(dense=False) (lse_row/lse_col, rowmax/rowarg,
+    colmax/colarg, pos_row_sum) without ever writing sim = alpha md0 md1^T (csrc/assign_tc.cu: two passes, each a
+    tcgen05 GEMM whose accumulator tiles are reduced in the epilogue)."""
+    _chk(md0, torch.bfloat16), _chk(md1, torch.bfloat16)
+    B, M, D = md0.shape
+    N = md1.shape[1]
+    dev = md0.device
+    f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+    out = {"lse_row": f(B, M), "lse_col": f(B, N), "rowmax": f(B, M), "colmax": f(B, N),
+           "rowarg": torch.empty(B, M, device=dev, dtype=torch.int32),
+           "colarg": torch.empty(B, N, device=dev, dtype=torch.int32),
+           "pos_row_sum": f(B, M) if gt_u8 is not None else None, "scores": None, "row_expsum": None}
+    call("lgb200_assign_fused_lse", ptr(md0), ptr(md1), float(alpha), ptr(out["lse_row"]), ptr(out["lse_col"]), B, M, N, D,
+         stream_ptr())
+    ls0, ls1 = (t.detach().float().contiguous() for t in (ls0, ls1))
+    call("lgb200_assign_fused_stats", ptr(md0), ptr(md1), float(alpha), ptr(out["lse_row"]), ptr(out["lse_col"]), ptr(ls0),
+         ptr(ls1), ptr(gt_u8), ptr(out["rowmax"]), ptr(out["rowarg"]), ptr(out["colmax"]), ptr(out["colarg"]),
+         ptr(out["pos_row_sum"]), B, M, N, D, stream_ptr())
+    return out
+
+
+def assign_fused_bwd(md0, md1, alpha, lse_row, lse_col, gt_u8, gt_t_u8, gcoef, rowcnt, colcnt, dmd0, dmd1):
+    """d(mdesc0), d(mdesc1) (bf16, written into dmd0 [B*M, D] / dmd1 [B*N, D]) of the NLL through sim: dsim is
+    recomputed per tile from the two LSE vectors and contracted with the other image's descriptors in the same kernel."""
+    B, M, D = md0.shape
+    N = md1.shape[1]
+    for t in (lse_row, lse_col, gcoef, rowcnt, colcnt):
+        _chk(t, torch.float32)
+    _chk(gt_u8), _chk(gt_t_u8), _chk(dmd0, torch.bfloat16), _chk(dmd1, torch.bfloat16)
+    call("lgb200_assign_fused_bwd", ptr(md0), ptr(md1), float(alpha), ptr(lse_row), ptr(lse_col), ptr(gt_u8), ptr(gt_t_u8),
+         ptr(gcoef), ptr(rowcnt), ptr(colcnt), ptr(dmd0), ptr(dmd1), B, M, N, D, stream_ptr())
 
 
 class AssignPositives(torch.autograd.Function):
@@ -331,7 +414,7 @@ def gt_matches_from_homography(kp0, kp1, H, pos_th=3.0, neg_th=6.0, dense=True):
     kp0 [B,M,2], kp1 [B,N,2] pixel coordinates, H [B,3,3] -> dict with `assignment` (bool [B,M,N], omitted when
     dense=False), `matches0/1` (int64: index, -1 unmatched, -2 ignored), `matching_scores0/1`, `proj_0to1/1to0`.
     The dense `reward` map of the reference is not produced (no consumer on the matcher's path)."""
-    from .synthetic import warp_points
+    from .geometry import inv3x3, warp_points
 
     kp0, kp1 = kp0.float().contiguous(), kp1.float().contiguous()
     _chk(kp0, torch.float32), _chk(kp1, torch.float32)
@@ -339,7 +422,7 @@ def gt_matches_from_homography(kp0, kp1, H, pos_th=3.0, neg_th=6.0, dense=True):
     N = kp1.shape[1]
     Hm = H.float().expand(B, 3, 3) if H.dim() == 2 else H.float()
     kp0_1 = warp_points(kp0, Hm).contiguous()  # O(M+N): homography.py:161-180
-    kp1_0 = warp_points(kp1, torch.inverse(Hm)).contiguous()
+    kp1_0 = warp_points(kp1, inv3x3(Hm)).contiguous()
     dev = kp0.device
     m0 = torch.empty(B, M, device=dev, dtype=torch.int64)
     m1 = torch.empty(B, N, device=dev, dtype=torch.int64)

@@ -17,6 +17,8 @@ import math
 import numpy as np
 import torch
 
+from .geometry import warp_points
+
 DEFAULT_CONF = {
     "name": "lightglue",
     "input_dim": 256,
@@ -90,13 +92,6 @@ def make_weights(conf, seed=0, dtype=torch.float32):
 # ----------------------------------------------------------------------------
 # ground truth (restated; runs on whatever device the keypoints live on)
 # ----------------------------------------------------------------------------
-def warp_points(pts, Hm):
-    """pts [B,N,2] -> H . pts (homogeneous divide, eps as geometry/utils.from_homogeneous)."""
-    ones = torch.ones_like(pts[..., :1])
-    ph = torch.cat([pts, ones], -1) @ Hm.transpose(-1, -2)
-    return ph[..., :2] / (ph[..., 2:] + 1e-5)
-
-
 @torch.no_grad()
 def gt_matches_from_homography(kp0, kp1, Hm, pos_th=3.0, neg_th=3.0):
     """Restates geometry/gt_generation.py:109-161: reprojection distance both

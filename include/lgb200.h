@@ -104,6 +104,16 @@ int lgb200_gemm_bf16(const void* A, const void* B, void* C, int batch, int M, in
 int64_t lgb200_gemm_splitk_ws_floats(int M, int N, int K);
 int lgb200_gemm_bf16_splitk(const void* A, const void* B, float* C, int M, int N, int K, int a_mn_major,
                             int b_mn_major, int64_t lda, int64_t ldb, int64_t ldc, float* ws, cudaStream_t stream);
+/* One nn.Linear-shaped GEMM on the same persistent tcgen05 kernel, with the epilogues the layer needs
+ * (replaces F.linear / its autograd, lightglue.py:139-148, 156-163, 174-183, 195-221, 280):
+ *   C[M,N] (c_dtype, row pitch ldc) = alpha * op(A) op(B)^T + bias[N]          (accumulate == 0)
+ *   C[M,N] (fp32)                  += alpha * op(A) op(B)^T + bias[N]          (accumulate != 0; TMA reduce-add in L2)
+ * A: [M,K] row pitch lda (or [K,M] when a_mn_major), B: [N,K] row pitch ldb (or [K,N] when b_mn_major), bf16;
+ * bias: fp32 [N] or NULL.  forward: A = x, B = W;  dgrad: A = dy, B = W (b_mn_major);  row pitches let C be a column
+ * block of a wider matrix (the [x | msg] FFN input, lightglue.py:162). */
+int lgb200_linear(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int a_mn_major,
+                  int b_mn_major, int64_t lda, int64_t ldb, int64_t ldc, int c_dtype, float alpha, int accumulate,
+                  cudaStream_t stream);
 
 /* ---- assignment head: sigmoid_log_double_softmax + NLL terms + argmax --------------------------------
  * replaces lightglue.py:256-268 (two log_softmax, transposed copy, slice assignment),
@@ -129,6 +139,23 @@ int lgb200_assign_bwd(const float* sim, const float* lse_row, const float* lse_c
                       const float* gcoef, const float* rowcnt, const float* colcnt, void* dsim, int out_dtype, int B,
                       int M, int N, cudaStream_t stream);
 /* filter_matches (lightglue.py:293-309): mutual check + threshold; m0,m1 int64, -1 = no match       */
+/* ---- assignment head fused with its similarity GEMM (csrc/assign_tc.cu; bf16 mdesc, D % 64 == 0, D <= 256) ----------
+ * sim = alpha * mdesc0 . mdesc1^T (lightglue.py:283) is produced tile by tile in tensor memory and consumed there; it
+ * is never written to memory.  md0: [B,M,D], md1: [B,N,D] bf16 contiguous.  Same outputs as lgb200_assign_lse /
+ * lgb200_assign_scores (without the dense scores) / lgb200_assign_bwd followed by the two d(mdesc) GEMMs. */
+int lgb200_assign_fused_lse(const void* md0, const void* md1, float alpha, float* lse_row, float* lse_col, int B, int M,
+                            int N, int D, cudaStream_t stream);
+/* gt ([B,M,N] bool) and pos_row_sum ([B,M]) are both set or both NULL. */
+int lgb200_assign_fused_stats(const void* md0, const void* md1, float alpha, const float* lse_row, const float* lse_col,
+                              const float* ls0, const float* ls1, const uint8_t* gt, float* rowmax, int* rowarg,
+                              float* colmax, int* colarg, float* pos_row_sum, int B, int M, int N, int D,
+                              cudaStream_t stream);
+/* dmd0 [B*M, D], dmd1 [B*N, D] bf16 = dsim . md1, dsim^T . md0 with
+ * dsim = gcoef[b] (2 gt - softmax_row rowcnt - softmax_col colcnt); gt_t = the [B,N,M] transpose of gt. */
+int lgb200_assign_fused_bwd(const void* md0, const void* md1, float alpha, const float* lse_row, const float* lse_col,
+                            const uint8_t* gt, const uint8_t* gt_t, const float* gcoef, const float* rowcnt,
+                            const float* colcnt, void* dmd0, void* dmd1, int B, int M, int N, int D,
+                            cudaStream_t stream);
 int lgb200_filter_matches(const float* rowmax, const int* rowarg, const int* colarg, float th, int64_t* m0,
                           int64_t* m1, float* ms0, float* ms1, int B, int M, int N, cudaStream_t stream);
 

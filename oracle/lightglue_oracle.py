@@ -71,7 +71,7 @@ class Bf16Mirror:
                   forward, gradient left in fp32 (the CUDA path accumulates the residual-stream gradient in fp32);
       store(x):   a tensor the CUDA path keeps in bf16 (every Linear output, rotated q / k, attention output,
                   LayerNorm+GELU output) -- rounded in forward and its gradient rounded in backward;
-      bias(b):    Linear biases are read from the bf16 weight shadow;
+      bias(b):    Linear biases stay fp32 (added to the fp32 accumulator in the GEMM epilogue);
       grad(x):    fp32 in forward, gradient produced in bf16 (the similarity matrix: dsim is bf16).
 
     Not mirrored (second-order): P is rounded after normalisation here and before it in the kernels; the shared
@@ -81,7 +81,7 @@ class Bf16Mirror:
         return bf16_round(x)
 
     operand = staticmethod(bf16_round)
-    bias = staticmethod(bf16_round)
+    bias = staticmethod(_id)
     store = staticmethod(_RoundBoth.apply)
     grad = staticmethod(_RoundGrad.apply)
 

@@ -55,6 +55,104 @@ def test_wgrad_splitk(T, M, N):
     assert rel_err(ops.wgrad_bf16(dy, wide[:, N:]), dy.double().t() @ wide[:, N:].double()) < 1e-5
 
 
+@pytest.mark.parametrize("T,K,N", [(4096, 256, 768), (1000, 512, 512), (777, 512, 256), (130, 256, 256), (64, 128, 72)])
+def test_linear_epilogues(T, K, N):
+    """lgb200_linear: y = x W^T + b with the fp32 bias added in the epilogue, into a column block of a wider matrix;
+    dx = dy W (W read as stored); fp32 accumulate-into-dx through the TMA reduce."""
+    wide = _rand(T, 2 * K, seed=1, dtype=torch.bfloat16)
+    x = wide[:, K:]                                   # row-strided A (the [x | msg] FFN input halves)
+    w = _rand(N, K, seed=2, dtype=torch.bfloat16, scale=K ** -0.5)
+    b = _rand(N, seed=3)
+    ref = x.double() @ w.double().t() + b.double()
+    y = ops.linear(x, w, b)
+    assert y.dtype == torch.bfloat16 and rel_err(y, ref) < 4e-3
+    y32 = ops.linear(x, w, b, out_dtype=torch.float32)
+    assert rel_err(y32, ref) < 1e-5
+    if N % 8 == 0:
+        out_wide = torch.zeros(T, 2 * N, device=DEV, dtype=torch.bfloat16)
+        ops.linear(x, w, b, out=out_wide[:, N:])          # row-strided C
+        assert rel_err(out_wide[:, N:], ref) < 4e-3 and float(out_wide[:, :N].abs().sum()) == 0.0
+    # dgrad: dy [T, N] @ W [N, K] (B operand MN-major, exactly as the weight lies in memory)
+    dy = _rand(T, N, seed=4, dtype=torch.bfloat16)
+    refdx = dy.double() @ w.double()
+    assert rel_err(ops.linear(dy, w, w_is_kn=True), refdx) < 4e-3
+    if K % 4 == 0:
+        acc0 = _rand(T, K, seed=5)
+        acc = acc0.clone()
+        ops.linear(dy, w, out=acc, w_is_kn=True, accumulate=True)
+        assert rel_err(acc, acc0.double() + refdx) < 1e-5
+        # a column slice of a wider weight (ffn.0's [x | msg] halves)
+        wwide = _rand(N, 2 * K, seed=6, dtype=torch.bfloat16, scale=K ** -0.5)
+        acc = acc0.clone()
+        ops.linear(dy, wwide[:, K:], out=acc, w_is_kn=True, accumulate=True)
+        assert rel_err(acc, acc0.double() + dy.double() @ wwide[:, K:].double()) < 1e-5
+
+
+def test_linear_autograd_function():
+    x = _rand(515, 256, seed=1, dtype=torch.bfloat16).requires_grad_(True)
+    lin = torch.nn.Linear(256, 384).to(DEV)
+    y = ops.LinearFn.apply(x, lin.weight, lin.bias)
+    g = _rand(515, 384, seed=2, dtype=torch.bfloat16)
+    y.backward(g)
+    xr = x.detach().double().requires_grad_(True)
+    wr = lin.weight.detach().to(torch.bfloat16).double().requires_grad_(True)
+    br = lin.bias.detach().double().requires_grad_(True)
+    (xr @ wr.t() + br).backward(g.double())
+    assert rel_err(x.grad, xr.grad) < 4e-3
+    assert rel_err(lin.weight.grad, wr.grad) < 1e-5 and rel_err(lin.bias.grad, br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B,M,N,D", [(2, 256, 256, 256), (3, 150, 203, 256), (1, 72, 300, 128), (2, 2048, 2048, 256),
+                                     (1, 130, 64, 64)])
+def test_assign_fused_matches_unfused_and_fp64(B, M, N, D):
+    """csrc/assign_tc.cu (similarity never leaves tensor memory) against (a) the round-1 path -- sim GEMM written to HBM,
+    assign_lse / assign_scores / assign_bwd, two d(mdesc) GEMMs -- and (b) an fp64 evaluation of the same bf16 operands."""
+    md0 = _rand(B, M, D, seed=1, dtype=torch.bfloat16, scale=2.0)
+    md1 = _rand(B, N, D, seed=2, dtype=torch.bfloat16, scale=2.0)
+    alpha = D ** -0.5
+    z0, z1 = _rand(B, M, seed=3), _rand(B, N, seed=4)
+    ls0, ls1 = torch.nn.functional.logsigmoid(z0), torch.nn.functional.logsigmoid(z1)
+    du0, du1 = torch.nn.functional.logsigmoid(-z0), torch.nn.functional.logsigmoid(-z1)
+    g = torch.Generator().manual_seed(5)
+    gt = torch.zeros(B, M, N, dtype=torch.bool)
+    K = min(M, N) // 3
+    for b in range(B):
+        gt[b, torch.randperm(M, generator=g)[:K], torch.randperm(N, generator=g)[:K]] = True
+    gt = gt.to(DEV)
+    gt_u8 = gt.view(torch.uint8)
+    f = ops.assign_fused_stats(md0, md1, alpha, ls0, ls1, gt_u8=gt_u8)
+    sim = ops.gemm_bf16(md0, md1, alpha=alpha)
+    u = ops.assign_stats(sim, ls0, ls1, du0, du1, gt_u8=gt_u8, dense=False)
+    # (a) same fp32 accumulators, different summation grouping in the LSE: 1e-5; integer outputs equal
+    for k in ("lse_row", "lse_col", "rowmax", "colmax"):
+        assert (f[k] - u[k]).abs().max().item() < 2e-4, k
+    same_r = (f["rowarg"] == u["rowarg"]).float().mean().item()
+    same_c = (f["colarg"] == u["colarg"]).float().mean().item()
+    assert same_r > 0.999 and same_c > 0.999, (same_r, same_c)  # argmax flips only on fp32-rounding near-ties
+    assert (f["pos_row_sum"] - u["pos_row_sum"]).abs().max().item() < 1e-3
+    # (b) fp64 on the same bf16 operands
+    s64 = (md0.double() @ md1.double().transpose(1, 2)) * alpha
+    assert (f["lse_row"].double() - torch.logsumexp(s64, 2)).abs().max().item() < 1e-4
+    assert (f["lse_col"].double() - torch.logsumexp(s64, 1)).abs().max().item() < 1e-4
+    sc = (s64 - torch.logsumexp(s64, 2, keepdim=True)) + (s64 - torch.logsumexp(s64, 1, keepdim=True)) + \
+        (ls0.double()[:, :, None] + ls1.double()[:, None, :])
+    assert (f["rowmax"].double() - sc.max(2).values).abs().max().item() < 1e-3
+    assert (f["colmax"].double() - sc.max(1).values).abs().max().item() < 1e-3
+    # backward
+    rowcnt, colcnt = gt_u8.sum(2, dtype=torch.float32), gt_u8.sum(1, dtype=torch.float32)
+    gc = (_rand(B, seed=6).abs() + 0.1) * alpha
+    dmd = torch.empty(B * M + B * N, D, device=DEV, dtype=torch.bfloat16)
+    ops.assign_fused_bwd(md0, md1, alpha, f["lse_row"], f["lse_col"], gt_u8, gt_u8.transpose(1, 2).contiguous(), gc, rowcnt,
+                         colcnt, dmd[:B * M], dmd[B * M:])
+    p_r = torch.exp(s64 - torch.logsumexp(s64, 2, keepdim=True))
+    p_c = torch.exp(s64 - torch.logsumexp(s64, 1, keepdim=True))
+    dsim = gc.double()[:, None, None] * (2 * gt.double() - p_r * rowcnt.double()[:, :, None] - p_c * colcnt.double()[:, None, :])
+    ref0 = (dsim @ md1.double()).reshape(B * M, D)
+    ref1 = (dsim.transpose(1, 2) @ md0.double()).reshape(B * N, D)
+    assert rel_err(dmd[:B * M], ref0) < 8e-3 and rel_err(dmd[B * M:], ref1) < 8e-3  # dsim and the output are bf16
+    torch.cuda.synchronize()
+
+
 def test_gemm_unaligned_output_uses_fallback_epilogue():
     """N = 130: C rows are not 16-byte multiples, so the TMA-store epilogue is replaced by plain stores."""
     a = _rand(2, 100, 64, seed=1, dtype=torch.bfloat16)

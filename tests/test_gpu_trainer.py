@@ -34,6 +34,7 @@ def test_flat_adam_with_grad_scaler_matches_torch():
     growth = torch.zeros(1, device=DEV, dtype=torch.int32)
     found = torch.zeros(1, device=DEV)
     lr_dev = torch.full((1,), 2e-3, device=DEV)
+    scaler.scale(torch.ones(1, device=DEV))  # GradScaler creates its scale tensor lazily on the first scale() call
     for t in range(6):
         g = _rand(n, 10 + t)
         if t == 2:
