@@ -70,11 +70,19 @@ int make_tmap(CUtensorMap* out, const void* base, bool fp32, int rank, const uin
       gstr[i - 1] = strides_bytes[i - 1];
     }
   }
-  CUresult r = fn(out, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  auto encode = [&]() {
+    return fn(out, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+              const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUresult r = encode();
+  if (r == CUDA_ERROR_INVALID_CONTEXT) {
+    // a thread that has not issued a CUDA runtime call yet (e.g. a fresh autograd worker whose first CUDA work is this
+    // entry point) has no current context for the driver API: bind the primary context and retry
+    cudaFree(nullptr);
+    r = encode();
+  }
   LGB_REQUIRE(r == CUDA_SUCCESS, kErrCuda, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
 }

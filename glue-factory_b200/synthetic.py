@@ -183,3 +183,59 @@ def to_device(data, device, non_blocking=False):
     if torch.is_tensor(data):
         return data.to(device, non_blocking=non_blocking)
     return data
+
+
+# ----------------------------------------------------------------------------
+# GlueStick (points + lines; BASELINE.json configs[4])
+# ----------------------------------------------------------------------------
+def make_gluestick_batch(B, N, L, seed, D=256, dtype=torch.float32):
+    """Synthetic GlueStick batch (SURVEY 8d, config 5 shape): the first 2L keypoints of each view are the endpoints of L
+    independent segments (wireframe.py:246-253, 290-294: lines_junc_idx = arange(2L).view(L, 2)), the rest plain
+    keypoints.  Point labels from the homography restatement; a segment of view 0 matches a segment of view 1 when both
+    endpoints correspond (either order)."""
+    d = make_pairs(B, N, seed=seed, D=D, dtype=dtype)
+    rs = np.random.RandomState(seed + 7)
+    out = dict(d)
+    for i in "01":
+        kp = d[f"keypoints{i}"]
+        out[f"lines{i}"] = kp[:, :2 * L].reshape(B, L, 2, 2).clone()
+        out[f"lines_junc_idx{i}"] = torch.arange(2 * L).view(1, L, 2).repeat(B, 1, 1)
+        out[f"line_scores{i}"] = torch.from_numpy(rs.uniform(0, 1, size=(B, L))).to(dtype)
+        out[f"keypoint_scores{i}"] = torch.from_numpy(rs.uniform(0, 1, size=(B, N))).to(dtype)
+    m0 = d["gt_matches0"][:, :2 * L].reshape(B, L, 2)
+    asg = torch.zeros(B, L, L, dtype=torch.bool)
+    for b in range(B):
+        for a in range(L):
+            e0, e1 = int(m0[b, a, 0]), int(m0[b, a, 1])
+            if 0 <= e0 < 2 * L and 0 <= e1 < 2 * L and e0 // 2 == e1 // 2 and e0 != e1:
+                asg[b, a, e0 // 2] = True
+    lm0 = torch.where(asg.any(2), asg.float().argmax(2), torch.full((B, L), -1, dtype=torch.long))
+    lm1 = torch.where(asg.any(1), asg.float().argmax(1), torch.full((B, L), -1, dtype=torch.long))
+    out.update(gt_line_assignment=asg, gt_line_matches0=lm0, gt_line_matches1=lm1)
+    return out
+
+
+def make_gluestick_weights(state_dict_like, seed=0, dtype=torch.float32):
+    """Deterministic weights for a GlueStick state_dict (names / shapes taken from `state_dict_like`, e.g. the plugin
+    module's own state_dict, whose tree equals the reference's): conv weights and biases U(-1/sqrt(fan_in), ..),
+    BatchNorm affine perturbed around (1, 0), bin scores around 1, running statistics left at their defaults."""
+    rs = np.random.RandomState(seed)
+    shapes = {k: tuple(v.shape) for k, v in state_dict_like.items()}
+    out = {}
+    for k, shp in shapes.items():
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.zeros((), dtype=torch.long)
+        elif k.endswith("running_mean"):
+            out[k] = torch.zeros(shp, dtype=dtype)
+        elif k.endswith("running_var"):
+            out[k] = torch.ones(shp, dtype=dtype)
+        elif len(shp) == 0:
+            out[k] = torch.tensor(1.0 + 0.1 * rs.standard_normal(), dtype=dtype)
+        elif k[: k.rfind(".")] + ".running_mean" in shapes:  # BatchNorm affine
+            base = 1.0 if k.endswith("weight") else 0.0
+            out[k] = torch.from_numpy(base + 0.1 * rs.standard_normal(shp)).to(dtype)
+        else:
+            wshape = shp if k.endswith("weight") else shapes[k[: -len("bias")] + "weight"]
+            bound = 1.0 / math.sqrt(wshape[1])
+            out[k] = torch.from_numpy(rs.uniform(-bound, bound, size=shp)).to(dtype)
+    return out

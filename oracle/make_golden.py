@@ -259,6 +259,46 @@ def run_gt_homography():
     print("gt_homography ->", path)
 
 
+def run_gluestick(name="gluestick_l4_n160", n_gnn=4, B=2, N=160, L=24, seed=31):
+    """Forward + loss + backward of the UNMODIFIED reference GlueStick (models/matchers/gluestick.py) in fp64, train
+    mode (BatchNorm batch statistics), on the synthetic points+lines batch: predictions, all loss entries, every
+    parameter gradient (summarised) and the updated BatchNorm running statistics.  Weights come from
+    synthetic.make_gluestick_weights over the PLUGIN's state_dict layout and are loaded strictly into the reference --
+    which also proves the two module trees carry identical names and shapes."""
+    from gluefactory.models import get_model
+    from gluefactory_b200.matchers.gluestick import GlueStick as Plugin
+
+    conf = {"GNN_layers": ["self", "cross"] * (n_gnn // 2), "filter_threshold": 0.2}
+    # weights are drawn in fp32 (what the CUDA plugin holds) and evaluated by the reference in fp64
+    sd = synthetic.make_gluestick_weights(Plugin(dict(conf)).state_dict(), seed=seed)
+    model = get_model("matchers.gluestick")(dict(conf, name="matchers.gluestick")).double()
+    assert list(model.state_dict().keys()) == list(sd.keys())
+    model.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}, strict=True)
+    model = model.train()
+    data = synthetic.make_gluestick_batch(B, N, L, seed + 1, dtype=torch.float64)
+    pred = model(data)
+    losses, _ = model.loss(pred, data)
+    losses["total"].mean().backward()
+    out = {"meta|conf": np.array(repr(conf)), "meta|B": np.array(B), "meta|N": np.array(N), "meta|L": np.array(L),
+           "meta|seed": np.array(seed)}
+    for k in ["matches0", "matches1", "matching_scores0", "matching_scores1", "log_assignment", "line_matches0",
+              "line_matches1", "line_matching_scores0", "line_log_assignment", "raw_line_scores"]:
+        out["pred|" + k] = pred[k].detach().numpy()
+    for k, v in losses.items():
+        out["loss|" + k] = v.detach().numpy() if torch.is_tensor(v) else np.array(v)
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        out.update(summarise("grad|" + k, p.grad))
+    for k, v in model.state_dict().items():
+        if "running_" in k:
+            out["bn|" + k] = v.numpy()
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: loss={losses['total'].mean().item():.6f} point matches={int((pred['matches0'] > -1).sum())} "
+          f"line matches={int((pred['line_matches0'] > -1).sum())} params={sum(p.numel() for p in model.parameters())} -> "
+          f"{path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 def run_eval_loss():
     """Validation-mode loss of the reference (train.py:92-93 do_evaluation: model.eval(), loss on the last layer only,
     lightglue.py:485 keeps one stacked layer and :588 uses log_assignment[-1]) + the matcher metrics."""
@@ -296,7 +336,7 @@ if __name__ == "__main__":
     if only:
         for name in only:
             {"gluestick_attn": run_gluestick_attention, "gt_homography": run_gt_homography,
-             "heads_grad": run_heads_grad, "autocast": run_autocast_cases, "eval_loss": run_eval_loss}[name]()
+             "heads_grad": run_heads_grad, "autocast": run_autocast_cases, "eval_loss": run_eval_loss, "gluestick": run_gluestick}[name]()
         sys.exit(0)
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -315,3 +355,4 @@ if __name__ == "__main__":
     run_gt_homography()
     run_autocast_cases()
     run_eval_loss()
+    run_gluestick()
