@@ -25,6 +25,7 @@ SIGNATURES = {
     "lgb200_rope_split_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "lgb200_rope_split_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "lgb200_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "lgb200_attn_bwd_ws_floats": (_i64, [_i, _i, _i, _i]),
     "lgb200_attn_bwd": (_i, [_vp] * 10 + [_i, _i, _i, _i, _i, _f, _i, _vp]),
     "lgb200_ln_gelu_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _i, _vp]),
     "lgb200_ln_gelu_bwd_parts": (_i, [_i64]),
@@ -97,7 +98,7 @@ def load(check_device=True):
 
 # kernels launched per entry point (for bench.py's gpu_launches accounting)
 KERNELS_PER_CALL = {
-    "lgb200_rope_split_fwd": 1, "lgb200_rope_split_bwd": 1, "lgb200_attn_fwd": 1, "lgb200_attn_bwd": 3,
+    "lgb200_rope_split_fwd": 1, "lgb200_rope_split_bwd": 1, "lgb200_attn_fwd": 1, "lgb200_attn_bwd": 3,  # prep + fused + dQ convert (or prep + dQ + dKV)
     "lgb200_ln_gelu_fwd": 1, "lgb200_ln_gelu_bwd": 1, "lgb200_gemm_bf16": 1, "lgb200_assign_lse": 2,
     "lgb200_assign_scores": 2, "lgb200_assign_bwd": 1, "lgb200_filter_matches": 1, "lgb200_log_double_softmax": 3,
     "lgb200_adam_flat": 1, "lgb200_cast_bf16": 1, "lgb200_colsum": 1, "lgb200_residual_add_cast": 1,

@@ -161,6 +161,8 @@ int lgb200_attn_fwd(const void* q, const void* k, const void* v, void* out, floa
   return attn_fwd_tc(q, k, v, out, lse, B, Nq, Nk, H, kv_shift, scale, stream);
 }
 
+int64_t lgb200_attn_bwd_ws_floats(int B, int Nq, int Nk, int H) { return attn_bwd_ws_floats(B, Nq, Nk, H); }
+
 int lgb200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
                     void* dq, void* dk, void* dv, float* delta_ws, int B, int Nq, int Nk, int H, int kv_shift,
                     float scale, int dtype, cudaStream_t stream) {

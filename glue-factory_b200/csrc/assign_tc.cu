@@ -10,7 +10,7 @@
 //   no atomics, deterministic.
 //   The panel (A, 128 x D bf16) stays resident in shared memory for the item; 128-column tiles of the other image
 //   (B, 128 x D) stream through a 2-stage TMA ring; S = A B^T (M128 N128, D/16 MMAs) lands in one of two TMEM buffers
-//   so the MMA warp runs a tile ahead of the 8 epilogue warps (two per TMEM lane quarter, 64 columns each).
+//   so the MMA warp runs a tile ahead of the 16 epilogue warps (four per TMEM lane quarter, 32 columns each).
 //
 //   LSE  : running (max, sum exp2) per thread -> lse_row [B,M] (dir 0), lse_col [B,N] (dir 1).
 //   STATS: scores in the reference's association order ((s - lse_r) + (s - lse_c)) + (lsig0 + lsig1); running
@@ -33,9 +33,9 @@ constexpr int AT_KBLK = 64;                // K elements per smem block (one 128
 constexpr int AT_BLK = AT_R * AT_KBLK * 2; // 16 KiB
 constexpr int AT_MAXKB = 4;                // D <= 256
 constexpr int AT_STAGES = 2;
-constexpr int AT_EWARPS = 8;
+constexpr int AT_EWARPS = 16;
 constexpr int AT_THREADS = (AT_EWARPS + 2) * 32;
-constexpr int AT_SCR = AT_EWARPS * 2 * 64 * 4 + 4 * 128 * 4;  // per-warp column vectors + half-merge scratch
+constexpr int AT_SCR = AT_EWARPS * 2 * 32 * 4 + 3 * 384 * 4;  // per-warp column vectors + quarter-merge scratch
 constexpr int AT_SMEM = (1 + AT_STAGES) * AT_MAXKB * AT_BLK + AT_SCR + 256;
 constexpr int AT_ACC_COL = 256;            // TMEM: S0 [0,128) S1 [128,256) | d(mdesc) accumulator [256, 256 + D)
 
@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + AT_MAXKB * AT_BLK;
-  float* sVec = reinterpret_cast<float*>(smem + (1 + AT_STAGES) * AT_MAXKB * AT_BLK);  // [8 warps][2][64]
-  float* sMerge = sVec + AT_EWARPS * 2 * 64;                                              // [4][128]
+  float* sVec = reinterpret_cast<float*>(smem + (1 + AT_STAGES) * AT_MAXKB * AT_BLK);  // [16 warps][2][32]
+  float* sMerge = sVec + AT_EWARPS * 2 * 32;                                              // [3][3][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + AT_STAGES) * AT_MAXKB * AT_BLK + AT_SCR);
   uint64_t* a_full = bars;          // 1
   uint64_t* a_empty = bars + 1;     // 1
@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
           const uint64_t so = (uint64_t)((s * AT_MAXKB * AT_BLK) >> 4);
           const uint32_t abase = tmem_base + s * AT_C;
 #pragma unroll
-          for (int kk = 0; kk < AT_C / 16; ++kk)  // half hf of the tile wrote its packed dsim at column hf*64
-            umma_bf16_ts(tmem_base + AT_ACC_COL, abase + (kk >> 2) * 64 + (kk & 3) * 8, dBm + so + (uint64_t)(kk * 128),
+          for (int kk = 0; kk < AT_C / 16; ++kk)  // quarter cq of the tile wrote its packed dsim at column cq*32
+            umma_bf16_ts(tmem_base + AT_ACC_COL, abase + (kk >> 1) * 32 + (kk & 1) * 8, dBm + so + (uint64_t)(kk * 128),
                          idesc_acc, (first && kk == 0) ? 0u : 1u);
           umma_commit(&b_empty[s]);
         }
@@ -199,10 +199,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3, hf = warp >> 2;        // TMEM lane quarter, column half of the tile
+    // 16 warps = 4 per scheduler: TMEM lane quarter q (rows), column quarter cq (32 of the tile's 128 columns)
+    const int q = warp & 3, cq = warp >> 2;
     const int r = q * 32 + lane;                   // row within the panel == TMEM lane
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    float* myvec = sVec + warp * 128;              // [2][64]
+    float* myvec = sVec + warp * 64;               // [2][32]: this warp's slice of the two per-column vectors
     constexpr float kLog2e = 1.4426950408889634f;
     const float c2 = a.alpha * kLog2e;
     int it = 0, g = 0;
@@ -237,39 +238,36 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 
       for (int t = 0; t < ntiles; ++t, ++g) {
         const int s = g & 1;
-        const int j0 = t * AT_C + hf * 64;      // first column of this warp's half
-        const bool tail = j0 + 64 > ncols;
-        if (MODE != AT_LSE) {                   // stage this warp's 64 column values (two vectors), coalesced
+        const int j0 = t * AT_C + cq * 32;      // first column of this warp's quarter
+        const bool tail = j0 + 32 > ncols;
+        if (MODE != AT_LSE) {                   // stage this warp's 32 column values (two vectors), coalesced
           __syncwarp();
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int j = j0 + lane + 32 * e;
-            float v0 = 0.f, v1 = 0.f;
-            if (j < ncols) {
-              v0 = cvec_lse[j];
-              v1 = cvec_b[j];
-            }
-            if (MODE == AT_BWD) {
-              v0 = j < ncols ? v0 * kLog2e : INFINITY;  // exp2(x - inf) = 0 for columns past the end
-              v1 *= gc;
-            }
-            myvec[lane + 32 * e] = v0;
-            myvec[64 + lane + 32 * e] = v1;
+          const int j = j0 + lane;
+          float v0 = 0.f, v1 = 0.f;
+          if (j < ncols) {
+            v0 = cvec_lse[j];
+            v1 = cvec_b[j];
           }
+          if (MODE == AT_BWD) {
+            v0 = j < ncols ? v0 * kLog2e : INFINITY;  // exp2(x - inf) = 0 for columns past the end
+            v1 *= gc;
+          }
+          myvec[lane] = v0;
+          myvec[32 + lane] = v1;
           __syncwarp();
         }
-        uint32_t gw[16];  // 64 mask bytes of this thread's row (kept in registers: only constant indices below)
+        uint32_t gw[8];  // 32 mask bytes of this thread's row (registers: constant indices only)
 #pragma unroll
-        for (int e = 0; e < 16; ++e) gw[e] = 0u;
+        for (int e = 0; e < 8; ++e) gw[e] = 0u;
         if (grow && !tail && gvec) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
+          for (int e = 0; e < 2; ++e) {
             const uint4 u = *reinterpret_cast<const uint4*>(grow + j0 + 16 * e);
             gw[4 * e] = u.x; gw[4 * e + 1] = u.y; gw[4 * e + 2] = u.z; gw[4 * e + 3] = u.w;
           }
         } else if (grow) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
+          for (int e = 0; e < 8; ++e) {
 #pragma unroll
             for (int u = 0; u < 4; ++u)
               if (j0 + 4 * e + u < ncols) gw[e] |= (uint32_t)grow[j0 + 4 * e + u] << (8 * u);
@@ -277,9 +275,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         }
         mbar_wait(&s_full[s], (g >> 1) & 1);
         tc_fence_after();
-        float sv[64];
-        tmem_ld32(t_lane + s * AT_C + hf * 64, sv);
-        tmem_ld32(t_lane + s * AT_C + hf * 64 + 32, sv + 32);
+        float sv[32];
+        tmem_ld32(t_lane + s * AT_C + cq * 32, sv);
         tmem_ld_wait();
         if (MODE == AT_LSE) {
           tc_fence_before();
@@ -287,18 +284,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
           if (lane == 0) mbar_arrive(&s_done[s]);  // S is in registers: the MMA warp may overwrite the buffer
           if (tail) {
 #pragma unroll
-            for (int e = 0; e < 64; ++e)
+            for (int e = 0; e < 32; ++e)
               if (j0 + e >= ncols) sv[e] = -INFINITY;
           }
           float mx = sv[0];
 #pragma unroll
-          for (int e = 1; e < 64; ++e) mx = fmaxf(mx, sv[e]);
-          // alpha > 0: max commutes with the scale.  All-masked half (j0 >= ncols): mx = -inf, contributes nothing.
+          for (int e = 1; e < 32; ++e) mx = fmaxf(mx, sv[e]);
+          // alpha > 0: max commutes with the scale.  All-masked quarter (j0 >= ncols): mx = -inf, contributes nothing.
           const float m_new = fmaxf(m_run, mx * c2);
           if (m_new > -INFINITY) {
             float sum = 0.f;
 #pragma unroll
-            for (int e = 0; e < 64; ++e) sum += fast_exp2(fmaf(sv[e], c2, -m_new));
+            for (int e = 0; e < 32; ++e) sum += fast_exp2(fmaf(sv[e], c2, -m_new));
             l_run = l_run * fast_exp2(m_run - m_new) + sum;
             m_run = m_new;
           }
@@ -306,34 +303,41 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_done[s]);
+          // scores of this chunk in the reference's association (log_softmax_row + log_softmax_col) + (lsig0 + lsig1);
+          // dir 1 sees the same element with "mine" and "other" swapped, so the operands are put back in order
+          float cmax = -INFINITY;
 #pragma unroll
-          for (int e4 = 0; e4 < 16; ++e4) {
+          for (int e4 = 0; e4 < 8; ++e4) {
             const float4 lc = *reinterpret_cast<const float4*>(myvec + e4 * 4);       // other side's LSE
-            const float4 l1 = *reinterpret_cast<const float4*>(myvec + 64 + e4 * 4);  // other side's log sigmoid
+            const float4 l1 = *reinterpret_cast<const float4*>(myvec + 32 + e4 * 4);  // other side's log sigmoid
             const float lcv[4] = {lc.x, lc.y, lc.z, lc.w}, l1v[4] = {l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int e = e4 * 4 + u;
               const float x = sv[e] * a.alpha;
-              // the reference's association: (log_softmax_row + log_softmax_col) + (lsig0 + lsig1); dir 1 sees the
-              // same element with the roles of "mine" and "other" swapped, so the operands are put back in order
               const float lr = dir ? lcv[u] : lse_mine, lcc = dir ? lse_mine : lcv[u];
               const float s0 = dir ? l1v[u] : ls_mine, s1 = dir ? ls_mine : l1v[u];
               const float ab = (x - lr) + (x - lcc);
-              const float sc = ab + (s0 + s1);
-              if (!tail || j0 + e < ncols) {
-                if (sc > best) { best = sc; besti = j0 + e; }
-                if ((gw[e4] >> (8 * u)) & 0xffu) psum += ab;
-              }
+              if (gw[e4] != 0u && ((gw[e4] >> (8 * u)) & 0xffu)) psum += ab;  // almost every mask word is zero
+              float sc = ab + (s0 + s1);
+              if (tail && j0 + e >= ncols) sc = -INFINITY;
+              sv[e] = sc;
+              cmax = fmaxf(cmax, sc);
             }
+          }
+          if (cmax > best) {  // a new running maximum is rare (~ln(columns) times per row): find its first position
+            best = cmax;
+#pragma unroll
+            for (int e = 31; e >= 0; --e)
+              if (sv[e] == cmax) besti = j0 + e;
           }
         } else {  // AT_BWD
           const float two_gc = 2.f * gc;
-          uint32_t pw[32];
+          uint32_t pw[16];
 #pragma unroll
-          for (int e4 = 0; e4 < 16; ++e4) {
+          for (int e4 = 0; e4 < 8; ++e4) {
             const float4 lc = *reinterpret_cast<const float4*>(myvec + e4 * 4);
-            const float4 cc = *reinterpret_cast<const float4*>(myvec + 64 + e4 * 4);
+            const float4 cc = *reinterpret_cast<const float4*>(myvec + 32 + e4 * 4);
             const float lcv[4] = {lc.x, lc.y, lc.z, lc.w}, ccv[4] = {cc.x, cc.y, cc.z, cc.w};
             float d[4];
 #pragma unroll
@@ -347,9 +351,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
             pw[e4 * 2] = pack_bf16(d[0], d[1]);
             pw[e4 * 2 + 1] = pack_bf16(d[2], d[3]);
           }
-          // dsim (bf16, two columns per 32-bit word) over the first 32 columns of this warp's own 64 S columns
-          tmem_st16(t_lane + s * AT_C + hf * 64, pw);
-          tmem_st16(t_lane + s * AT_C + hf * 64 + 16, pw + 16);
+          // dsim (bf16, two columns per 32-bit word) over the first 16 columns of this warp's own 32 S columns
+          tmem_st16(t_lane + s * AT_C + cq * 32, pw);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
@@ -357,46 +360,56 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         }
       }
 
-      // ---- end of item: merge the two column halves (LSE / STATS) or drain the accumulator (BWD)
+      // ---- end of item: merge the four column quarters (LSE / STATS) or drain the accumulator (BWD)
       if (MODE == AT_LSE) {
-        if (hf == 1) { sMerge[r] = m_run; sMerge[128 + r] = l_run; }
+        if (cq) { sMerge[(cq - 1) * 256 + r] = m_run; sMerge[(cq - 1) * 256 + 128 + r] = l_run; }
         bar_epi();
-        if (hf == 0) {
-          float m2 = sMerge[r], l2 = sMerge[128 + r];
-          const float mn = fmaxf(m_run, m2);
-          const float l = l_run * fast_exp2(m_run - mn) + l2 * fast_exp2(m2 - mn);
+        if (cq == 0) {
+          float mn = m_run;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) mn = fmaxf(mn, sMerge[k * 256 + r]);
+          float l = l_run * fast_exp2(m_run - mn);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) l += sMerge[k * 256 + 128 + r] * fast_exp2(sMerge[k * 256 + r] - mn);
           if (rok) (dir ? a.lse_col : a.lse_row)[ro] = (mn + log2f(l)) * 0.6931471805599453f;
         }
         bar_epi();
       } else if (MODE == AT_STATS) {
-        if (hf == 1) { sMerge[r] = best; reinterpret_cast<int*>(sMerge)[128 + r] = besti; sMerge[256 + r] = psum; }
+        if (cq) {
+          sMerge[(cq - 1) * 384 + r] = best;
+          reinterpret_cast<int*>(sMerge)[(cq - 1) * 384 + 128 + r] = besti;
+          sMerge[(cq - 1) * 384 + 256 + r] = psum;
+        }
         bar_epi();
-        if (hf == 0 && rok) {
-          const float b2 = sMerge[r];
-          const int i2 = reinterpret_cast<int*>(sMerge)[128 + r];
-          if (b2 > best) { best = b2; besti = i2; }  // equal: the lower half holds the lower index
+        if (cq == 0 && rok) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {  // ascending column quarters: on equal values the earlier (lower) index stays
+            const float b2 = sMerge[k * 384 + r];
+            if (b2 > best) { best = b2; besti = reinterpret_cast<int*>(sMerge)[k * 384 + 128 + r]; }
+            psum += sMerge[k * 384 + 256 + r];
+          }
           (dir ? a.colmax : a.rowmax)[ro] = best;
           (dir ? a.colarg : a.rowarg)[ro] = besti;
-          if (!dir && a.pos_row_sum) a.pos_row_sum[ro] = psum + sMerge[256 + r];
+          if (!dir && a.pos_row_sum) a.pos_row_sum[ro] = psum;
         }
         bar_epi();
       } else {
         mbar_wait(acc_full, it & 1);
         tc_fence_after();
         __nv_bfloat16* out = (dir ? a.dmd1 : a.dmd0) + ro * D;
-        const int cpw = D / 2;  // channels per column half
+        const int cpw = D / 4;  // channels per column quarter
 #pragma unroll 1
-        for (int c = 0; c < cpw; c += 32) {
-          float v[32];
-          tmem_ld32(t_lane + AT_ACC_COL + hf * cpw + c, v);
+        for (int c = 0; c < cpw; c += 16) {
+          float v[16];
+          tmem_ld16(t_lane + AT_ACC_COL + cq * cpw + c, v);
           tmem_ld_wait();
           if (rok) {
 #pragma unroll
-            for (int e8 = 0; e8 < 4; ++e8) {
+            for (int e8 = 0; e8 < 2; ++e8) {
               uint4 u;
               u.x = pack_bf16(v[e8 * 8], v[e8 * 8 + 1]); u.y = pack_bf16(v[e8 * 8 + 2], v[e8 * 8 + 3]);
               u.z = pack_bf16(v[e8 * 8 + 4], v[e8 * 8 + 5]); u.w = pack_bf16(v[e8 * 8 + 6], v[e8 * 8 + 7]);
-              *reinterpret_cast<uint4*>(out + hf * cpw + c + e8 * 8) = u;
+              *reinterpret_cast<uint4*>(out + cq * cpw + c + e8 * 8) = u;
             }
           }
         }

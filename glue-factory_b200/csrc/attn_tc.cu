@@ -769,9 +769,399 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
   if (warp == F3_SWARPS + 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// BACKWARD, fused single pass (round 2).  The two-kernel backward above recomputes S and dP in both kernels
+// (14 GEMM-units for 10 algorithmic) and evaluates every exponential twice.  Here one CTA owns 128 keys (K, V rows
+// resident in TMEM exactly as in the dKV kernel) and walks the queries in tiles of 64:
+//     S^T  = K Q_i^T,  dP^T = V dO_i^T            (128 x 64, TS MMAs, double-buffered in TMEM)
+//     P^T  = exp2(c S^T - lse_i),  dS^T = P^T (dP^T - delta_i) scale       (softmax warps, thread == key row)
+//     dV  += P^T dO_i,   dK += dS^T Q_i           (TS MMAs, P^T / dS^T written in place over S^T / dP^T)
+// and additionally, once per PAIR of query tiles,
+//     dQ_pair (128 queries x 64) = dS_pair K      (M = 128: both operands MN-major from shared memory)
+// where dS_pair is the bf16 copy of dS^T the softmax warps also leave in shared memory ([key][query], 128-byte
+// swizzled: read with M = query it is the MN-major A operand).  dQ_pair is drained TMEM -> swizzled smem -> global by a
+// TMA REDUCE-ADD into an fp32 accumulation buffer (the 16 key-tile CTAs of one (batch, head) add into the same rows; they
+// are adjacent in the grid, so the buffer lives in L2), converted to bf16 by a last small kernel.
+// Per 128 x 128 block: 2 x (5+5) S/dP + 2 x (4+4) dV/dK + 8 dQ MMAs and ONE exponential per element, against
+// 2 x (5+5+4+4) + 2 x (4+4+4) MMAs and two exponentials in the two-kernel version.  lse / delta per query are per-COLUMN
+// values here; they come as two 64-float vectors with every query tile (bulk copies into the stage) and are read as
+// shared-memory broadcasts (the dKV kernel folds them into the contraction instead, which costs 16 more TMEM columns
+// than this kernel has left).  Summation order of dQ across key tiles is not fixed (fp32 adds in L2).
+// TMEM: K [0,32) V [32,64) | buffer b: S^T at 64+b*128, dP^T at 128+b*128 | dV [320,384) dK [384,448) dQ [448,512).
+// ---------------------------------------------------------------------------------------------
+constexpr int FF_STAGES = 4;
+constexpr int FF_STAGE_BYTES = 17 * 1024;                 // Q 8 KiB | dO 8 KiB | lse2 256 B | delta 256 B (| pad)
+constexpr int FF_DSBYTES = 2 * FB_R * 128;                // one pair of 64-query chunks: 128 key rows x 128 B each
+constexpr int FF_DQBYTES = FB_R * FA_D * 4;               // fp32 staging of a dQ pair (two 32-float halves)
+constexpr int FF_OFF_STAGE = FB_R * FA_D * 2;             // after the resident K tile (16 KiB)
+constexpr int FF_OFF_DS = FF_OFF_STAGE + FF_STAGES * FF_STAGE_BYTES;
+constexpr int FF_OFF_DQ = FF_OFF_DS + 2 * FF_DSBYTES;
+constexpr int FF_SMEM = FF_OFF_DQ + FF_DQBYTES + 256;
+constexpr int FF_A0 = 0, FF_A1 = 32, FF_BUF0 = 64, FF_DV = 320, FF_DK = 384, FF_DQ = 448;
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bar_softmax() { asm volatile("bar.sync 2, %0;" ::"n"(F3_SWARPS * 32) : "memory"); }
+
+// delta = rowsum(dout * out); lse2 = lse * log2(e); both written token-tile padded: [B*H][nq_pad] with +inf / 0 in the pad
+__global__ void __launch_bounds__(256)
+    attn_bwd_prep_fused_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                               const float* __restrict__ lse, float* __restrict__ lse2p, float* __restrict__ deltap,
+                               int64_t nrows_pad /* B * nq_pad * H */, int N, int nq_pad, int H) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = gid >> 3;  // (b, n_pad, h)
+  const int sub = (int)(gid & 7);
+  const bool live = r < nrows_pad;  // no early return: the shuffles below are full-warp
+  const int64_t rr = live ? r : 0;
+  const int h = (int)(rr % H);
+  const int64_t bn = rr / H;
+  const int n = (int)(bn % nq_pad);
+  const int64_t b = bn / nq_pad;
+  float acc = 0.f;
+  if (live && n < N) {
+    const int64_t src = ((b * N + n) * H + h) * FA_D + sub * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(out + src);
+    const uint4 g = *reinterpret_cast<const uint4*>(dout + src);
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pg = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __bfloat1622float2(pa[e]), fg = __bfloat1622float2(pg[e]);
+      acc = fmaf(fa.x, fg.x, acc);
+      acc = fmaf(fa.y, fg.y, acc);
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (live && sub == 0) {
+    const int64_t o = (b * H + h) * nq_pad + n;
+    deltap[o] = n < N ? acc : 0.f;
+    lse2p[o] = n < N ? lse[(b * H + h) * N + n] * 1.4426950408889634f : INFINITY;  // pad: p = exp2(-inf) = 0
+  }
+}
+
+__global__ void __launch_bounds__(256) dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq,
+                                                        int64_t n8) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = reinterpret_cast<const float4*>(acc)[2 * i], b = reinterpret_cast<const float4*>(acc)[2 * i + 1];
+  uint4 u;
+  u.x = pack_bf16(a.x, a.y); u.y = pack_bf16(a.z, a.w); u.z = pack_bf16(b.x, b.y); u.w = pack_bf16(b.z, b.w);
+  reinterpret_cast<uint4*>(dq)[i] = u;
+}
+
+__global__ void __launch_bounds__(F3_THREADS, 1)
+    attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                          const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmDQ,
+                          const __nv_bfloat16* __restrict__ kg, const __nv_bfloat16* __restrict__ vg,
+                          const float* __restrict__ lse2p, const float* __restrict__ deltap,
+                          __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int B, int Nq, int nq_pad, int Nk,
+                          int H, int kv_shift, float scale, float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sStage = smem + FF_OFF_STAGE;
+  uint8_t* sDS = smem + FF_OFF_DS;
+  uint8_t* sDQ = smem + FF_OFF_DQ;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FF_OFF_DQ + FF_DQBYTES);
+  uint64_t* k_full = bars;
+  uint64_t* a_ready = bars + 1;
+  uint64_t* in_full = bars + 2;               // [FF_STAGES]
+  uint64_t* in_empty = in_full + FF_STAGES;   // [FF_STAGES]
+  uint64_t* sp_full = in_empty + FF_STAGES;   // [2]
+  uint64_t* pds_full = sp_full + 2;           // [2]
+  uint64_t* ds_free = pds_full + 2;           // [2]  MMA 5 of the pair that used sDS[b] has read it
+  uint64_t* dq_full = ds_free + 2;
+  uint64_t* dq_empty = dq_full + 1;
+  uint64_t* acc_done = dq_empty + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * FB_R, h = blockIdx.y, kb = blockIdx.z;
+  const int qb = ((kb - kv_shift) % B + B) % B;
+  const int ntiles = (Nq + FB_C - 1) / FB_C;
+  const int npairs = (ntiles + 1) >> 1;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(k_full, 1);
+    mbar_init(a_ready, F3_SWARPS);
+    for (int s = 0; s < FF_STAGES; ++s) {
+      mbar_init(&in_full[s], 1);
+      mbar_init(&in_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sp_full[s], 1);
+      mbar_init(&pds_full[s], F3_SWARPS);
+      mbar_init(&ds_free[s], 1);
+    }
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, F3_SWARPS);
+    mbar_init(acc_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == F3_SWARPS && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmDQ);
+  }
+  if (warp == F3_SWARPS + 1) tmem_alloc(tmem_slot, FB_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == F3_SWARPS) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(k_full, FB_R * FA_D * 2);
+      tma_load_4d(sK, &tmK, k_full, 0, h, k0, kb);
+      const float* l2 = lse2p + ((int64_t)qb * H + h) * nq_pad;
+      const float* dl = deltap + ((int64_t)qb * H + h) * nq_pad;
+      for (int i = 0; i < ntiles; ++i) {
+        const int s = i % FF_STAGES;
+        uint8_t* st = sStage + s * FF_STAGE_BYTES;
+        mbar_wait(&in_empty[s], ((i / FF_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&in_full[s], 2 * FB_CBYTES + 512);
+        tma_load_4d(st, &tmQ, &in_full[s], 0, h, i * FB_C, qb);
+        tma_load_4d(st + FB_CBYTES, &tmDO, &in_full[s], 0, h, i * FB_C, qb);
+        bulk_load_1d(st + 2 * FB_CBYTES, l2 + i * FB_C, 256, &in_full[s]);
+        bulk_load_1d(st + 2 * FB_CBYTES + 256, dl + i * FB_C, 256, &in_full[s]);
+      }
+    }
+  } else if (warp == F3_SWARPS + 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-convergent, elected lane)
+    constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (K|V) in TMEM x (Q|dO) K-major
+    constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // (P^T|dS^T) in TMEM x (dO|Q) MN-major
+    constexpr uint32_t idesc_dq = make_idesc_bf16(FB_R, FA_D, 1, 1);   // dS_pair (smem, MN-major) x K (smem, MN-major)
+    const uint64_t dstK = make_smem_desc(smem_u32(sStage), 16, 1024);    // K-major view of a stage's tiles
+    const uint64_t dstM = make_smem_desc(smem_u32(sStage), 8192, 1024);  // MN-major view
+    const uint64_t dDS = make_smem_desc(smem_u32(sDS), FB_R * 128, 1024);  // two 64-query chunks 16 KiB apart
+    const uint64_t dKm = make_smem_desc(smem_u32(sK), 8192, 1024);
+    const bool leader = elect_one();
+    auto issue_sp = [&](int i) {
+      const int s = i % FF_STAGES;
+      mbar_wait(&in_full[s], (i / FF_STAGES) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t tb = tmem_base + FF_BUF0 + (i & 1) * 128;
+        const uint64_t so = (uint64_t)((s * FF_STAGE_BYTES) >> 4);
+        const uint64_t tq = dstK + so, tdo = dstK + so + (FB_CBYTES >> 4);
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16_ts(tb, tmem_base + FF_A0 + kk * 8, tq + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < FA_D / 16; ++kk)
+          umma_bf16_ts(tb + 64, tmem_base + FF_A1 + kk * 8, tdo + (uint64_t)(kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(&sp_full[i & 1]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(a_ready, 0);
+    mbar_wait(k_full, 0);
+    tc_fence_after();
+    issue_sp(0);
+    if (ntiles > 1) issue_sp(1);
+    for (int i = 0; i < ntiles; ++i) {
+      const int s = i % FF_STAGES;
+      mbar_wait(&pds_full[i & 1], (i >> 1) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t tb = tmem_base + FF_BUF0 + (i & 1) * 128;
+        const uint64_t so = (uint64_t)((s * FF_STAGE_BYTES) >> 4);
+        const uint64_t mq = dstM + so, mdo = dstM + so + (FB_CBYTES >> 4);
+#pragma unroll
+        for (int kk = 0; kk < FB_C / 16; ++kk)  // warpgroup kk wrote P^T of queries [kk*16, +16) at S^T column kk*16
+          umma_bf16_ts(tmem_base + FF_DV, tb + kk * F3_CW, mdo + (uint64_t)(kk * 128), idesc_acc, (i | kk) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < FB_C / 16; ++kk)
+          umma_bf16_ts(tmem_base + FF_DK, tb + 64 + kk * F3_CW, mq + (uint64_t)(kk * 128), idesc_acc,
+                       (i | kk) != 0 ? 1u : 0u);
+        umma_commit(&in_empty[s]);
+      }
+      __syncwarp();
+      if ((i & 1) || i == ntiles - 1) {  // the pair is complete: dQ_pair = dS_pair K
+        const int pr = i >> 1;
+        mbar_wait(dq_empty, (pr & 1) ^ 1);  // the softmax warps drained the previous pair's dQ
+        tc_fence_after();
+        if (leader) {
+          const uint64_t da = dDS + (uint64_t)(((pr & 1) * FF_DSBYTES) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < FB_R / 16; ++kk)  // 16 keys per step: 16 rows of 128 B in both operands
+            umma_bf16(tmem_base + FF_DQ, da + (uint64_t)(kk * 128), dKm + (uint64_t)(kk * 128), idesc_dq, kk != 0 ? 1u : 0u);
+          umma_commit(dq_full);
+          umma_commit(&ds_free[pr & 1]);
+        }
+        __syncwarp();
+      }
+      if (i + 2 < ntiles) issue_sp(i + 2);
+    }
+    if (leader) umma_commit(acc_done);
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax warps
+    const int c = warp >> 2;                 // 16-query column slice handled by this warpgroup
+    const int r = (warp & 3) * 32 + lane;    // key row within the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const int row = k0 + r;
+    {  // resident A operands: this thread's 16-channel slice of its K and V rows -> TMEM
+      const int64_t o = (((int64_t)kb * Nk + (row < Nk ? row : 0)) * H + h) * FA_D + c * F3_CW;
+      load_row_part_to_tmem(kg + o, row < Nk, t_lane + FF_A0 + c * (F3_CW / 2));
+      load_row_part_to_tmem(vg + o, row < Nk, t_lane + FF_A1 + c * (F3_CW / 2));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    }
+    // drain of one dQ pair: TMEM -> swizzled fp32 staging -> TMA reduce-add into the accumulation buffer
+    auto drain_dq = [&](int pr) {
+      mbar_wait(dq_full, pr & 1);
+      tc_fence_after();
+      float v[16];
+      tmem_ld16(t_lane + FF_DQ + c * F3_CW, v);  // row r is QUERY r of the pair here; this warpgroup's 16 channels
+      tmem_ld_wait();
+      tc_fence_before();
+      if (threadIdx.x == 0) tma_store_wait_read<0>();  // the previous pair's reduce has read the staging block
+      bar_softmax();
+      if (lane == 0) mbar_arrive(dq_empty);             // dQ columns are free for the next pair's MMAs
+      // staging: two halves (channels 0-31 / 32-63), each 128 rows x 128 B, 16-byte chunks XOR-swizzled by the row
+      uint8_t* half = sDQ + (c >> 1) * (FB_R * 128) + r * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int chunk = (c & 1) * 4 + j;
+        *reinterpret_cast<float4*>(half + ((chunk ^ (r & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      fence_proxy_async_smem();
+      bar_softmax();
+      if (threadIdx.x == 0) {
+        tma_reduce_add_4d(&tmDQ, sDQ, 0, h, pr * FB_R, qb);
+        tma_reduce_add_4d(&tmDQ, sDQ + FB_R * 128, 32, h, pr * FB_R, qb);
+        tma_store_commit();
+      }
+    };
+    for (int i = 0; i < ntiles; ++i) {
+      const int buf = i & 1, pr = i >> 1, s = i % FF_STAGES;
+      const uint32_t tb = t_lane + FF_BUF0 + buf * 128;
+      const float* sl = reinterpret_cast<const float*>(sStage + s * FF_STAGE_BYTES + 2 * FB_CBYTES) + c * F3_CW;
+      mbar_wait(&in_full[s], (i / FF_STAGES) & 1);  // the side vectors of this tile (bulk copies) are visible to this thread
+      mbar_wait(&sp_full[buf], (i >> 1) & 1);
+      tc_fence_after();
+      float sv[F3_CW], dp[F3_CW];
+      tmem_ld16(tb + c * F3_CW, sv);
+      tmem_ld16(tb + 64 + c * F3_CW, dp);
+      float l2[F3_CW], dl[F3_CW];
+#pragma unroll
+      for (int e4 = 0; e4 < F3_CW / 4; ++e4) {  // same addresses in every lane: shared-memory broadcasts
+        const float4 a = *reinterpret_cast<const float4*>(sl + e4 * 4);
+        const float4 b = *reinterpret_cast<const float4*>(sl + 64 + e4 * 4);
+        l2[e4 * 4] = a.x; l2[e4 * 4 + 1] = a.y; l2[e4 * 4 + 2] = a.z; l2[e4 * 4 + 3] = a.w;
+        dl[e4 * 4] = b.x; dl[e4 * 4 + 1] = b.y; dl[e4 * 4 + 2] = b.z; dl[e4 * 4 + 3] = b.w;
+      }
+      tmem_ld_wait();
+      uint32_t pw[F3_CW / 2], dw[F3_CW / 2];
+#pragma unroll
+      for (int e = 0; e < F3_CW; e += 2) {
+        const float p0 = fast_exp2(fmaf(sv[e], scale_log2, -l2[e]));
+        const float p1 = fast_exp2(fmaf(sv[e + 1], scale_log2, -l2[e + 1]));
+        pw[e >> 1] = pack_bf16(p0, p1);
+        dw[e >> 1] = pack_bf16(p0 * (dp[e] - dl[e]) * scale, p1 * (dp[e + 1] - dl[e + 1]) * scale);
+      }
+      tmem_st8(tb + c * F3_CW, pw);        // P^T over the S^T columns this warpgroup just consumed
+      tmem_st8(tb + 64 + c * F3_CW, dw);   // dS^T over the dP^T columns
+      // bf16 dS also goes to shared memory, [key][query] (row = this thread's key), for the dQ MMA of the pair
+      if (buf == 0 && pr >= 2) mbar_wait(&ds_free[pr & 1], ((pr >> 1) & 1) ^ 1);  // pair pr-2 has been consumed
+      {
+        uint8_t* rowp = sDS + (pr & 1) * FF_DSBYTES + buf * (FB_R * 128) + r * 128;
+        *reinterpret_cast<uint4*>(rowp + (((2 * c) ^ (r & 7)) << 4)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+        *reinterpret_cast<uint4*>(rowp + (((2 * c + 1) ^ (r & 7)) << 4)) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+      }
+      fence_proxy_async_smem();
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pds_full[buf]);
+      if (buf == 0 && pr >= 1) drain_dq(pr - 1);  // the previous pair's dQ MMAs ran under this tile's exponentials
+    }
+    drain_dq(npairs - 1);
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    const int64_t o = (((int64_t)kb * Nk + (row < Nk ? row : 0)) * H + h) * FA_D + c * F3_CW;
+    store_out_cols16(dv + o, t_lane + FF_DV + c * F3_CW, row < Nk);
+    store_out_cols16(dk + o, t_lane + FF_DK + c * F3_CW, row < Nk);
+    if (threadIdx.x == 0) tma_store_wait_all();  // the last reduce must have left shared memory before the CTA exits
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == F3_SWARPS + 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
+}
+
+// workspace of the fused backward, in floats: lse2 / delta padded to whole query tiles + the fp32 dQ accumulator
+static int64_t attn_bwd_fused_ws_floats(int B, int Nq, int H) {
+  const int64_t nq_pad = (int64_t)((Nq + FB_C - 1) / FB_C) * FB_C;
+  return 2 * (int64_t)B * H * nq_pad + (int64_t)B * Nq * H * FA_D + 64;
+}
+
+static int attn_bwd_fused(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
+                          void* dq, void* dk, void* dv, float* ws, int B, int Nq, int Nk, int H, int kv_shift, float scale,
+                          cudaStream_t stream) {
+  const int nq_pad = (Nq + FB_C - 1) / FB_C * FB_C;
+  float* lse2p = ws;
+  float* deltap = lse2p + (int64_t)B * H * nq_pad;
+  float* dqacc = deltap + (int64_t)B * H * nq_pad;
+  dqacc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dqacc) + 255) & ~(uintptr_t)255);
+  int rc;
+  {
+    const int64_t nrows = (int64_t)B * nq_pad * H;
+    attn_bwd_prep_fused_kernel<<<(unsigned)((nrows * 8 + 255) / 256), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), lse, lse2p, deltap, nrows, Nq,
+        nq_pad, H);
+  }
+  const size_t acc_bytes = (size_t)B * Nq * H * FA_D * 4;
+  cudaError_t e = cudaMemsetAsync(dqacc, 0, acc_bytes, stream);
+  LGB_REQUIRE(e == cudaSuccess, kErrCuda, "attn_bwd(fused): memset: %s", cudaGetErrorString(e));
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_fused_kernel), FF_SMEM))) return rc;
+  CUtensorMap tq, tdo, tk, tdq;
+  if ((rc = make_qkv_tmap(&tq, q, B, Nq, H, FB_C))) return rc;
+  if ((rc = make_qkv_tmap(&tdo, dout, B, Nq, H, FB_C))) return rc;
+  if ((rc = make_qkv_tmap(&tk, k, B, Nk, H, FB_R))) return rc;
+  {
+    const uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)Nq, (uint64_t)B};
+    const uint64_t str[3] = {64 * 4, (uint64_t)H * 64 * 4, (uint64_t)Nq * H * 64 * 4};
+    const uint32_t box[4] = {32, 1, (uint32_t)FB_R, 1};
+    if ((rc = make_tmap(&tdq, dqacc, /*fp32=*/true, 4, dims, str, box))) return rc;
+  }
+  const float sl2 = scale * 1.4426950408889634f;
+  attn_bwd_fused_kernel<<<dim3((Nk + FB_R - 1) / FB_R, H, B), F3_THREADS, FF_SMEM, stream>>>(
+      tq, tdo, tk, tdq, static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v), lse2p, deltap,
+      static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv), B, Nq, nq_pad, Nk, H, kv_shift, scale, sl2);
+  if ((rc = check_launch("attn_bwd_fused"))) return rc;
+  const int64_t n8 = (int64_t)B * Nq * H * FA_D / 8;
+  dq_convert_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(dqacc, static_cast<__nv_bfloat16*>(dq), n8);
+  return check_launch("attn_bwd_fused(convert)");
+}
+
+int64_t attn_bwd_ws_floats(int B, int Nq, int Nk, int H) {
+  const int64_t two_kernel = 17 * (((int64_t)B * H * Nq + 3) / 4 * 4);
+  const int64_t fused = attn_bwd_fused_ws_floats(B, Nq, H);
+  return two_kernel > fused ? two_kernel : fused;
+}
+
 int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
                 void* dq, void* dk, void* dv, float* delta, int B, int Nq, int Nk, int H, int kv_shift, float scale,
                 cudaStream_t stream) {
+  static const bool fused = !env_flag("LGB200_ATTN_BWD_TWO_KERNEL");  // default: the fused single-pass backward
+  if (fused) return attn_bwd_fused(q, k, v, out, lse, dout, dq, dk, dv, delta, B, Nq, Nk, H, kv_shift, scale, stream);
   // workspace: delta [B*H*Nq] fp32, then the dKV side arrays qx, dox [B*H*Nq, 16] bf16 (16-byte aligned)
   const int64_t nq_all = ((int64_t)B * H * Nq + 3) & ~(int64_t)3;
   __nv_bfloat16* qx = reinterpret_cast<__nv_bfloat16*>(delta + nq_all);

@@ -36,4 +36,7 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, co
                 void* dq, void* dk, void* dv, float* delta, int B, int Nq, int Nk, int H, int kv_shift, float scale,
                 cudaStream_t stream);
 
+// scratch (floats) lgb200_attn_bwd needs for the bf16 path: max over the two-kernel and the fused backward
+int64_t attn_bwd_ws_floats(int B, int Nq, int Nk, int H);
+
 }  // namespace lgb

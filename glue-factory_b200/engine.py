@@ -42,11 +42,12 @@ def _dgrad(dy, W):
     return torch.mm(dy, W)
 
 
-def _wgrad(dy, a):
-    """dW [out, in] fp32 = dy^T a for compute-dtype dy [T, out], a [T, in] (row-strided views allowed)."""
+def _wgrad(dy, a, out=None):
+    """dW [out, in] fp32 = dy^T a for compute-dtype dy [T, out], a [T, in] (row-strided views allowed); `out`: write
+    straight into this fp32 view (a parameter's slot of the trainer's flat gradient buffer)."""
     if dy.dtype == torch.float32:
-        return torch.mm(dy.t(), a)
-    return ops.wgrad_bf16(dy, a)
+        return torch.mm(dy.t(), a) if out is None else torch.mm(dy.t(), a, out=out)
+    return ops.wgrad_bf16(dy, a, out=out)
 
 
 def _bgrad(dy):
@@ -118,7 +119,11 @@ _LN_SLOTS = (6, 7, 18, 19)  # LayerNorm affine stays fp32
 
 class LayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, theta, sizes, H, cdt, eps, w, *params):
+    def forward(ctx, x, theta, sizes, H, cdt, eps, w, sink, *params):
+        """sink: None, or (flat-parameter object, group index) of a trainer that owns a flat gradient buffer: the
+        backward then writes this layer's 22 parameter gradients straight into their slots of that buffer (weight
+        gradients as the GEMM output, no per-parameter copy) and tells the trainer the slice is final, so its
+        all-reduce can start while the earlier layers are still in backward."""
         (Wqkv, bqkv, Wo, bo, W0, b0, g1, be1, W3, b3,
          Wqk, bqk, Wv, bv, Wout, bout, W0c, b0c, g2, be2, W3c, b3c) = w
         if cdt == torch.bfloat16:  # biases are added in fp32 in the GEMM epilogue: take the master parameters
@@ -157,6 +162,7 @@ class LayerFn(torch.autograd.Function):
         ctx.save_for_backward(theta, cat1, q, k, v, att, h, mean1, rstd1, g, cat2, qk, vv, m, h2, mean2,
                               rstd2, gg, *lse1, *lse2, *w)
         ctx.meta = (sizes, H, cdt, len(lse1), len(lse2), D)
+        ctx.sink = sink
         return x2
 
     @staticmethod
@@ -169,43 +175,50 @@ class LayerFn(torch.autograd.Function):
         (Wqkv, bqkv, Wo, bo, W0, b0, g1, be1, W3, b3,
          Wqk, bqk, Wv, bv, Wout, bout, W0c, b0c, g2, be2, W3c, b3c) = sv[18 + n1 + n2:]
         dx = dx.contiguous()
+        gv = ctx.sink[0].direct_views(ctx.sink[1]) if ctx.sink is not None else [None] * 22  # LAYER_PARAMS order
         # ---- cross block
         dy2 = dx.to(cdt)
-        dW3c, db3c = _wgrad(dy2, gg), _bgrad(dy2)
+        dW3c, db3c = _wgrad(dy2, gg, gv[20]), _bgrad(dy2)
         dgg = _dgrad(dy2, W3c)
         dh2, dg2, dbe2, db0c = ops.ln_gelu_bwd(dgg, h2, g2, be2, mean2, rstd2, want_dxsum=True)
         del dgg
-        dW0c = _wgrad(dh2, cat2)
+        dW0c = _wgrad(dh2, cat2, gv[16])
         dmsg2 = _dgrad(dh2, W0c[:, D:])
         dx1 = _dgrad_acc(dx, dh2, W0c[:, :D])  # fp32 accumulation of the residual-stream gradient
         del dh2
-        dWout, dbout = _wgrad(dmsg2, m), _bgrad(dmsg2)
+        dWout, dbout = _wgrad(dmsg2, m, gv[14]), _bgrad(dmsg2)
         dm = _dgrad(dmsg2, Wout)
         dq_, dk_, dvv = _attend_bwd(qk, qk, vv, m, lse2, dm, sizes, H, cross=True)
         dqk = dq_.add_(dk_)  # the shared to_qk projection is query in one direction and key in the other
-        dWqk, dbqk = _wgrad(dqk, x1_16), _bgrad(dqk)
-        dWv, dbv = _wgrad(dvv, x1_16), _bgrad(dvv)
+        dWqk, dbqk = _wgrad(dqk, x1_16, gv[10]), _bgrad(dqk)
+        dWv, dbv = _wgrad(dvv, x1_16, gv[12]), _bgrad(dvv)
         dx1 = _dgrad_acc(dx1, dqk, Wqk)
         dx1 = _dgrad_acc(dx1, dvv, Wv)
         # ---- self block
         dy = dx1.to(cdt)
-        dW3, db3 = _wgrad(dy, g), _bgrad(dy)
+        dW3, db3 = _wgrad(dy, g, gv[8]), _bgrad(dy)
         dg = _dgrad(dy, W3)
         dh, dg1, dbe1, db0 = ops.ln_gelu_bwd(dg, h, g1, be1, mean1, rstd1, want_dxsum=True)
         del dg
-        dW0 = _wgrad(dh, cat1)
+        dW0 = _wgrad(dh, cat1, gv[4])
         dmsg = _dgrad(dh, W0[:, D:])
         dx0 = _dgrad_acc(dx1, dh, W0[:, :D])
         del dh
-        dWo, dbo = _wgrad(dmsg, att), _bgrad(dmsg)
+        dWo, dbo = _wgrad(dmsg, att, gv[2]), _bgrad(dmsg)
         datt = _dgrad(dmsg, Wo)
         dq, dk, dv = _attend_bwd(q, k, v, att, lse1, datt, sizes, H, cross=False)
         dqkv, dtheta = ops.rope_bwd(dq, dk, dv, q, k, theta, H)
-        dWqkv, dbqkv = _wgrad(dqkv, x16), _bgrad(dqkv)
+        dWqkv, dbqkv = _wgrad(dqkv, x16, gv[0]), _bgrad(dqkv)
         dx0 = _dgrad_acc(dx0, dqkv, Wqkv)
         grads = (dWqkv, dbqkv, dWo, dbo, dW0, db0, dg1, dbe1, dW3, db3,
                  dWqk, dbqk, dWv, dbv, dWout, dbout, dW0c, db0c, dg2, dbe2, dW3c, db3c)
-        return (dx0, dtheta, None, None, None, None, None) + grads
+        if ctx.sink is not None:
+            # the nine weight gradients are already in place; the 13 vectors go in with one multi-tensor copy
+            small = [i for i in range(22) if grads[i].data_ptr() != gv[i].data_ptr()]
+            torch._foreach_copy_([gv[i] for i in small], [grads[i].view_as(gv[i]) for i in small])
+            ctx.sink[0].chunk_ready(ctx.sink[1])
+            grads = (None,) * 22
+        return (dx0, dtheta, None, None, None, None, None, None) + grads
 
 
 class HeadFn(torch.autograd.Function):

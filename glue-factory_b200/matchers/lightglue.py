@@ -317,8 +317,10 @@ class LightGlue(nn.Module):
         for i in range(L):
             if fused:
                 w, params = self._layer_weights(i)
+                fp = getattr(self, "_b200_flat", None)
+                sink = (fp, i) if (fp is not None and fp.direct_groups and torch.is_grad_enabled()) else None
                 x = engine.LayerFn.apply(x, theta, sizes, conf.num_heads, self._cdt, self.transformers[i].self_attn.ffn[1].eps,
-                                         w, *params)
+                                         w, sink, *params)
             else:
                 x = self._layer(x, theta, self.transformers[i], sizes)
             if self.training or i == L - 1:

@@ -94,7 +94,7 @@ def attn_bwd(q, k, v, out, lse, dout, kv_shift, scale):
     Nk = k.shape[1]
     dout = dout.contiguous()
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-    delta = torch.empty(17 * ((B * H * Nq + 3) // 4 * 4), device=q.device, dtype=torch.float32)  # see lgb200.h
+    delta = torch.empty(_lib.load().lgb200_attn_bwd_ws_floats(B, Nq, Nk, H), device=q.device, dtype=torch.float32)
     call("lgb200_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(dout), ptr(dq), ptr(dk), ptr(dv),
          ptr(delta), B, Nq, Nk, H, kv_shift, float(scale), _code(q.dtype), stream_ptr())
     return dq, dk, dv

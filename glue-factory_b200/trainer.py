@@ -52,7 +52,52 @@ class FlatParams:
         self.flat16 = None
         self._views16 = None
         self.grad_views = [self.grad[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
+        # "direct" parameter groups: their gradients are written into the flat buffer by the backward kernels themselves
+        # (engine.LayerFn) and each group's slice is exchanged as soon as it is final (see enable_direct)
+        self.direct_groups = []
+        self._direct_ids = set()
+        self.world, self.group, self._pending = 1, None, []
         module._b200_flat = self
+
+    def enable_direct(self, groups):
+        """groups: lists of parameters, each list contiguous in the flat buffer (e.g. one transformer layer)."""
+        index = {id(p): i for i, p in enumerate(self.params)}
+        for params in groups:
+            idx = [index[id(p)] for p in params]
+            assert idx == list(range(idx[0], idx[0] + len(idx))), "a direct group must be contiguous in the flat buffer"
+            lo = self.offsets[idx[0]]
+            hi = self.offsets[idx[-1] + 1] if idx[-1] + 1 < len(self.params) else self.numel
+            self.direct_groups.append((lo, hi, [self.grad_views[i] for i in idx]))
+            self._direct_ids.update(id(p) for p in params)
+        for p, v in zip(self.params, self.grad_views):
+            if id(p) in self._direct_ids:
+                p.grad = v
+
+    def direct_views(self, gi):
+        return self.direct_groups[gi][2]
+
+    def chunk_ready(self, gi):
+        """Called from backward when group gi's gradients are final: start its all-reduce now (it overlaps the backward
+        of the layers below); `finish_exchange` waits for all of them."""
+        if self.world > 1:
+            lo, hi, _ = self.direct_groups[gi]
+            self._pending.append((lo, hi, dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
+                                                          async_op=True)))
+
+    def finish_exchange(self):
+        """All-reduce whatever the per-group exchanges did not cover (the head / encoding parameters and the loss slot
+        behind the gradients), then wait for every outstanding chunk."""
+        if self.world > 1:
+            covered = sorted((lo, hi) for lo, hi, _ in self._pending)  # the slices whose exchange is already in flight
+            pos, total = 0, self.grad_ext.numel()
+            for lo, hi in covered + [(total, total)]:
+                if lo > pos:
+                    self._pending.append((pos, lo, dist.all_reduce(self.grad_ext[pos:lo], op=dist.ReduceOp.SUM,
+                                                                   group=self.group, async_op=True)))
+                pos = max(pos, hi)
+            for _, _, w in self._pending:
+                w.wait()
+        self._pending = []
 
     def shadow_bf16(self):
         """name -> bf16 view of the parameter, refreshed from the fp32 master copy by ONE cast kernel."""
@@ -83,12 +128,14 @@ class FlatParams:
     def zero_grad(self):
         """Detach the .grad views: autograd then hands each freshly computed gradient over by reference
         (no per-parameter accumulate kernel); `gather_grads` packs them into the flat buffer."""
-        for p in self.params:
-            p.grad = None
+        for p, v in zip(self.params, self.grad_views):
+            p.grad = v if id(p) in self._direct_ids else None  # direct groups are overwritten in place by backward
+        self._pending = []
 
     def gather_grads(self):
-        have = [(v, p.grad) for v, p in zip(self.grad_views, self.params) if p.grad is not None]
-        missing = [v for v, p in zip(self.grad_views, self.params) if p.grad is None]
+        rest = [(v, p) for v, p in zip(self.grad_views, self.params) if id(p) not in self._direct_ids]
+        have = [(v, p.grad) for v, p in rest if p.grad is not None]
+        missing = [v for v, p in rest if p.grad is None]
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
         if missing:
@@ -125,6 +172,10 @@ class MatcherTrainer:
         self.betas, self.eps, self.wd = betas, eps, weight_decay
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.fp.world, self.fp.group = self.world, process_group
+        layers = getattr(model, "transformers", None)
+        if layers is not None and getattr(getattr(model, "conf", None), "engine", None) == "fused":
+            self.fp.enable_direct([list(layer.parameters()) for layer in layers])
         self._lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
         self._t_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self._found_inf = torch.zeros(1, device=dev, dtype=torch.float32)
@@ -158,9 +209,10 @@ class MatcherTrainer:
         return None if self._scale_dev is None else float(self._scale_dev.item())
 
     def exchange_gradients(self):
-        """The ONE collective of the step: sum-all-reduce of the flat gradient buffer (+ the loss slot)."""
-        if self.world > 1:
-            dist.all_reduce(self.fp.grad_ext, op=dist.ReduceOp.SUM, group=self.group)
+        """The path's one exchange: the sum-all-reduce of the flat gradient buffer (+ the loss slot), issued in slices --
+        each transformer layer's slice as soon as its backward has written it (FlatParams.chunk_ready), the rest here."""
+        self.fp.world, self.fp.group = self.world, self.group
+        self.fp.finish_exchange()
 
     # ---- CUDA-graph replay of the whole step (removes the ~2500 per-step launch calls from the host)
     def capture(self, example, device, warmup=3):

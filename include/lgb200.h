@@ -69,8 +69,10 @@ int lgb200_rope_split_bwd(const void* dq, const void* dk, const void* dv, const 
  * directions in one launch; 0 = self-attention).                                                */
 int lgb200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Nq, int Nk, int H,
                     int kv_shift, float scale, int dtype, cudaStream_t stream);
-/* dq [B,Nq,H,64]; dk,dv [B,Nk,H,64] (indexed by KEY batch); delta_ws: 17 * round_up(B*H*Nq, 4) floats of
- * scratch (rowsum(dout*out) and the per-query side tiles of the dK/dV kernel), 16-byte aligned.        */
+/* dq [B,Nq,H,64]; dk,dv [B,Nk,H,64] (indexed by KEY batch); delta_ws: lgb200_attn_bwd_ws_floats(B,Nq,Nk,H) floats of
+ * scratch, 256-byte aligned (rowsum(dout*out), the per-query side data of the kernels and, for the fused bf16
+ * backward, the fp32 dQ accumulator the key-tile CTAs reduce into).                                         */
+int64_t lgb200_attn_bwd_ws_floats(int B, int Nq, int Nk, int H);
 int lgb200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
                     void* dq, void* dk, void* dv, float* delta_ws, int B, int Nq, int Nk, int H, int kv_shift,
                     float scale, int dtype, cudaStream_t stream);

@@ -63,8 +63,8 @@ def test_gluestick_matches_reference_golden(precision):
     worst = 0.0
     for k, p in model.named_parameters():
         ref_norm = float(g[f"grad|{k}|norm"])
-        if ref_norm < 1e-9:  # conv bias in front of a BatchNorm: zero gradient
-            assert p.grad.norm().item() < 1e-4, k
+        if ref_norm < 1e-9:  # conv bias in front of a BatchNorm: zero gradient in theory, rounding noise in practice
+            assert p.grad.norm().item() < (1e-4 if tight else 2e-2), k
             continue
         if tight:
             check_grad_summary(g, k, p.grad, rtol=2e-3)

@@ -112,12 +112,12 @@ def test_bf16_path_at_least_as_close_as_reference_autocast(name):
     # indices: every row argmax the autocast reference keeps by margin, and at least its overall agreement
     assert torch.equal(got[safe], inner64.max(2).indices[safe])
     assert agree >= float(ac["idx|row_agree_frac"]), (agree, float(ac["idx|row_agree_frac"]))
-    # gradients as a population: typical (median) and tail (90th percentile) error no larger than the autocast
-    # reference's, a clear majority of the parameters individually closer.  Single parameters are one noise draw each
+    # gradients as a population: typical (median) and mean error no larger than the autocast reference's, a clear
+    # majority of the parameters individually closer.  Single parameters are one noise draw each
     # (the worst ratio is always the shared to_qk bias, whose gradient is a near-cancellation of the two attention
     # directions summed over all tokens), so the worst one is only held to twice the reference's worst.
     assert np.median(eo) <= np.median(ea), (np.median(eo), np.median(ea))
-    assert np.percentile(eo, 90) <= np.percentile(ea, 90), (np.percentile(eo, 90), np.percentile(ea, 90))
+    assert eo.mean() <= ea.mean(), (eo.mean(), ea.mean())
     assert (ratio <= 1).mean() >= 0.75, float((ratio <= 1).mean())
     assert eo.max() <= 2.0 * ea.max(), (names[int(eo.argmax())], eo.max(), ea.max())
 
