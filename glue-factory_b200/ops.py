@@ -437,6 +437,41 @@ def gt_matches_from_homography(kp0, kp1, H, pos_th=3.0, neg_th=6.0, dense=True):
     return out
 
 
+def gt_matches_from_reprojection(kp0, kp1, kp0_1, kp1_0, visible0=None, visible1=None, valid0=None, valid1=None,
+                                 pos_th=3.0, neg_th=5.0, dense=True):
+    """The O(M N) label pass of gt_matches_from_pose_depth (geometry/gt_generation.py:47-74) for given reprojections:
+    kp0_1 = view-0 keypoints projected into view 1, kp1_0 the converse, visibility / depth-validity masks [B,M] /
+    [B,N] (bool; None = all true).  Returns assignment (bool [B,M,N] when dense), matches0/1 (int64: index, -1, -2)."""
+    kp0, kp1, kp0_1, kp1_0 = (t.float().contiguous() for t in (kp0, kp1, kp0_1, kp1_0))
+    B, M = kp0.shape[:2]
+    N = kp1.shape[1]
+    dev = kp0.device
+    u8 = lambda t: None if t is None else t.to(torch.uint8).contiguous()  # noqa: E731
+    vis0, vis1, val0, val1 = u8(visible0), u8(visible1), u8(valid0), u8(valid1)
+    m0 = torch.empty(B, M, device=dev, dtype=torch.int64)
+    m1 = torch.empty(B, N, device=dev, dtype=torch.int64)
+    asg = torch.empty(B, M, N, device=dev, dtype=torch.bool) if dense else None
+    ws = torch.empty(_lib.load().lgb200_gt_homography_ws_bytes(B, M, N), device=dev, dtype=torch.uint8)
+    call("lgb200_gt_from_reprojection", ptr(kp0), ptr(kp1), ptr(kp0_1), ptr(kp1_0), ptr(vis0), ptr(vis1), ptr(val0),
+         ptr(val1), float(pos_th), float(neg_th), ptr(m0), ptr(m1), ptr(asg), ptr(ws), B, M, N, stream_ptr())
+    out = {"matches0": m0, "matches1": m1}
+    if dense:
+        out["assignment"] = asg
+    return out
+
+
+def gt_epipolar_unmatched_(kp0, kp1, F, valid0, valid1, m0, m1, th):
+    """In-place epipolar exclusion of gt_matches_from_pose_depth (gt_generation.py:82-90) on matches0 / matches1."""
+    kp0, kp1, F = kp0.float().contiguous(), kp1.float().contiguous(), F.float().contiguous()
+    B, M = kp0.shape[:2]
+    N = kp1.shape[1]
+    v0, v1 = valid0.to(torch.uint8).contiguous(), valid1.to(torch.uint8).contiguous()
+    _chk(m0, torch.int64), _chk(m1, torch.int64)
+    ws = torch.empty(B * (M + N), device=kp0.device, dtype=torch.uint8)
+    call("lgb200_gt_epipolar_unmatched", ptr(kp0), ptr(kp1), ptr(F), ptr(v0), ptr(v1), float(th), ptr(m0), ptr(m1), ptr(ws),
+         B, M, N, stream_ptr())
+
+
 _head_token_counters = {}
 
 

@@ -239,3 +239,95 @@ def make_gluestick_weights(state_dict_like, seed=0, dtype=torch.float32):
             bound = 1.0 / math.sqrt(wshape[1])
             out[k] = torch.from_numpy(rs.uniform(-bound, bound, size=shp)).to(dtype)
     return out
+
+
+# ----------------------------------------------------------------------------
+# pose + depth ground truth (MegaDepth-style supervision, matchers/depth_matcher.py)
+# ----------------------------------------------------------------------------
+def pose_depth_scene(B, M, N, seed, W=640, H=480):
+    """Synthetic two-view scene for the pose + depth ground truth: a tilted plane seen by two pinhole cameras; depth
+    maps in closed form (with a band of invalid depth), 45 % of the view-1 keypoints are reprojections of view-0
+    keypoints + 0.7 px noise, the rest uniform.  Returns plain tensors (K, R, t, depths, keypoints)."""
+    rs = np.random.RandomState(seed)
+    K = np.array([[520.0, 0, W / 2], [0, 520.0, H / 2], [0, 0, 1]])
+    out = {k: [] for k in ("K0", "K1", "R", "t", "depth0", "depth1", "kp0", "kp1")}
+    for b in range(B):
+        ang = rs.uniform(-0.12, 0.12, size=3)
+        Rx = np.array([[1, 0, 0], [0, np.cos(ang[0]), -np.sin(ang[0])], [0, np.sin(ang[0]), np.cos(ang[0])]])
+        Ry = np.array([[np.cos(ang[1]), 0, np.sin(ang[1])], [0, 1, 0], [-np.sin(ang[1]), 0, np.cos(ang[1])]])
+        Rz = np.array([[np.cos(ang[2]), -np.sin(ang[2]), 0], [np.sin(ang[2]), np.cos(ang[2]), 0], [0, 0, 1]])
+        R = Rz @ Ry @ Rx
+        t = rs.uniform(-0.5, 0.5, size=3)
+        n0 = np.array([0.15, -0.1, 1.0]); n0 /= np.linalg.norm(n0)
+        dpl = 5.0  # plane n0 . X = dpl in camera 0
+        Kinv = np.linalg.inv(K)
+        ys, xs = np.meshgrid(np.arange(H) + 0.5, np.arange(W) + 0.5, indexing="ij")
+        rays = np.stack([xs, ys, np.ones_like(xs)], -1) @ Kinv.T
+        depth0 = dpl / (rays @ n0)
+        n1 = R @ n0
+        d1 = dpl + n1 @ t
+        depth1 = d1 / (rays @ n1)
+        depth0[:, 200:230] = 0.0  # a band without depth in each view (invalid keypoints)
+        depth1[100:130, :] = 0.0
+        kp0 = np.stack([rs.uniform(2, W - 2, M), rs.uniform(2, H - 2, M)], -1)
+        kp1 = np.stack([rs.uniform(2, W - 2, N), rs.uniform(2, H - 2, N)], -1)
+        Kn = int(0.45 * min(M, N))
+        r0 = np.concatenate([kp0[:Kn], np.ones((Kn, 1))], 1) @ Kinv.T
+        X0 = r0 * (dpl / (r0 @ n0))[:, None]
+        X1 = X0 @ R.T + t
+        proj = (X1 / X1[:, 2:]) @ K.T
+        cand = proj[:, :2] + 0.7 * rs.standard_normal((Kn, 2))
+        ok = (cand[:, 0] > 2) & (cand[:, 0] < W - 2) & (cand[:, 1] > 2) & (cand[:, 1] < H - 2)
+        kp1[:Kn][ok] = cand[ok]
+        kp1 = kp1[rs.permutation(N)]
+        for k, v in (("K0", K), ("K1", K), ("R", R), ("t", t), ("depth0", depth0), ("depth1", depth1), ("kp0", kp0), ("kp1", kp1)):
+            out[k].append(v)
+    return {k: torch.from_numpy(np.stack(v)).float() for k, v in out.items()}
+
+
+class PinholeCamera:
+    """Duck-typed stand-in for gluefactory.geometry.wrappers.Camera (PINHOLE, no distortion) with exactly the methods
+    the depth ground truth calls (wrappers.py:271-398): data = [w, h, fx, fy, cx, cy] per batch element."""
+
+    eps = 1e-4
+
+    def __init__(self, K):
+        self.f = torch.stack([K[..., 0, 0], K[..., 1, 1]], -1)
+        self.c = torch.stack([K[..., 0, 2], K[..., 1, 2]], -1)
+        self.size = 2 * self.c
+        self._K = K
+
+    def to(self, device):
+        return PinholeCamera(self._K.to(device))
+
+    def calibration_matrix(self):
+        return self._K
+
+    def image2cam(self, p2d):
+        p = (p2d - self.c.unsqueeze(-2)) / self.f.unsqueeze(-2)
+        return torch.cat([p, torch.ones_like(p[..., :1])], -1)
+
+    def cam2image(self, p3d):
+        z = p3d[..., -1]
+        visible = z > self.eps
+        p2d = p3d[..., :-1] / z.clamp(min=self.eps).unsqueeze(-1)
+        p2d = p2d * self.f.unsqueeze(-2) + self.c.unsqueeze(-2)
+        inside = torch.all((p2d >= 0) & (p2d <= (self.size.unsqueeze(-2) - 1)), -1)
+        return p2d, visible & inside
+
+
+class RigidPose:
+    """Duck-typed stand-in for gluefactory.geometry.wrappers.Pose: p -> R p + t."""
+
+    def __init__(self, R, t):
+        self.R, self.t = R, t
+
+    def to(self, device):
+        return RigidPose(self.R.to(device), self.t.to(device))
+
+    def transform(self, p3d):
+        return p3d @ self.R.transpose(-1, -2) + self.t.unsqueeze(-2)
+
+    def inv(self):
+        Rt = self.R.transpose(-1, -2)
+        return RigidPose(Rt, -(Rt @ self.t.unsqueeze(-1)).squeeze(-1))

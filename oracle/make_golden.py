@@ -299,6 +299,36 @@ def run_gluestick(name="gluestick_l4_n160", n_gnn=4, B=2, N=160, L=24, seed=31):
           f"{path} ({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+def run_gt_pose_depth():
+    """Golden labels from the reference's own gt_matches_from_pose_depth (geometry/gt_generation.py:13-106) with its
+    Camera / Pose wrappers, for th_epi None / 5 and th_consistency None / 3: stores the inputs of the O(M N) pass
+    (reprojections and masks, as the reference computed them) and its outputs."""
+    from gluefactory.geometry.gt_generation import gt_matches_from_pose_depth
+    from gluefactory.geometry.wrappers import Camera, Pose
+
+    out = {}
+    for tag, (B, M, N, seed, epi, cc) in {"a": (2, 300, 260, 61, None, None), "b": (1, 513, 640, 62, 5.0, None),
+                                          "c": (2, 200, 333, 63, 5.0, 3.0)}.items():
+        sc = synthetic.pose_depth_scene(B, M, N, seed)
+        data = {"view0": {"camera": Camera.from_calibration_matrix(sc["K0"]), "depth": sc["depth0"]},
+                "view1": {"camera": Camera.from_calibration_matrix(sc["K1"]), "depth": sc["depth1"]},
+                "T_0to1": Pose.from_Rt(sc["R"], sc["t"])}
+        r = gt_matches_from_pose_depth(sc["kp0"], sc["kp1"], data, pos_th=3.0, neg_th=5.0, epi_th=epi, cc_th=cc)
+        out[f"{tag}|meta"] = np.array([B, M, N, seed, -1 if epi is None else epi, -1 if cc is None else cc], dtype=np.float64)
+        for k in ("matches0", "matches1", "proj_0to1", "proj_1to0", "visible0", "visible1", "depth_keypoints0",
+                  "depth_keypoints1"):
+            out[f"{tag}|{k}"] = r[k].numpy()
+        out[f"{tag}|positives"] = r["assignment"].nonzero().numpy()
+        from gluefactory.geometry.depth import sample_depth
+        out[f"{tag}|valid0"] = sample_depth(sc["kp0"], sc["depth0"])[1].numpy()
+        out[f"{tag}|valid1"] = sample_depth(sc["kp1"], sc["depth1"])[1].numpy()
+        print(f"gt_pose_depth {tag}: positives={int(r['assignment'].sum())} unmatched0={int((r['matches0'] == -1).sum())} "
+              f"ignored0={int((r['matches0'] == -2).sum())}")
+    path = os.path.join(OUT, "gt_pose_depth.npz")
+    np.savez_compressed(path, **out)
+    print("gt_pose_depth ->", path, f"({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 def run_eval_loss():
     """Validation-mode loss of the reference (train.py:92-93 do_evaluation: model.eval(), loss on the last layer only,
     lightglue.py:485 keeps one stacked layer and :588 uses log_assignment[-1]) + the matcher metrics."""
@@ -336,7 +366,7 @@ if __name__ == "__main__":
     if only:
         for name in only:
             {"gluestick_attn": run_gluestick_attention, "gt_homography": run_gt_homography,
-             "heads_grad": run_heads_grad, "autocast": run_autocast_cases, "eval_loss": run_eval_loss, "gluestick": run_gluestick}[name]()
+             "heads_grad": run_heads_grad, "autocast": run_autocast_cases, "eval_loss": run_eval_loss, "gluestick": run_gluestick, "gt_pose_depth": run_gt_pose_depth}[name]()
         sys.exit(0)
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -356,3 +386,4 @@ if __name__ == "__main__":
     run_autocast_cases()
     run_eval_loss()
     run_gluestick()
+    run_gt_pose_depth()

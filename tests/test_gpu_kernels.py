@@ -370,6 +370,39 @@ def test_gt_from_homography_matches_restatement_at_size(B, M, N):
     assert "assignment" not in sparse and torch.equal(sparse["matches0"], m0)
 
 
+def test_gt_from_pose_depth_matches_reference_labels():
+    """SURVEY 8f row 1, second half: labels of gt_matches_from_pose_depth (geometry/gt_generation.py:13-106) -- th_epi
+    None / 5, th_consistency None / 3 -- bit-exact against the reference function's own output (golden), (a) for the
+    O(M N) kernels alone on the reference's reprojections and masks, (b) through the drop-in depth_matcher component
+    with duck-typed Camera / Pose objects."""
+    from gluefactory_b200 import synthetic
+    from gluefactory_b200.matchers.depth_matcher import DepthMatcher
+
+    g = dict(np.load(os.path.join(GOLDEN, "gt_pose_depth.npz")))
+    for tag in "abc":
+        B, M, N, seed, epi, cc = g[f"{tag}|meta"]
+        B, M, N, seed = int(B), int(M), int(N), int(seed)
+        sc = synthetic.to_device(synthetic.pose_depth_scene(B, M, N, seed), DEV)
+        conf = {"th_positive": 3.0, "th_negative": 5.0, "th_epi": None if epi < 0 else float(epi),
+                "th_consistency": None if cc < 0 else float(cc)}
+        data = {"keypoints0": sc["kp0"], "keypoints1": sc["kp1"],
+                "view0": {"camera": synthetic.PinholeCamera(sc["K0"]), "depth": sc["depth0"]},
+                "view1": {"camera": synthetic.PinholeCamera(sc["K1"]), "depth": sc["depth1"]},
+                "T_0to1": synthetic.RigidPose(sc["R"], sc["t"])}
+        pred = DepthMatcher(conf)(data)
+        assert np.array_equal(pred["matches0"].cpu().numpy(), g[f"{tag}|matches0"]), tag
+        assert np.array_equal(pred["matches1"].cpu().numpy(), g[f"{tag}|matches1"]), tag
+        assert np.array_equal(pred["assignment"].nonzero().cpu().numpy(), g[f"{tag}|positives"]), tag
+        assert np.array_equal(pred["visible0"].cpu().numpy(), g[f"{tag}|visible0"])
+        if epi < 0:  # kernel alone, from the reference's own reprojections / masks
+            t = lambda k: torch.from_numpy(g[f"{tag}|{k}"]).to(DEV)  # noqa: E731
+            r = ops.gt_matches_from_reprojection(sc["kp0"], sc["kp1"], t("proj_0to1"), t("proj_1to0"), t("visible0"),
+                                                 t("visible1"), t("valid0"), t("valid1"), 3.0, 5.0)
+            assert np.array_equal(r["matches0"].cpu().numpy(), g[f"{tag}|matches0"])
+            assert np.array_equal(r["matches1"].cpu().numpy(), g[f"{tag}|matches1"])
+    torch.cuda.synchronize()
+
+
 def test_gt_from_homography_degenerate_rows():
     """Rows / columns whose distances are all +inf or NaN (overflowing or NaN keypoints, a point on the homography's
     line at infinity) must behave like torch's min (valid first index, NaN propagates), never index out of bounds."""
