@@ -143,8 +143,8 @@ class LightGlue(nn.Module):
         "num_heads": 4,
         "flash": False,  # accepted for config compatibility; attention is always the fused kernel
         "mp": False,
-        "depth_confidence": -1,
-        "width_confidence": -1,
+        "depth_confidence": -1,  # > 0: early stopping at inference (eval mode, one pair; _forward_adaptive)
+        "width_confidence": -1,  # > 0: point pruning at inference
         "filter_threshold": 0.0,
         "checkpointed": False,  # accepted; the fused attention keeps no N x N activations to checkpoint
         "weights": None,
@@ -289,9 +289,7 @@ class LightGlue(nn.Module):
             assert key in data, f"Missing key {key} in data"
         _lib.load()  # raises unless the CUDA library is built and the device is a B200 (no CPU fallback)
         conf = self.conf
-        if not self.training and (conf.depth_confidence > 0 or conf.width_confidence > 0):
-            raise NotImplementedError("adaptive depth/width (early stop, point pruning) is not built yet; "
-                                      "set depth_confidence = width_confidence = -1")
+        adaptive = not self.training and (conf.depth_confidence > 0 or conf.width_confidence > 0)
         kpts0, kpts1 = data["keypoints0"], data["keypoints1"]
         B, M, _ = kpts0.shape
         N = kpts1.shape[1]
@@ -314,6 +312,8 @@ class LightGlue(nn.Module):
         fused = conf.engine == "fused"
         if fused:
             self._refresh_shadow()
+        if adaptive:
+            return self._forward_adaptive(x, theta, sizes)
         for i in range(L):
             if fused:
                 w, params = self._layer_weights(i)
@@ -359,6 +359,75 @@ class LightGlue(nn.Module):
                 self._argmax_with_dustbin(st["colmax"], st["colarg"], du1, M).contiguous())
             pred["_b200_row_expsum"] = st["row_expsum"]
         return pred
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _forward_adaptive(self, x, theta, sizes):
+        """Inference-time adaptive depth / width (lightglue.py:461-526, 545-576; eval only, one pair): after every
+        layer but the last, (a) stop when the fraction of confident points exceeds depth_confidence, (b) drop the points
+        predicted unmatchable (matchability <= 1 - width_confidence) unless their confidence is still low, compacting the
+        token matrix and the rotary angles with index_select.  The layers run on the same kernels (M != N after the
+        first pruning); the two per-token logits come from one head_token pass.  On an early stop the assignment head of
+        the stopping layer is used (upstream LightGlue's behaviour; the in-tree reference cannot take that branch: it
+        stacks an empty list after the break, lightglue.py:485-492, 533)."""
+        conf = self.conf
+        B, M, N = sizes
+        assert B == 1, "adaptive depth / width runs one pair at a time (lightglue.py:487, 492)"
+        assert conf.engine == "fused"
+        dev, D, L = x.device, conf.descriptor_dim, conf.n_layers
+        do_stop, do_prune = conf.depth_confidence > 0, conf.width_confidence > 0
+        ind0, ind1 = torch.arange(M, device=dev), torch.arange(N, device=dev)
+        prune0 = torch.ones(1, M, device=dev, dtype=torch.int64)
+        prune1 = torch.ones(1, N, device=dev, dtype=torch.int64)
+        m, n = M, N
+        last = L - 1
+        for i in range(L):
+            w, params = self._layer_weights(i)
+            x = engine.LayerFn.apply(x, theta, (1, m, n), conf.num_heads, self._cdt, self.transformers[i].self_attn.ffn[1].eps,
+                                     w, None, *params)
+            if i == L - 1:
+                break
+            la, tk = self.log_assignment[i], self.token_confidence[i].token[0]
+            _, zt, _, _ = ops.head_token_fwd(x, la.matchability.weight.view(-1), la.matchability.bias, tk.weight.view(-1),
+                                             tk.bias, self._cdt)
+            token = torch.sigmoid(zt[:, 1]) if do_stop else None  # token confidences only exist with early stopping on
+            if do_stop:
+                thr = self.confidence_thresholds[i]
+                ratio = 1.0 - (token < thr).float().sum() / (M + N)  # relative to the ORIGINAL point count (lightglue.py:489)
+                if bool(ratio > conf.depth_confidence):
+                    last = i
+                    break
+            if do_prune:
+                keep = torch.sigmoid(zt[:, 0]) > (1 - conf.width_confidence)
+                if token is not None:  # low-confidence points are never pruned (lightglue.py:556-557)
+                    keep = keep | (token <= self.confidence_thresholds[i])
+                k0, k1 = torch.where(keep[:m])[0], torch.where(keep[m:])[0]
+                ind0, ind1 = ind0.index_select(0, k0), ind1.index_select(0, k1)
+                sel = torch.cat([k0, k1 + m])
+                x, theta = x.index_select(0, sel).contiguous(), theta.index_select(0, sel).contiguous()
+                m, n = int(k0.numel()), int(k1.numel())
+                assert m > 0 and n > 0, "point pruning removed every keypoint of a view"
+                prune0[:, ind0] += 1
+                prune1[:, ind1] += 1
+        d0, d1 = x[:m].view(1, m, D), x[m:].view(1, n, D)
+        md0, md1, z0, z1 = self._head_inputs(d0, d1, last)
+        sim = ops._similarity(md0, md1, self._bf16)
+        st = ops.assign_stats(sim, F.logsigmoid(z0), F.logsigmoid(z1), F.logsigmoid(-z0), F.logsigmoid(-z1), dense=True)
+        m0, m1, ms0, ms1 = ops.filter_matches(st["rowmax"], st["rowarg"], st["colarg"], conf.filter_threshold)
+        if do_prune:  # scatter back to the full keypoint sets (lightglue.py:517-526)
+            m0_ = torch.full((1, M), -1, device=dev, dtype=m0.dtype)
+            m1_ = torch.full((1, N), -1, device=dev, dtype=m1.dtype)
+            m0_[:, ind0] = torch.where(m0 == -1, -1, ind1[None].gather(1, m0.clamp(min=0)))
+            m1_[:, ind1] = torch.where(m1 == -1, -1, ind0[None].gather(1, m1.clamp(min=0)))
+            ms0_, ms1_ = torch.zeros(1, M, device=dev), torch.zeros(1, N, device=dev)
+            ms0_[:, ind0] = ms0
+            ms1_[:, ind1] = ms1
+            m0, m1, ms0, ms1 = m0_, m1_, ms0_, ms1_
+        else:
+            prune0, prune1 = torch.ones_like(ms0) * L, torch.ones_like(ms1) * L
+        return {"matches0": m0, "matches1": m1, "matching_scores0": ms0, "matching_scores1": ms1,
+                "ref_descriptors0": d0[:, None], "ref_descriptors1": d1[:, None], "log_assignment": st["scores"],
+                "prune0": prune0, "prune1": prune1, "stop_layer": last}
 
     # ------------------------------------------------------------------------------------------
     def _loss_fused(self, pred, data, layers_x, gt_u8, rowcnt, colcnt, neg0, neg1, num_pos, num_neg0, num_neg1):

@@ -329,6 +329,46 @@ def run_gt_pose_depth():
     print("gt_pose_depth ->", path, f"({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+def run_adaptive():
+    """Inference-time point pruning (lightglue.py:461-526, 545-558) of the unmodified reference in
+    eval mode, fp32 (its pruning branch mixes default-dtype buffers with the model dtype, so fp64 fails).  The seed is
+    chosen so that every pruning decision clears its threshold by a margin (checked below), i.e. the fixture does not
+    hinge on fp32 rounding.  Early stopping is not recorded: the reference cannot take that branch without crashing
+    (`torch.stack` of the empty `all_desc0` list after the `break`, lightglue.py:485-492, 533)."""
+    from gluefactory.models import get_model
+
+    conf = dict(synthetic.DEFAULT_CONF, n_layers=5, width_confidence=0.6, depth_confidence=-1, filter_threshold=0.0)
+    N, M = 224, 200
+    for seed in range(70, 90):
+        w = synthetic.make_weights(conf, seed=seed)
+        model = get_model("matchers.lightglue")(dict(conf, name="matchers.lightglue"))
+        model.load_state_dict(w, strict=False)
+        model = model.eval()
+        data = synthetic.make_pairs(1, N, seed=seed + 1, M=M)
+        margins = []
+        orig = model.get_pruning_mask
+
+        def spy(confidences, scores, layer_index, _orig=orig):
+            margins.append((scores - (1 - conf["width_confidence"])).abs().min().item())
+            return _orig(confidences, scores, layer_index)
+        model.get_pruning_mask = spy
+        with torch.no_grad():
+            pred = model(data)
+        kept = pred["log_assignment"].shape[1] - 1
+        if min(margins) > 2e-4 and 20 < kept < M - 20:
+            break
+    else:
+        raise RuntimeError("no seed with comfortable pruning margins")
+    out = {"meta|conf": np.array(repr(conf)), "meta|seed": np.array(seed), "meta|M": np.array(M), "meta|N": np.array(N),
+           "meta|min_margin": np.array(min(margins))}
+    for k in ["matches0", "matches1", "matching_scores0", "matching_scores1", "prune0", "prune1", "log_assignment"]:
+        out["pred|" + k] = pred[k].numpy()
+    path = os.path.join(OUT, "adaptive_prune.npz")
+    np.savez_compressed(path, **out)
+    print(f"adaptive_prune: seed={seed} kept0={kept} kept1={pred['log_assignment'].shape[2] - 1} min margin={min(margins):.2e} "
+          f"matches={int((pred['matches0'] > -1).sum())} -> {path}")
+
+
 def run_eval_loss():
     """Validation-mode loss of the reference (train.py:92-93 do_evaluation: model.eval(), loss on the last layer only,
     lightglue.py:485 keeps one stacked layer and :588 uses log_assignment[-1]) + the matcher metrics."""
@@ -366,7 +406,7 @@ if __name__ == "__main__":
     if only:
         for name in only:
             {"gluestick_attn": run_gluestick_attention, "gt_homography": run_gt_homography,
-             "heads_grad": run_heads_grad, "autocast": run_autocast_cases, "eval_loss": run_eval_loss, "gluestick": run_gluestick, "gt_pose_depth": run_gt_pose_depth}[name]()
+             "heads_grad": run_heads_grad, "autocast": run_autocast_cases, "eval_loss": run_eval_loss, "gluestick": run_gluestick, "gt_pose_depth": run_gt_pose_depth, "adaptive": run_adaptive}[name]()
         sys.exit(0)
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -387,3 +427,4 @@ if __name__ == "__main__":
     run_eval_loss()
     run_gluestick()
     run_gt_pose_depth()
+    run_adaptive()

@@ -158,6 +158,61 @@ def test_eval_mode_loss_uses_last_head(engine):
         np.testing.assert_allclose(metrics[k].cpu().numpy(), g["metric|" + k], rtol=1e-3, atol=1e-6, err_msg=k)
 
 
+def test_adaptive_point_pruning_matches_reference():
+    """SURVEY 8f row 4: inference-time point pruning (lightglue.py:461-526) against the reference in eval mode (fp32;
+    tests/golden/adaptive_prune.npz, every pruning decision clears its threshold by > 2e-4): the same points survive
+    every layer (prune0/1), the same pruned log-assignment, the same matches scattered back to the full sets."""
+    import ast
+    import os
+
+    from tests.util import GOLDEN
+
+    g = dict(np.load(os.path.join(GOLDEN, "adaptive_prune.npz")))
+    conf = ast.literal_eval(str(g["meta|conf"]))
+    seed, M, N = int(g["meta|seed"]), int(g["meta|M"]), int(g["meta|N"])
+    model = _build(conf, synthetic.make_weights(conf, seed=seed), "fp32").eval()
+    d = synthetic.to_device(synthetic.make_pairs(1, N, seed=seed + 1, M=M), DEV)
+    with torch.no_grad():
+        pred = model(d)
+    assert np.array_equal(pred["prune0"].cpu().numpy(), g["pred|prune0"]) and np.array_equal(pred["prune1"].cpu().numpy(), g["pred|prune1"])
+    assert pred["log_assignment"].shape == g["pred|log_assignment"].shape
+    np.testing.assert_allclose(pred["log_assignment"].cpu().numpy(), g["pred|log_assignment"], rtol=1e-3, atol=1e-3)
+    assert np.array_equal(pred["matches0"].cpu().numpy(), g["pred|matches0"])
+    assert np.array_equal(pred["matches1"].cpu().numpy(), g["pred|matches1"])
+    np.testing.assert_allclose(pred["matching_scores0"].cpu().numpy(), g["pred|matching_scores0"], rtol=1e-3, atol=1e-6)
+    # bf16 path: same code, pruning counts within a few points of the fp32 path
+    mb = _build(conf, synthetic.make_weights(conf, seed=seed), "bf16").eval()
+    with torch.no_grad():
+        pb = mb(d)
+    assert abs(int((pb["prune0"] == conf["n_layers"]).sum()) - int((pred["prune0"] == conf["n_layers"]).sum())) <= 8
+
+
+def test_adaptive_early_stop():
+    """Early stopping (lightglue.py:486-490, 560-571): with confident token heads the matcher stops after the first
+    layer and uses that layer's assignment head; with depth_confidence out of reach it runs all layers and equals the
+    plain forward."""
+    conf = dict(synthetic.DEFAULT_CONF, n_layers=4, depth_confidence=0.9)
+    w = synthetic.make_weights(conf, seed=77)
+    d = synthetic.to_device(synthetic.make_pairs(1, 192, seed=78), DEV)
+    for i in range(3):
+        w[f"token_confidence.{i}.token.0.bias"] = torch.tensor([6.0])  # sigmoid(6 +- small) > every threshold
+        w[f"token_confidence.{i}.token.0.weight"] = w[f"token_confidence.{i}.token.0.weight"] * 0.01
+    model = _build(conf, w, "fp32").eval()
+    with torch.no_grad():
+        pred = model(d)
+        assert pred["stop_layer"] == 0
+        # same result as a one-layer model that uses head 0
+        w1 = {k: v for k, v in w.items() if k.startswith(("posenc", "transformers.0.", "log_assignment.0."))}
+        x_ref = _build(dict(conf, n_layers=1, depth_confidence=-1), w1, "fp32").eval()(d)
+    assert torch.equal(pred["matches0"], x_ref["matches0"])
+    np.testing.assert_allclose(pred["log_assignment"].cpu().numpy(), x_ref["log_assignment"].cpu().numpy(), rtol=1e-5, atol=1e-5)
+    model2 = _build(dict(conf, depth_confidence=1.5), w, "fp32").eval()
+    plain = _build(dict(conf, depth_confidence=-1), w, "fp32").eval()
+    with torch.no_grad():
+        a, b = model2(d), plain(d)
+    assert a["stop_layer"] == 3 and torch.equal(a["matches0"], b["matches0"])
+
+
 def test_nan_propagates_to_loss():
     """train.py:477-480 skips the step on a NaN loss; the kernels must not trap or hide it."""
     conf = dict(synthetic.DEFAULT_CONF, n_layers=1)
