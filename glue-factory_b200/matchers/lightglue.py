@@ -166,10 +166,10 @@ class LightGlue(nn.Module):
         assert conf.engine in ("fused", "autograd"), conf.engine
         d, h, n = conf.descriptor_dim, conf.num_heads, conf.n_layers
         assert d % h == 0 and d // h == 64, "the lgb200 kernels are built for head_dim 64"
-        if conf.add_scale_ori:
-            raise NotImplementedError("add_scale_ori (SIFT scale/orientation encoding) is not built yet")
         self.input_proj = nn.Linear(conf.input_dim, d) if conf.input_dim != d else nn.Identity()
-        self.posenc = LearnableFourierPositionalEncoding(2, 64, 64)
+        # add_scale_ori (SIFT-style features, lightglue.py:347-349, 426-443): scale and orientation join (x, y) as inputs
+        # of the learnt Fourier encoding, Wr becomes [32, 4]; only the rotary ANGLES change, not the kernels
+        self.posenc = LearnableFourierPositionalEncoding(2 + 2 * bool(conf.add_scale_ori), 64, 64)
         self.transformers = nn.ModuleList([TransformerLayer(d, h) for _ in range(n)])
         self.log_assignment = nn.ModuleList([MatchAssignment(d) for _ in range(n)])
         self.token_confidence = nn.ModuleList([TokenConfidence(d) for _ in range(n - 1)])
@@ -304,7 +304,12 @@ class LightGlue(nn.Module):
         if not isinstance(self.input_proj, nn.Identity):
             x = self._lin(x, self.input_proj).float()
         # rotary angles, cached for all layers (lightglue.py:456-458); cos/sin are taken in-kernel
-        kp = torch.cat([kpts0.reshape(B * M, 2), kpts1.reshape(B * N, 2)], 0)
+        if conf.add_scale_ori:
+            ext = lambda k, sc, o: torch.cat([k, (sc if sc.dim() == 3 else sc[..., None]).float(),  # noqa: E731
+                                              (o if o.dim() == 3 else o[..., None]).float()], -1)
+            kpts0, kpts1 = ext(kpts0, data["scales0"], data["oris0"]), ext(kpts1, data["scales1"], data["oris1"])
+        kd = kpts0.shape[-1]
+        kp = torch.cat([kpts0.reshape(B * M, kd), kpts1.reshape(B * N, kd)], 0)
         theta = F.linear(kp, self.posenc.Wr.weight.float()).float().contiguous()
         sizes = (B, M, N)
         all0, all1, layers_x = [], [], []

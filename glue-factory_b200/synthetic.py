@@ -39,7 +39,7 @@ def state_dict_spec(conf):
     spec = []
     if Din != D:
         spec += [("input_proj.weight", (D, Din)), ("input_proj.bias", (D,))]
-    spec += [("posenc.Wr.weight", (dh // 2, 2))]
+    spec += [("posenc.Wr.weight", (dh // 2, 2 + 2 * bool(conf.get("add_scale_ori", False))))]
     for i in range(L):
         p = f"transformers.{i}.self_attn"
         spec += [(p + ".Wqkv.weight", (3 * D, D)), (p + ".Wqkv.bias", (3 * D,)),
@@ -172,6 +172,16 @@ def make_pairs(B, N, seed=1234, D=256, image_size=1024, frac=0.4, M=None, with_g
                                           data["H_0to1"][b:b + 1].double()) for b in range(B)]  # per pair: bounded memory
         data.update({"gt_assignment": torch.cat([g[0] for g in gts]), "gt_matches0": torch.cat([g[1] for g in gts]),
                      "gt_matches1": torch.cat([g[2] for g in gts])})
+    return data
+
+
+def add_scale_ori_inputs(data, seed):
+    """Per-keypoint scale / orientation of SIFT-style extractors (the extra inputs of `add_scale_ori`, lightglue.py:426-443)."""
+    rs = np.random.RandomState(seed)
+    for i in "01":
+        k = data[f"keypoints{i}"]
+        data[f"scales{i}"] = torch.from_numpy(rs.uniform(0.5, 4.0, size=tuple(k.shape[:2]))).to(k.dtype)
+        data[f"oris{i}"] = torch.from_numpy(rs.uniform(-3.14, 3.14, size=tuple(k.shape[:2]))).to(k.dtype)
     return data
 
 

@@ -246,6 +246,9 @@ def lightglue_forward(w, data, conf, rnd=_id):
     d0, d1 = data["descriptors0"], data["descriptors1"]
     if "input_proj.weight" in w:
         d0, d1 = _linear(d0, w, "input_proj", rnd), _linear(d1, w, "input_proj", rnd)
+    if conf.get("add_scale_ori"):  # lightglue.py:426-443
+        k0 = torch.cat([k0, data["scales0"][..., None], data["oris0"][..., None]], -1)
+        k1 = torch.cat([k1, data["scales1"][..., None], data["oris1"][..., None]], -1)
     th0, th1 = posenc_angles(w, k0), posenc_angles(w, k1)
     all0, all1 = [], []
     for i in range(L):

@@ -66,6 +66,8 @@ def build_reference(conf, weights, dtype):
 def run_case(name, conf, B, N, M, seed, dtype=torch.float64, sub=1):
     weights = synthetic.make_weights(conf, seed=seed)
     data = synthetic.make_pairs(B, N, seed=seed + 1, D=conf["input_dim"], M=M, dtype=dtype)
+    if conf.get("add_scale_ori"):
+        data = synthetic.add_scale_ori_inputs(data, seed + 2)
     model = build_reference(conf, weights, dtype)
     pred = model(data)
     losses, _ = model.loss(pred, data)
@@ -406,7 +408,9 @@ if __name__ == "__main__":
     if only:
         for name in only:
             {"gluestick_attn": run_gluestick_attention, "gt_homography": run_gt_homography,
-             "heads_grad": run_heads_grad, "autocast": run_autocast_cases, "eval_loss": run_eval_loss, "gluestick": run_gluestick, "gt_pose_depth": run_gt_pose_depth, "adaptive": run_adaptive}[name]()
+             "heads_grad": run_heads_grad, "autocast": run_autocast_cases, "eval_loss": run_eval_loss, "gluestick": run_gluestick, "gt_pose_depth": run_gt_pose_depth, "adaptive": run_adaptive,
+             "sift": lambda: run_case("lg_sift_d256_l2_n96", dict(synthetic.DEFAULT_CONF, n_layers=2, input_dim=128,
+                                                                  add_scale_ori=True), B=1, N=96, M=80, seed=16)}[name]()
         sys.exit(0)
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -417,6 +421,7 @@ if __name__ == "__main__":
     run_case("lg_d256_l3_n160", mid, B=2, N=160, M=160, seed=13)
     disk = dict(synthetic.DEFAULT_CONF, n_layers=2, input_dim=128)
     run_case("lg_disk_d256_l2_n128", disk, B=1, N=128, M=128, seed=14)
+    run_case("lg_sift_d256_l2_n96", dict(synthetic.DEFAULT_CONF, n_layers=2, input_dim=128, add_scale_ori=True), B=1, N=96, M=80, seed=16)
     full = dict(synthetic.DEFAULT_CONF)
     run_case("lg_full_l9_n512", full, B=1, N=512, M=512, seed=15, sub=8)
     run_heads()

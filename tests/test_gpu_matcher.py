@@ -15,7 +15,7 @@ from gluefactory_b200 import synthetic
 from gluefactory_b200.matchers.lightglue import LightGlue
 from gluefactory_b200.trainer import MatcherTrainer
 from oracle import lightglue_oracle as O
-from tests.util import CASES, check_grad_summary, load_case, rel_err
+from tests.util import CASES, EXTRA_CASES, check_grad_summary, load_case, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -34,7 +34,7 @@ def _f32(data):
 
 
 @pytest.mark.parametrize("engine", ["fused", "autograd"])
-@pytest.mark.parametrize("name", CASES[:4])
+@pytest.mark.parametrize("name", CASES[:4] + EXTRA_CASES)
 def test_fp32_path_matches_reference_golden(name, engine):
     g, conf, w, data = load_case(name)
     model = _build(conf, w, "fp32", engine)

@@ -10,6 +10,7 @@ from gluefactory_b200 import synthetic
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["lg_small_d128_l2_n96", "lg_small_d128_l2_m80_n112", "lg_d256_l3_n160",
          "lg_disk_d256_l2_n128", "lg_full_l9_n512"]
+EXTRA_CASES = ["lg_sift_d256_l2_n96"]  # add_scale_ori (SIFT-style scale / orientation inputs), input_dim 128, M != N
 
 
 def load_case(name, dtype=torch.float64):
@@ -19,6 +20,8 @@ def load_case(name, dtype=torch.float64):
     B, N, M, seed = (int(g["meta|" + k]) for k in ["B", "N", "M", "seed"])
     weights = {k: v.to(dtype) for k, v in synthetic.make_weights(conf, seed=seed).items()}
     data = synthetic.make_pairs(B, N, seed=seed + 1, D=conf["input_dim"], M=M, dtype=dtype)
+    if conf.get("add_scale_ori"):
+        data = synthetic.add_scale_ori_inputs(data, seed + 2)
     return g, conf, weights, data
 
 
