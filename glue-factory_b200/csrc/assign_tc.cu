@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         const int s = g & 1;
         const int j0 = t * AT_C + cq * 32;      // first column of this warp's quarter
         const bool tail = j0 + 32 > ncols;
-        if (MODE != AT_LSE) {                   // stage this warp's 32 column values (two vectors), coalesced
+        if (MODE != AT_LSE) {                   // stage this warp's 32 per-column values, coalesced
           __syncwarp();
           const int j = j0 + lane;
           float v0 = 0.f, v1 = 0.f;
@@ -251,6 +251,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
           if (MODE == AT_BWD) {
             v0 = j < ncols ? v0 * kLog2e : INFINITY;  // exp2(x - inf) = 0 for columns past the end
             v1 *= gc;
+          } else {
+            v0 = j < ncols ? v1 - v0 : -INFINITY;     // STATS: other side's (log sigmoid - lse); -inf masks the tail
           }
           myvec[lane] = v0;
           myvec[32 + lane] = v1;
@@ -303,26 +305,27 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_done[s]);
-          // scores of this chunk in the reference's association (log_softmax_row + log_softmax_col) + (lsig0 + lsig1);
-          // dir 1 sees the same element with "mine" and "other" swapped, so the operands are put back in order
+          // score_ij = (2 alpha S_ij + [lsig - lse]_other(j)) + [lsig - lse]_mine: the second bracket is constant along
+          // this thread's sweep, so the running max / first argmax is taken over the first term only (an FMA and an
+          // FMNMX per element) and the constant is added when the result is written.  (assign_scores in assign.cu keeps
+          // the reference's association order for the fp32 parity path; the two agree to fp32 rounding.)
+          const float a2 = 2.f * a.alpha;
           float cmax = -INFINITY;
 #pragma unroll
           for (int e4 = 0; e4 < 8; ++e4) {
-            const float4 lc = *reinterpret_cast<const float4*>(myvec + e4 * 4);       // other side's LSE
-            const float4 l1 = *reinterpret_cast<const float4*>(myvec + 32 + e4 * 4);  // other side's log sigmoid
-            const float lcv[4] = {lc.x, lc.y, lc.z, lc.w}, l1v[4] = {l1.x, l1.y, l1.z, l1.w};
+            const float4 cv = *reinterpret_cast<const float4*>(myvec + e4 * 4);
+            sv[e4 * 4] = fmaf(sv[e4 * 4], a2, cv.x); sv[e4 * 4 + 1] = fmaf(sv[e4 * 4 + 1], a2, cv.y);
+            sv[e4 * 4 + 2] = fmaf(sv[e4 * 4 + 2], a2, cv.z); sv[e4 * 4 + 3] = fmaf(sv[e4 * 4 + 3], a2, cv.w);
+            cmax = fmaxf(fmaxf(cmax, fmaxf(sv[e4 * 4], sv[e4 * 4 + 1])), fmaxf(sv[e4 * 4 + 2], sv[e4 * 4 + 3]));
+            if (gw[e4] != 0u) {  // a ground-truth positive in these four columns (rare): sum_j gt (2 s - lse_r - lse_c)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int e = e4 * 4 + u;
-              const float x = sv[e] * a.alpha;
-              const float lr = dir ? lcv[u] : lse_mine, lcc = dir ? lse_mine : lcv[u];
-              const float s0 = dir ? l1v[u] : ls_mine, s1 = dir ? ls_mine : l1v[u];
-              const float ab = (x - lr) + (x - lcc);
-              if (gw[e4] != 0u && ((gw[e4] >> (8 * u)) & 0xffu)) psum += ab;  // almost every mask word is zero
-              float sc = ab + (s0 + s1);
-              if (tail && j0 + e >= ncols) sc = -INFINITY;
-              sv[e] = sc;
-              cmax = fmaxf(cmax, sc);
+              for (int u = 0; u < 4; ++u)
+                if ((gw[e4] >> (8 * u)) & 0xffu) {
+                  const int e = e4 * 4 + u;
+                  // 2 alpha S = sv[e] - cv; the other side's lse comes from memory, mine from the register
+                  const float two_x = sv[e] - myvec[e];
+                  psum += two_x - lse_mine - cvec_lse[j0 + e];
+                }
             }
           }
           if (cmax > best) {  // a new running maximum is rare (~ln(columns) times per row): find its first position
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
             if (b2 > best) { best = b2; besti = reinterpret_cast<int*>(sMerge)[k * 384 + 128 + r]; }
             psum += sMerge[k * 384 + 256 + r];
           }
-          (dir ? a.colmax : a.rowmax)[ro] = best;
+          (dir ? a.colmax : a.rowmax)[ro] = best + (ls_mine - lse_mine);
           (dir ? a.colarg : a.rowarg)[ro] = besti;
           if (!dir && a.pos_row_sum) a.pos_row_sum[ro] = psum;
         }

@@ -933,6 +933,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
         const int s = i % FF_STAGES;
         uint8_t* st = sStage + s * FF_STAGE_BYTES;
         mbar_wait(&in_empty[s], ((i / FF_STAGES) & 1) ^ 1);
+        LGB_TR(0, i, 0);
         mbar_expect_tx(&in_full[s], 2 * FB_CBYTES + 512);
         tma_load_4d(st, &tmQ, &in_full[s], 0, h, i * FB_C, qb);
         tma_load_4d(st + FB_CBYTES, &tmDO, &in_full[s], 0, h, i * FB_C, qb);
@@ -977,6 +978,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
       const int s = i % FF_STAGES;
       mbar_wait(&pds_full[i & 1], (i >> 1) & 1);
       tc_fence_after();
+      if (leader) LGB_TR(1, i, 0);
       if (leader) {
         const uint32_t tb = tmem_base + FF_BUF0 + (i & 1) * 128;
         const uint64_t so = (uint64_t)((s * FF_STAGE_BYTES) >> 4);
@@ -990,6 +992,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
                        (i | kk) != 0 ? 1u : 0u);
         umma_commit(&in_empty[s]);
       }
+      if (leader) LGB_TR(1, i, 1);
       __syncwarp();
       if ((i & 1) || i == ntiles - 1) {  // the pair is complete: dQ_pair = dS_pair K
         const int pr = i >> 1;
@@ -1005,7 +1008,9 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
         }
         __syncwarp();
       }
+      if (leader) LGB_TR(1, i, 2);
       if (i + 2 < ntiles) issue_sp(i + 2);
+      if (leader) LGB_TR(1, i, 3);
     }
     if (leader) umma_commit(acc_done);
     __syncwarp();
@@ -1057,6 +1062,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
       mbar_wait(&in_full[s], (i / FF_STAGES) & 1);  // the side vectors of this tile (bulk copies) are visible to this thread
       mbar_wait(&sp_full[buf], (i >> 1) & 1);
       tc_fence_after();
+      if (lane == 0 && (warp == 0 || warp == 15)) LGB_TR(2 + (warp == 15), i, 0);
       float sv[F3_CW], dp[F3_CW];
       tmem_ld16(tb + c * F3_CW, sv);
       tmem_ld16(tb + 64 + c * F3_CW, dp);
@@ -1077,6 +1083,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
         pw[e >> 1] = pack_bf16(p0, p1);
         dw[e >> 1] = pack_bf16(p0 * (dp[e] - dl[e]) * scale, p1 * (dp[e + 1] - dl[e + 1]) * scale);
       }
+      if (lane == 0 && (warp == 0 || warp == 15)) LGB_TR(2 + (warp == 15), i, 1);
       tmem_st8(tb + c * F3_CW, pw);        // P^T over the S^T columns this warpgroup just consumed
       tmem_st8(tb + 64 + c * F3_CW, dw);   // dS^T over the dP^T columns
       // bf16 dS also goes to shared memory, [key][query] (row = this thread's key), for the dQ MMA of the pair
@@ -1091,7 +1098,9 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[buf]);
+      if (lane == 0 && (warp == 0 || warp == 15)) LGB_TR(2 + (warp == 15), i, 2);
       if (buf == 0 && pr >= 1) drain_dq(pr - 1);  // the previous pair's dQ MMAs ran under this tile's exponentials
+      if (lane == 0 && (warp == 0 || warp == 15)) LGB_TR(2 + (warp == 15), i, 3);
     }
     drain_dq(npairs - 1);
     mbar_wait(acc_done, 0);

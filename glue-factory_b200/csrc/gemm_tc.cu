@@ -16,7 +16,10 @@
 
 namespace lgb {
 
-constexpr int GB_M = 128, GB_N = 128, GB_K = 64, G_STAGES = 4;
+#ifndef LGB_G_STAGES
+#define LGB_G_STAGES 4
+#endif
+constexpr int GB_M = 128, GB_N = 128, GB_K = 64, G_STAGES = LGB_G_STAGES;
 constexpr int G_TILE = GB_M * GB_K * 2;  // 16 KiB per operand per stage
 constexpr int G_EPI = 4 * 2 * 4096;      // per-warp staging: two 32-row x 128-byte blocks
 constexpr int G_BIAS = 4 * GB_N * 4;     // per-warp copy of the tile's 128 bias values

@@ -15,10 +15,10 @@ buf = (ctypes.c_longlong * 1024)()
 rc = lib.lgb200_debug_read_trace(buf, 1024)
 t = torch.tensor(list(buf)).view(4, 64, 4)
 t0 = int(t[t > 0].min())
-names = ["producer: empty-wait done, side tile arrive",
-         "mma: pds-wait done, acc issued, sp(i+2) issued",
-         "softmax w0: sp-wait done, ld done, math done, arrive",
-         "softmax w15: sp-wait done, ld done, math done, arrive"]
+names = ["producer: empty-wait done",
+         "mma: pds-wait done, dV/dK issued, (dQ issued), sp(i+2) issued",
+         "softmax w0: sp-wait done, math done, arrive done, drain done",
+         "softmax w15: sp-wait done, math done, arrive done, drain done"]
 for role in range(4):
     print(names[role])
     for i in range(32):
