@@ -811,13 +811,15 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, const vo
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
-__device__ __forceinline__ void bar_softmax() { asm volatile("bar.sync 2, %0;" ::"n"(F3_SWARPS * 32) : "memory"); }
+constexpr int FF_DWARPS = 4;                               // dedicated dQ-drain warpgroup (warps 16..19)
+constexpr int FF_THREADS = (F3_SWARPS + FF_DWARPS + 2) * 32;
+__device__ __forceinline__ void bar_drain() { asm volatile("bar.sync 2, %0;" ::"n"(FF_DWARPS * 32) : "memory"); }
 
-// delta = rowsum(dout * out); lse2 = lse * log2(e); both written token-tile padded: [B*H][nq_pad] with +inf / 0 in the pad
+// delta = rowsum(dout * out) * scale; lse2 = lse * log2(e); both written token-tile padded: [B*H][nq_pad] with +inf / 0 in the pad
 __global__ void __launch_bounds__(256)
     attn_bwd_prep_fused_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                                const float* __restrict__ lse, float* __restrict__ lse2p, float* __restrict__ deltap,
-                               int64_t nrows_pad /* B * nq_pad * H */, int N, int nq_pad, int H) {
+                               int64_t nrows_pad /* B * nq_pad * H */, int N, int nq_pad, int H, float scale) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t r = gid >> 3;  // (b, n_pad, h)
   const int sub = (int)(gid & 7);
@@ -846,7 +848,7 @@ __global__ void __launch_bounds__(256)
   acc += __shfl_xor_sync(0xffffffffu, acc, 4);
   if (live && sub == 0) {
     const int64_t o = (b * H + h) * nq_pad + n;
-    deltap[o] = n < N ? acc : 0.f;
+    deltap[o] = n < N ? acc * scale : 0.f;  // pre-multiplied: dS = P (dP scale - delta scale)
     lse2p[o] = n < N ? lse[(b * H + h) * N + n] * 1.4426950408889634f : INFINITY;  // pad: p = exp2(-inf) = 0
   }
 }
@@ -861,7 +863,7 @@ __global__ void __launch_bounds__(256) dq_convert_kernel(const float* __restrict
   reinterpret_cast<uint4*>(dq)[i] = u;
 }
 
-__global__ void __launch_bounds__(F3_THREADS, 1)
+__global__ void __launch_bounds__(FF_THREADS, 1)
     attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                           const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmDQ,
                           const __nv_bfloat16* __restrict__ kg, const __nv_bfloat16* __restrict__ vg,
@@ -906,23 +908,23 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
       mbar_init(&ds_free[s], 1);
     }
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, F3_SWARPS);
+    mbar_init(dq_empty, FF_DWARPS);
     mbar_init(acc_done, 1);
     mbar_fence_init();
   }
-  if (warp == F3_SWARPS && lane == 0) {
+  if (warp == F3_SWARPS + FF_DWARPS && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmDQ);
   }
-  if (warp == F3_SWARPS + 1) tmem_alloc(tmem_slot, FB_TMEM_COLS);
+  if (warp == F3_SWARPS + FF_DWARPS + 1) tmem_alloc(tmem_slot, FB_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == F3_SWARPS) {
+  if (warp == F3_SWARPS + FF_DWARPS) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(k_full, FB_R * FA_D * 2);
@@ -941,7 +943,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
         bulk_load_1d(st + 2 * FB_CBYTES + 256, dl + i * FB_C, 256, &in_full[s]);
       }
     }
-  } else if (warp == F3_SWARPS + 1) {
+  } else if (warp == F3_SWARPS + FF_DWARPS + 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-convergent, elected lane)
     constexpr uint32_t idesc_s = make_idesc_bf16(FB_R, FB_C, 0, 0);    // (K|V) in TMEM x (Q|dO) K-major
     constexpr uint32_t idesc_acc = make_idesc_bf16(FB_R, FA_D, 0, 1);  // (P^T|dS^T) in TMEM x (dO|Q) MN-major
@@ -1014,6 +1016,45 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
     }
     if (leader) umma_commit(acc_done);
     __syncwarp();
+  } else if (warp >= F3_SWARPS) {
+    // ------------------------------------------------------------------ dQ drain warpgroup
+    // One pair of query tiles at a time: dQ_pair (128 queries x 64 channels fp32, TMEM) -> registers -> swizzled
+    // staging -> TMA reduce-add into the fp32 accumulator.  Kept off the softmax warps: in the first version they did
+    // this between two tiles (two 512-thread barriers + the TMEM read + the staging stores = 840 clk every other tile,
+    // the longest item of their per-pair critical path in the clock64 trace).
+    const int r = (warp & 3) * 32 + lane;    // query row of the pair == TMEM lane (warps 16..19 -> lane quarters 0..3)
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const bool issuer = warp == F3_SWARPS && lane == 0;
+    for (int pr = 0; pr < npairs; ++pr) {
+      mbar_wait(dq_full, pr & 1);
+      tc_fence_after();
+      float v[FA_D];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) tmem_ld16(t_lane + FF_DQ + q4 * 16, v + q4 * 16);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);          // dQ columns are free for the next pair's MMAs
+      if (issuer) tma_store_wait_read<0>();          // the previous pair's reduce has read the staging block
+      bar_drain();
+      // staging: two halves (channels 0-31 / 32-63), each 128 rows x 128 B, 16-byte chunks XOR-swizzled by the row
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint8_t* half = sDQ + hf * (FB_R * 128) + r * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(half + ((j ^ (r & 7)) << 4)) =
+              make_float4(v[hf * 32 + 4 * j], v[hf * 32 + 4 * j + 1], v[hf * 32 + 4 * j + 2], v[hf * 32 + 4 * j + 3]);
+      }
+      fence_proxy_async_smem();
+      bar_drain();
+      if (issuer) {
+        tma_reduce_add_4d(&tmDQ, sDQ, 0, h, pr * FB_R, qb);
+        tma_reduce_add_4d(&tmDQ, sDQ + FB_R * 128, 32, h, pr * FB_R, qb);
+        tma_store_commit();
+      }
+    }
+    if (issuer) tma_store_wait_all();  // the last reduce must have left shared memory before the CTA exits
   } else {
     // ------------------------------------------------------------------ softmax warps
     const int c = warp >> 2;                 // 16-query column slice handled by this warpgroup
@@ -1029,32 +1070,6 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
     }
-    // drain of one dQ pair: TMEM -> swizzled fp32 staging -> TMA reduce-add into the accumulation buffer
-    auto drain_dq = [&](int pr) {
-      mbar_wait(dq_full, pr & 1);
-      tc_fence_after();
-      float v[16];
-      tmem_ld16(t_lane + FF_DQ + c * F3_CW, v);  // row r is QUERY r of the pair here; this warpgroup's 16 channels
-      tmem_ld_wait();
-      tc_fence_before();
-      if (threadIdx.x == 0) tma_store_wait_read<0>();  // the previous pair's reduce has read the staging block
-      bar_softmax();
-      if (lane == 0) mbar_arrive(dq_empty);             // dQ columns are free for the next pair's MMAs
-      // staging: two halves (channels 0-31 / 32-63), each 128 rows x 128 B, 16-byte chunks XOR-swizzled by the row
-      uint8_t* half = sDQ + (c >> 1) * (FB_R * 128) + r * 128;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int chunk = (c & 1) * 4 + j;
-        *reinterpret_cast<float4*>(half + ((chunk ^ (r & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      }
-      fence_proxy_async_smem();
-      bar_softmax();
-      if (threadIdx.x == 0) {
-        tma_reduce_add_4d(&tmDQ, sDQ, 0, h, pr * FB_R, qb);
-        tma_reduce_add_4d(&tmDQ, sDQ + FB_R * 128, 32, h, pr * FB_R, qb);
-        tma_store_commit();
-      }
-    };
     for (int i = 0; i < ntiles; ++i) {
       const int buf = i & 1, pr = i >> 1, s = i % FF_STAGES;
       const uint32_t tb = t_lane + FF_BUF0 + buf * 128;
@@ -1081,7 +1096,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
         const float p0 = fast_exp2(fmaf(sv[e], scale_log2, -l2[e]));
         const float p1 = fast_exp2(fmaf(sv[e + 1], scale_log2, -l2[e + 1]));
         pw[e >> 1] = pack_bf16(p0, p1);
-        dw[e >> 1] = pack_bf16(p0 * (dp[e] - dl[e]) * scale, p1 * (dp[e + 1] - dl[e + 1]) * scale);
+        dw[e >> 1] = pack_bf16(p0 * fmaf(dp[e], scale, -dl[e]), p1 * fmaf(dp[e + 1], scale, -dl[e + 1]));  // dl = delta * scale
       }
       if (lane == 0 && (warp == 0 || warp == 15)) LGB_TR(2 + (warp == 15), i, 1);
       tmem_st8(tb + c * F3_CW, pw);        // P^T over the S^T columns this warpgroup just consumed
@@ -1099,20 +1114,16 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[buf]);
       if (lane == 0 && (warp == 0 || warp == 15)) LGB_TR(2 + (warp == 15), i, 2);
-      if (buf == 0 && pr >= 1) drain_dq(pr - 1);  // the previous pair's dQ MMAs ran under this tile's exponentials
-      if (lane == 0 && (warp == 0 || warp == 15)) LGB_TR(2 + (warp == 15), i, 3);
     }
-    drain_dq(npairs - 1);
     mbar_wait(acc_done, 0);
     tc_fence_after();
     const int64_t o = (((int64_t)kb * Nk + (row < Nk ? row : 0)) * H + h) * FA_D + c * F3_CW;
     store_out_cols16(dv + o, t_lane + FF_DV + c * F3_CW, row < Nk);
     store_out_cols16(dk + o, t_lane + FF_DK + c * F3_CW, row < Nk);
-    if (threadIdx.x == 0) tma_store_wait_all();  // the last reduce must have left shared memory before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == F3_SWARPS + 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
+  if (warp == F3_SWARPS + FF_DWARPS + 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
 }
 
 // workspace of the fused backward, in floats: lse2 / delta padded to whole query tiles + the fp32 dQ accumulator
@@ -1134,7 +1145,7 @@ static int attn_bwd_fused(const void* q, const void* k, const void* v, const voi
     const int64_t nrows = (int64_t)B * nq_pad * H;
     attn_bwd_prep_fused_kernel<<<(unsigned)((nrows * 8 + 255) / 256), 256, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), lse, lse2p, deltap, nrows, Nq,
-        nq_pad, H);
+        nq_pad, H, scale);
   }
   const size_t acc_bytes = (size_t)B * Nq * H * FA_D * 4;
   cudaError_t e = cudaMemsetAsync(dqacc, 0, acc_bytes, stream);
@@ -1151,7 +1162,7 @@ static int attn_bwd_fused(const void* q, const void* k, const void* v, const voi
     if ((rc = make_tmap(&tdq, dqacc, /*fp32=*/true, 4, dims, str, box))) return rc;
   }
   const float sl2 = scale * 1.4426950408889634f;
-  attn_bwd_fused_kernel<<<dim3((Nk + FB_R - 1) / FB_R, H, B), F3_THREADS, FF_SMEM, stream>>>(
+  attn_bwd_fused_kernel<<<dim3((Nk + FB_R - 1) / FB_R, H, B), FF_THREADS, FF_SMEM, stream>>>(
       tq, tdo, tk, tdq, static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v), lse2p, deltap,
       static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv), B, Nq, nq_pad, Nk, H, kv_shift, scale, sl2);
   if ((rc = check_launch("attn_bwd_fused"))) return rc;

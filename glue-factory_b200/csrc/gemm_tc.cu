@@ -5,7 +5,7 @@
 //
 // Persistent CTAs (one per SM) walk 128x128 tiles of C, n fastest so neighbouring CTAs share the A tile in L2.
 // Warp roles: warps 0-3 epilogue, warp 4 TMA producer (one elected lane), warp 5 MMA issuer (warp-convergent, one
-// elected lane) + TMEM owner.  4-stage smem ring of 64-wide K blocks (one 128-byte swizzle atom per operand row)
+// elected lane) + TMEM owner.  6-stage smem ring of 64-wide K blocks (one 128-byte swizzle atom per operand row)
 // that runs ahead across tile boundaries; TWO accumulators in TMEM, so the MMAs of tile i+1 overlap the epilogue
 // of tile i; the epilogue stages 32-row x 128-byte blocks in swizzled smem and stores them with TMA.
 #include <string.h>
@@ -17,7 +17,7 @@
 namespace lgb {
 
 #ifndef LGB_G_STAGES
-#define LGB_G_STAGES 4
+#define LGB_G_STAGES 6  // 192 KiB of operand tiles in flight per SM: 629 vs 691 us over the layer's GEMM shapes (4 stages)
 #endif
 constexpr int GB_M = 128, GB_N = 128, GB_K = 64, G_STAGES = LGB_G_STAGES;
 constexpr int G_TILE = GB_M * GB_K * 2;  // 16 KiB per operand per stage
