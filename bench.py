@@ -286,12 +286,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("LGB200_BENCH_BATCH", "32")), help="pairs per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--kpts", type=int, default=2048, help="keypoints per image: 2048 = BASELINE configs[2] (the headline), "
+                    "1024 = configs[1] (recorded under profiles/, not the driver's line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying "
                     "one CUDA graph of the whole training step")
     args = ap.parse_args()
 
+    global N_KPTS, ATTN_FLOPS_PER_PAIR
+    N_KPTS = args.kpts
+    ATTN_FLOPS_PER_PAIR = 21 * (2 * N_KPTS * N_KPTS * D_DESC) * N_LAYERS
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -320,7 +325,7 @@ def main():
     # is keypoints + descriptors + image sizes + the homography, nothing N x N crosses PCIe
     from gluefactory_b200.matchers.homography_matcher import HomographyMatcher
 
-    trainer = MatcherTrainer(model, lr=1e-4, ground_truth=HomographyMatcher({"th_positive": 3.0, "th_negative": 3.0}))
+    trainer = MatcherTrainer(model, lr=1e-4, ground_truth=HomographyMatcher({"th_positive": 3.0, "th_negative": 3.0, "transposed_assignment": True}))
 
     B = args.batch
     pool = [pin(synthetic.make_pairs(B, N_KPTS, seed=1234 + 1000 * rank + i, with_gt=False)) for i in range(2)]
@@ -391,7 +396,8 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": f"LightGlue matcher train step, N=M={N_KPTS} keypoints, d={D_DESC}, L={N_LAYERS}, H={N_HEADS} "
-                               "(BASELINE.json configs[2]); device GT labels+forward+loss+backward+all-reduce+Adam",
+                               f"(BASELINE.json configs[{2 if N_KPTS == 2048 else 1}]); device GT labels+forward+loss+backward+"
+                               "all-reduce+Adam",
                    "pairs_per_gpu_per_step": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "launch": "cuda-graph replay of the whole step" if use_graph else "eager (host launches)",
                    "l2": "per-step working set (activations + N x N similarities, >1 GB) exceeds the 126 MB L2; inputs rotate",

@@ -53,7 +53,7 @@ SIGNATURES = {
     "lgb200_sinkhorn": (_i, [_vp, _f, _i, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_gt_homography_ws_bytes": (_sz, [_i, _i, _i]),
     "lgb200_gt_from_homography": (_i, [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "lgb200_gt_from_reprojection": (_i, [_vp] * 8 + [_f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lgb200_gt_from_reprojection": (_i, [_vp] * 8 + [_f, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_gt_epipolar_unmatched": (_i, [_vp] * 5 + [_f, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_adam_flat": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _i, _vp, _f, _vp, _vp, _vp, _vp]),
     "lgb200_flat_grad_check": (_i, [_vp, _i64, _vp, _vp]),

@@ -29,6 +29,15 @@ constexpr int FA_KBYTES = FA_BN * FA_D * 2;   // 8 KiB
 constexpr int FA_SMEM = FA_QBYTES + FA_STAGES * 2 * FA_KBYTES + 256;
 constexpr int FA_TMEM_COLS = 256;             // S0 [0,64) S1 [64,128) (P over their first 32 columns), O [128,192)
 constexpr int FA_S_COL = 0, FA_O_COL = 128;
+// P_j gets its own columns [192,224) / [224,256).  The first version of this kernel wrote P over the first 32 columns of
+// the S tile it came from (as the backward kernels do) and was NOT deterministic: S(j+2) is issued right behind P V(j)
+// into the same buffer, and with the write-after-read distance of zero MMAs (the backward has >= 4 MMAs in between)
+// repeated launches differed, occasionally by a whole 128-row block (scripts/stress_attn.py).
+#ifdef LGB_FWD_PALIAS
+#define FA_P_COL(j) (FA_S_COL + ((j) & 1) * FA_BN)
+#else
+#define FA_P_COL(j) (192 + ((j) & 1) * 32)
+#endif
 
 // Optional clock64 pipeline trace of CTA (0,0,0) (read back with lgb200_debug_read_trace / scripts/trace_attn.py):
 // -DLGB_TRACE=1 traces the dKV kernel, -DLGB_TRACE=3 the forward kernel.
@@ -167,7 +176,7 @@ __global__ void __launch_bounds__(192, 2)
       tc_fence_after();
       if (leader) {
         const uint64_t dv = dV0 + (uint64_t)((s * FA_KBYTES) >> 4);
-        const uint32_t pcol = tmem_base + FA_S_COL + (j & 1) * FA_BN;  // keys [kk*16, +16) at P columns kk*8
+        const uint32_t pcol = tmem_base + FA_P_COL(j);  // keys [kk*16, +16) at P columns kk*8
 #pragma unroll
         for (int kk = 0; kk < FA_BN / 16; ++kk)
           umma_bf16_ts(tmem_base + FA_O_COL, pcol + kk * 8, dv + (uint64_t)(kk * 128), idesc_o,
@@ -207,7 +216,11 @@ __global__ void __launch_bounds__(192, 2)
       // exact running maximum, one of a warp's 32 rows moves in most tiles and the skip would rarely trigger.)
       const float m_cand = fmaxf(m, mx * scale_log2);
       float alpha = 1.f, m_new = m;
+#ifdef LGB_FWD_EAGER
+      if (true) {
+#else
       if (__any_sync(0xffffffffu, m_cand - m > 8.f)) {  // first tile: m = -inf, always taken
+#endif
         m_new = m_cand;
         alpha = fast_exp2(m - m_new);  // first tile: exp2(-inf) = 0 (O is overwritten by its P V anyway)
         if (j > 0) {                   // the P V of tile j-1 must have landed before its result is rescaled
@@ -235,8 +248,8 @@ __global__ void __launch_bounds__(192, 2)
         lsum += p0 + p1;
         pw[e >> 1] = pack_bf16(p0, p1);
       }
-      tmem_st16(sbuf, pw);            // P_j over the first 32 columns of the S tile it came from
-      tmem_st16(sbuf + 16, pw + 16);
+      tmem_st16(t_lane + FA_P_COL(j), pw);  // P_j (bf16, two keys per column) into its own 32 TMEM columns
+      tmem_st16(t_lane + FA_P_COL(j) + 16, pw + 16);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

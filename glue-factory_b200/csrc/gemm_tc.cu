@@ -233,6 +233,216 @@ __global__ void __launch_bounds__(192, 1)
   if (warp == 5) tmem_dealloc(tmem_base, 256);
 }
 
+// ---------------------------------------------------------------------------------------------
+// A-panel-resident variant for the layer's K <= 256 GEMMs (y = x W^T and dx = dy W with a 256-wide contraction: 6 of the
+// 10 forward projections and 5 of the 9 input-gradient GEMMs of a layer).  The generic kernel above re-loads the A tile
+// for every n-tile and is bound by the L2 -> SM path (128 KiB of operands per 128 x 128 output tile, ncu: DRAM 50 %,
+// tensor 37 %, nothing saturated).  Here a work item is one 128-row panel of A: the panel (KB x 16 KiB) is loaded ONCE
+// into one of two resident buffers (the next item's panel is prefetched while this one is multiplied), only the B
+// blocks stream through a ring, and the CTA walks all n-tiles of the panel.  Operand bytes per panel for N = 256:
+// 64 + 128 KiB instead of 256 KiB; for N = 768: 64 + 384 instead of 768.  A is K-major (rows of x / dy).
+// Same TMEM double-buffered accumulators and the same epilogue (bias, bf16 / fp32, TMA store or reduce-add).
+// ---------------------------------------------------------------------------------------------
+constexpr int GP_KB = 4;                      // K <= 256
+constexpr int GP_BSTAGES = 4;                 // 16 KiB B blocks in flight
+constexpr int GP_BBLK = GB_N * GB_K * 2;      // 16 KiB
+constexpr int GP_SMEM = 2 * GP_KB * G_TILE + GP_BSTAGES * GP_BBLK + G_EPI + G_BIAS + 256;
+
+template <bool B_MN, typename OutT>
+__global__ void __launch_bounds__(192, 1)
+    gemm_apanel_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmC, int M, int N, int K, float alpha, int tiles_m, int tiles_n,
+                       const float* __restrict__ bias, int reduce_add) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                                   // [2 panels][GP_KB blocks]
+  uint8_t* sB = smem + 2 * GP_KB * G_TILE;              // [GP_BSTAGES]
+  uint8_t* sEp = sB + GP_BSTAGES * GP_BBLK;
+  float* sBias = reinterpret_cast<float*>(sEp + G_EPI);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEp + G_EPI + G_BIAS);
+  uint64_t* a_full = bars;                 // [2]
+  uint64_t* a_empty = bars + 2;            // [2]
+  uint64_t* b_full = bars + 4;             // [GP_BSTAGES]
+  uint64_t* b_empty = b_full + GP_BSTAGES; // [GP_BSTAGES]
+  uint64_t* acc_full = b_empty + GP_BSTAGES;  // [2]
+  uint64_t* acc_empty = acc_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = (K + GB_K - 1) / GB_K;
+  const int nitems = tiles_m;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    for (int s = 0; s < GP_BSTAGES; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      auto load_panel = [&](int item, int li) {  // li: this CTA's running item index -> panel buffer li & 1
+        const int pa = li & 1;
+        mbar_wait(&a_empty[pa], ((li >> 1) & 1) ^ 1);
+        mbar_expect_tx(&a_full[pa], KB * G_TILE);
+        for (int kb = 0; kb < KB; ++kb) tma_load_3d(sA + (pa * GP_KB + kb) * G_TILE, &tmA, &a_full[pa], kb * GB_K, item * GB_M, 0);
+      };
+      int li = 0, bi = 0;
+      if ((int)blockIdx.x < nitems) load_panel(blockIdx.x, 0);
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++li) {
+        for (int nt = 0; nt < tiles_n; ++nt) {
+          // the next item's panel is requested after this item's first n-tile is on its way: its buffer is released when
+          // the PREVIOUS item's MMAs retire, and by then they have (the B ring's back-pressure paces this thread)
+          if (nt == (tiles_n > 1 ? 1 : 0) && item + (int)gridDim.x < nitems && tiles_n > 1)
+            load_panel(item + gridDim.x, li + 1);
+          for (int kb = 0; kb < KB; ++kb, ++bi) {
+            const int s = bi % GP_BSTAGES;
+            mbar_wait(&b_empty[s], ((bi / GP_BSTAGES) & 1) ^ 1);
+            mbar_expect_tx(&b_full[s], GP_BBLK);
+            uint8_t* bb = sB + s * GP_BBLK;
+            if (!B_MN) {
+              tma_load_3d(bb, &tmB, &b_full[s], kb * GB_K, nt * GB_N, 0);
+            } else {
+              tma_load_3d(bb, &tmB, &b_full[s], nt * GB_N, kb * GB_K, 0);
+              tma_load_3d(bb + 8192, &tmB, &b_full[s], nt * GB_N + 64, kb * GB_K, 0);
+            }
+          }
+        }
+        if (tiles_n == 1 && item + (int)gridDim.x < nitems) load_panel(item + gridDim.x, li + 1);
+      }
+    }
+  } else if (warp == 5) {
+    constexpr uint32_t idesc = make_idesc_bf16(GB_M, GB_N, 0, B_MN ? 1 : 0);
+    const uint64_t ad0 = make_smem_desc(smem_u32(sA), 16, 1024);
+    const uint64_t bd0 = B_MN ? make_smem_desc(smem_u32(sB), 8192, 1024) : make_smem_desc(smem_u32(sB), 16, 1024);
+    constexpr uint64_t a_step = 32 >> 4, b_step = (B_MN ? 2048 : 32) >> 4;
+    const bool leader = elect_one();
+    int li = 0, bi = 0, lt = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++li) {
+      const int pa = li & 1;
+      mbar_wait(&a_full[pa], (li >> 1) & 1);
+      for (int nt = 0; nt < tiles_n; ++nt, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb, ++bi) {
+          const int s = bi % GP_BSTAGES;
+          mbar_wait(&b_full[s], (bi / GP_BSTAGES) & 1);
+          tc_fence_after();
+          if (leader) {
+            const uint64_t ao = (uint64_t)(((pa * GP_KB + kb) * G_TILE) >> 4), bo = (uint64_t)((s * GP_BBLK) >> 4);
+#pragma unroll
+            for (int kk = 0; kk < GB_K / 16; ++kk)
+              umma_bf16(tmem_base + acc * GB_N, ad0 + ao + kk * a_step, bd0 + bo + kk * b_step, idesc, (kb | kk) != 0 ? 1u : 0u);
+            umma_commit(&b_empty[s]);
+          }
+          __syncwarp();
+        }
+        if (leader) {
+          umma_commit(&acc_full[acc]);
+          if (nt == tiles_n - 1) umma_commit(&a_empty[pa]);  // every MMA that reads this panel has been issued
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    constexpr int CW = 128 / (int)sizeof(OutT);
+    uint8_t* stage = sEp + warp * 8192;
+    int lt = 0, nblk = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int m0 = item * GB_M;
+      for (int nt = 0; nt < tiles_n; ++nt, ++lt) {
+        const int n0 = nt * GB_N, acc = lt & 1;
+        float* sb = sBias + warp * GB_N;
+        if (bias) {
+          __syncwarp();
+          const int col = n0 + lane * 4;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col + 3 < N && (reinterpret_cast<uintptr_t>(bias + col) & 15) == 0) {
+            bv = *reinterpret_cast<const float4*>(bias + col);
+          } else {
+            if (col < N) bv.x = bias[col];
+            if (col + 1 < N) bv.y = bias[col + 1];
+            if (col + 2 < N) bv.z = bias[col + 2];
+            if (col + 3 < N) bv.w = bias[col + 3];
+          }
+          *reinterpret_cast<float4*>(sb + lane * 4) = bv;
+          __syncwarp();
+        }
+        mbar_wait(&acc_full[acc], (lt >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < GB_N / CW; ++c, ++nblk) {
+          uint8_t* blk = stage + (nblk & 1) * 4096;
+          float v[CW];
+#pragma unroll
+          for (int q = 0; q < CW / 32; ++q)
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * GB_N + c * CW + q * 32, v + q * 32);
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          tmem_ld_wait();
+          if (c == GB_N / CW - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+          }
+          if (bias) {
+#pragma unroll
+            for (int q4 = 0; q4 < CW / 4; ++q4) {
+              const float4 bq = *reinterpret_cast<const float4*>(sb + c * CW + q4 * 4);
+              v[4 * q4] = fmaf(v[4 * q4], alpha, bq.x); v[4 * q4 + 1] = fmaf(v[4 * q4 + 1], alpha, bq.y);
+              v[4 * q4 + 2] = fmaf(v[4 * q4 + 2], alpha, bq.z); v[4 * q4 + 3] = fmaf(v[4 * q4 + 3], alpha, bq.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < CW; ++i) v[i] *= alpha;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 u;
+            if constexpr (sizeof(OutT) == 4) {
+              u.x = __float_as_uint(v[4 * j]); u.y = __float_as_uint(v[4 * j + 1]);
+              u.z = __float_as_uint(v[4 * j + 2]); u.w = __float_as_uint(v[4 * j + 3]);
+            } else {
+              u.x = pack_bf16(v[8 * j], v[8 * j + 1]); u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+              u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            }
+            *reinterpret_cast<uint4*>(blk + lane * 128 + ((j ^ (lane & 7)) << 4)) = u;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (reduce_add) tma_reduce_add_3d(&tmC, blk, n0 + c * CW, m0 + warp * 32, 0);
+            else tma_store_3d(&tmC, blk, n0 + c * CW, m0 + warp * 32, 0);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 256);
+}
+
 template <bool A_MN, bool B_MN, typename OutT>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int batch, int M, int N, int K,
                        int64_t ldc, int64_t strideC, float alpha, cudaStream_t stream, int kps = 0,
@@ -396,6 +606,34 @@ extern "C" int lgb200_linear(const void* A, const void* B, void* C, const float*
   CUtensorMap ta, tb;
   int rc = make_ab_maps(&ta, &tb, A, B, 1, M, N, K, a_mn_major, b_mn_major, lda, ldb, 0, 0);
   if (rc) return rc;
+  {  // A-panel-resident kernel: K <= 256, K-major A, C reachable by TMA
+    const int es = c_dtype == LGB200_F32 ? 4 : 2;
+    static const bool off = env_flag("LGB200_GEMM_NO_APANEL");
+    const bool c_ok = (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc * es) % 16 == 0;
+    if (!off && !a_mn_major && K <= GP_KB * GB_K && c_ok && (c_dtype == LGB200_F32 || c_dtype == LGB200_BF16)) {
+      CUtensorMap tc;
+      const uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, 1};
+      const uint64_t str[2] = {(uint64_t)ldc * es, (uint64_t)M * ldc * es};
+      const uint32_t box[3] = {128u / es, 32u, 1u};
+      if ((rc = make_tmap(&tc, C, es == 4, 3, dims, str, box))) return rc;
+      const int tiles_m = (M + GB_M - 1) / GB_M, tiles_n = (N + GB_N - 1) / GB_N;
+      const int sms = device_sm_count();
+      const unsigned grid = (unsigned)(tiles_m < sms ? tiles_m : sms);
+#define LGB_AP_LAUNCH(BMJ, T)                                                                                    \
+  {                                                                                                              \
+    auto kern = gemm_apanel_kernel<BMJ, T>;                                                                      \
+    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), GP_SMEM))) return rc;                        \
+    kern<<<grid, 192, GP_SMEM, stream>>>(ta, tb, tc, M, N, K, alpha, tiles_m, tiles_n, bias, accumulate ? 1 : 0); \
+    return check_launch("linear(apanel)");                                                                       \
+  }
+      if (c_dtype == LGB200_F32) {
+        if (b_mn_major) LGB_AP_LAUNCH(true, float) else LGB_AP_LAUNCH(false, float)
+      } else {
+        if (b_mn_major) LGB_AP_LAUNCH(true, __nv_bfloat16) else LGB_AP_LAUNCH(false, __nv_bfloat16)
+      }
+#undef LGB_AP_LAUNCH
+    }
+  }
 #define LGB_LIN_CASE(AM, BMJ)                                                                                       \
   if (a_mn_major == AM && b_mn_major == BMJ) {                                                                      \
     if (c_dtype == LGB200_F32)                                                                                      \

@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(256) gt_h_label_kernel(const float* __restrict
                                                         int64_t* __restrict__ m0, int64_t* __restrict__ m1,
                                                         uint8_t* __restrict__ assignment, int M, int N,
                                                         const uint8_t* __restrict__ valid0,
-                                                        const uint8_t* __restrict__ valid1) {
+                                                        const uint8_t* __restrict__ valid1,
+                                                        uint8_t* __restrict__ assignment_t /* [B,N,M] or null */) {
   // valid0 / valid1 (or null): "unmatched" additionally requires a valid depth (gt_generation.py:66-67)
   const int b = blockIdx.y, t = blockIdx.x * 256 + threadIdx.x;
   if (t < M) {
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(256) gt_h_label_kernel(const float* __restrict
     if (row_d0[o] > neg2 && (!valid0 || valid0[o])) m = -1;
     m0[o] = m;
     if (pos && assignment) assignment[((int64_t)b * M + t) * N + j] = 1;
+    if (pos && assignment_t) assignment_t[((int64_t)b * N + j) * M + t] = 1;  // the transposed copy, for column-wise readers
   }
   if (t < N) {
     const int64_t o = (int64_t)b * N + t;
@@ -248,8 +250,8 @@ size_t lgb200_gt_homography_ws_bytes(int B, int M, int N) {
 
 int lgb200_gt_from_reprojection(const float* kp0, const float* kp1, const float* kp0_1, const float* kp1_0,
                                 const uint8_t* vis0, const uint8_t* vis1, const uint8_t* valid0, const uint8_t* valid1,
-                                float pos_th, float neg_th, int64_t* m0, int64_t* m1, uint8_t* assignment, void* ws, int B,
-                                int M, int N, cudaStream_t stream) {
+                                float pos_th, float neg_th, int64_t* m0, int64_t* m1, uint8_t* assignment,
+                                uint8_t* assignment_t, void* ws, int B, int M, int N, cudaStream_t stream) {
   LGB_REQUIRE(kp0 && kp1 && kp0_1 && kp1_0 && m0 && m1 && ws, kErrInvalid, "gt_from_reprojection: null pointer");
   LGB_REQUIRE(B > 0 && M > 0 && N > 0, kErrInvalid, "gt_from_reprojection: empty input B=%d M=%d N=%d", B, M, N);
   LGB_REQUIRE(((reinterpret_cast<uintptr_t>(kp0) | reinterpret_cast<uintptr_t>(kp1) |
@@ -271,6 +273,10 @@ int lgb200_gt_from_reprojection(const float* kp0, const float* kp1, const float*
     cudaError_t e = cudaMemsetAsync(assignment, 0, (size_t)B * M * N, stream);
     LGB_REQUIRE(e == cudaSuccess, kErrCuda, "gt_from_reprojection: memset: %s", cudaGetErrorString(e));
   }
+  if (assignment_t) {
+    cudaError_t e = cudaMemsetAsync(assignment_t, 0, (size_t)B * M * N, stream);
+    LGB_REQUIRE(e == cudaSuccess, kErrCuda, "gt_from_reprojection: memset: %s", cudaGetErrorString(e));
+  }
   gt_h_scan_kernel<<<dim3(nstrips, B), 256, 0, stream>>>(
       reinterpret_cast<const float2*>(kp0), reinterpret_cast<const float2*>(kp1),
       reinterpret_cast<const float2*>(kp0_1), reinterpret_cast<const float2*>(kp1_0), row_dist, row_arg, row_d0,
@@ -280,7 +286,7 @@ int lgb200_gt_from_reprojection(const float* kp0, const float* kp1, const float*
   const int L = M > N ? M : N;
   gt_h_label_kernel<<<dim3((L + 255) / 256, B), 256, 0, stream>>>(row_dist, row_arg, row_d0, col_dist, col_arg, col_d1,
                                                                   pos_th * pos_th, neg_th * neg_th, m0, m1, assignment,
-                                                                  M, N, valid0, valid1);
+                                                                  M, N, valid0, valid1, assignment_t);
   return check_launch("gt_from_reprojection");
 }
 
@@ -288,7 +294,7 @@ int lgb200_gt_from_homography(const float* kp0, const float* kp1, const float* k
                               float neg_th, int64_t* m0, int64_t* m1, uint8_t* assignment, void* ws, int B, int M,
                               int N, cudaStream_t stream) {
   return lgb200_gt_from_reprojection(kp0, kp1, kp0_1, kp1_0, nullptr, nullptr, nullptr, nullptr, pos_th, neg_th, m0, m1,
-                                     assignment, ws, B, M, N, stream);
+                                     assignment, nullptr, ws, B, M, N, stream);
 }
 
 int lgb200_gt_epipolar_unmatched(const float* kp0, const float* kp1, const float* F, const uint8_t* valid0,

@@ -69,6 +69,9 @@ class DepthMatcher(nn.Module):
         "overlap_th": 0.2,
         "min_visibility_th": 0.5,
         "dense_assignment": True,  # plugin-only: materialise the boolean [B,M,N] assignment (the reference always does)
+        # plugin-only: also emit `assignment_t`, the [B,N,M] transpose, in the same pass (saves the B200 matcher's loss a
+        # 0.5 ms transpose per step: its fused assignment backward walks the mask by columns too)
+        "transposed_assignment": False,
     }
     required_data_keys = ["view0", "view1", "T_0to1"]
 
@@ -109,7 +112,7 @@ class DepthMatcher(nn.Module):
         kp1_0, visible1 = project(kp1, d1, depth0, cam1, cam0, T_1to0, valid1, ccth=conf.th_consistency)
         out = ops.gt_matches_from_reprojection(kp0, kp1, kp0_1, kp1_0, visible0, visible1, valid0, valid1,
                                                pos_th=conf.th_positive, neg_th=conf.th_negative,
-                                               dense=bool(conf.dense_assignment))
+                                               dense=bool(conf.dense_assignment), dense_t=bool(conf.transposed_assignment))
         if conf.th_epi is not None:
             # F = K1^-T [t]x R K0^-1 (gt_generation.py:76-80, epipolar.py:7-9); note the reference thresholds the
             # epipolar distance with th_negative (neg_th), not with th_epi, which only switches the step on

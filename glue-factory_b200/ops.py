@@ -409,7 +409,7 @@ def wgrad_bf16(dy, a, out=None):
     return out
 
 
-def gt_matches_from_homography(kp0, kp1, H, pos_th=3.0, neg_th=6.0, dense=True):
+def gt_matches_from_homography(kp0, kp1, H, pos_th=3.0, neg_th=6.0, dense=True, dense_t=False):
     """Device-side gt_matches_from_homography (geometry/gt_generation.py:109-161; defaults as the reference's).
     kp0 [B,M,2], kp1 [B,N,2] pixel coordinates, H [B,3,3] -> dict with `assignment` (bool [B,M,N], omitted when
     dense=False), `matches0/1` (int64: index, -1 unmatched, -2 ignored), `matching_scores0/1`, `proj_0to1/1to0`.
@@ -418,27 +418,19 @@ def gt_matches_from_homography(kp0, kp1, H, pos_th=3.0, neg_th=6.0, dense=True):
 
     kp0, kp1 = kp0.float().contiguous(), kp1.float().contiguous()
     _chk(kp0, torch.float32), _chk(kp1, torch.float32)
-    B, M = kp0.shape[:2]
-    N = kp1.shape[1]
+    B = kp0.shape[0]
     Hm = H.float().expand(B, 3, 3) if H.dim() == 2 else H.float()
     kp0_1 = warp_points(kp0, Hm).contiguous()  # O(M+N): homography.py:161-180
     kp1_0 = warp_points(kp1, inv3x3(Hm)).contiguous()
-    dev = kp0.device
-    m0 = torch.empty(B, M, device=dev, dtype=torch.int64)
-    m1 = torch.empty(B, N, device=dev, dtype=torch.int64)
-    asg = torch.empty(B, M, N, device=dev, dtype=torch.bool) if dense else None
-    ws = torch.empty(_lib.load().lgb200_gt_homography_ws_bytes(B, M, N), device=dev, dtype=torch.uint8)
-    call("lgb200_gt_from_homography", ptr(kp0), ptr(kp1), ptr(kp0_1), ptr(kp1_0), float(pos_th), float(neg_th), ptr(m0),
-         ptr(m1), ptr(asg), ptr(ws), B, M, N, stream_ptr())
-    out = {"matches0": m0, "matches1": m1, "matching_scores0": (m0 > -1).float(), "matching_scores1": (m1 > -1).float(),
-           "proj_0to1": kp0_1, "proj_1to0": kp1_0}
-    if dense:
-        out["assignment"] = asg
+    out = gt_matches_from_reprojection(kp0, kp1, kp0_1, kp1_0, pos_th=pos_th, neg_th=neg_th, dense=dense, dense_t=dense_t)
+    m0, m1 = out["matches0"], out["matches1"]
+    out.update({"matching_scores0": (m0 > -1).float(), "matching_scores1": (m1 > -1).float(), "proj_0to1": kp0_1,
+                "proj_1to0": kp1_0})
     return out
 
 
 def gt_matches_from_reprojection(kp0, kp1, kp0_1, kp1_0, visible0=None, visible1=None, valid0=None, valid1=None,
-                                 pos_th=3.0, neg_th=5.0, dense=True):
+                                 pos_th=3.0, neg_th=5.0, dense=True, dense_t=False):
     """The O(M N) label pass of gt_matches_from_pose_depth (geometry/gt_generation.py:47-74) for given reprojections:
     kp0_1 = view-0 keypoints projected into view 1, kp1_0 the converse, visibility / depth-validity masks [B,M] /
     [B,N] (bool; None = all true).  Returns assignment (bool [B,M,N] when dense), matches0/1 (int64: index, -1, -2)."""
@@ -451,12 +443,15 @@ def gt_matches_from_reprojection(kp0, kp1, kp0_1, kp1_0, visible0=None, visible1
     m0 = torch.empty(B, M, device=dev, dtype=torch.int64)
     m1 = torch.empty(B, N, device=dev, dtype=torch.int64)
     asg = torch.empty(B, M, N, device=dev, dtype=torch.bool) if dense else None
+    asg_t = torch.empty(B, N, M, device=dev, dtype=torch.bool) if dense_t else None
     ws = torch.empty(_lib.load().lgb200_gt_homography_ws_bytes(B, M, N), device=dev, dtype=torch.uint8)
     call("lgb200_gt_from_reprojection", ptr(kp0), ptr(kp1), ptr(kp0_1), ptr(kp1_0), ptr(vis0), ptr(vis1), ptr(val0),
-         ptr(val1), float(pos_th), float(neg_th), ptr(m0), ptr(m1), ptr(asg), ptr(ws), B, M, N, stream_ptr())
+         ptr(val1), float(pos_th), float(neg_th), ptr(m0), ptr(m1), ptr(asg), ptr(asg_t), ptr(ws), B, M, N, stream_ptr())
     out = {"matches0": m0, "matches1": m1}
     if dense:
         out["assignment"] = asg
+    if dense_t:
+        out["assignment_t"] = asg_t  # [B,N,M]: the same mask transposed (read by the fused assignment backward)
     return out
 
 

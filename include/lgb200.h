@@ -255,11 +255,13 @@ int lgb200_gt_from_homography(const float* kp0, const float* kp1, const float* k
 /* Same O(M N) label pass for ANY pair of reprojections (pose + depth ground truth, geometry/gt_generation.py:13-106):
  * vis0 [B,M] / vis1 [B,N] (bool, both or neither): the joint distance of a pair counts only when both points are
  * visible in the other view; valid0 / valid1 (bool, both or neither): "unmatched" (-1) additionally needs a valid depth.
- * ws: lgb200_gt_homography_ws_bytes(B, M, N).  With all four masks NULL this is lgb200_gt_from_homography. */
+ * assignment_t (may be NULL): the [B,N,M] transpose of `assignment`, written in the same pass (the fused assignment
+ * backward walks the mask by columns too).  ws: lgb200_gt_homography_ws_bytes(B, M, N).  With all four masks NULL this is
+ * lgb200_gt_from_homography. */
 int lgb200_gt_from_reprojection(const float* kp0, const float* kp1, const float* kp0_1, const float* kp1_0,
                                 const uint8_t* vis0, const uint8_t* vis1, const uint8_t* valid0, const uint8_t* valid1,
-                                float pos_th, float neg_th, int64_t* m0, int64_t* m1, uint8_t* assignment, void* ws, int B,
-                                int M, int N, cudaStream_t stream);
+                                float pos_th, float neg_th, int64_t* m0, int64_t* m1, uint8_t* assignment,
+                                uint8_t* assignment_t, void* ws, int B, int M, int N, cudaStream_t stream);
 /* Extra unmatched labels from epipolar geometry (gt_generation.py:82-90; th_epi of matchers/depth_matcher.py): points
  * without valid depth that are still "ignore" (-2) become -1 when every still-ignored point of the other view is
  * further than th from their epipolar line (symmetric distance of geometry/epipolar.py:59-72, F [B,3,3] row-major).

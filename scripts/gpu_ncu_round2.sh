@@ -7,3 +7,5 @@ timeout 300 $NCU -k regex:gemm_bf16_kernel -s 40 -c 10 -o gpurun_out/r02_gemm -f
 timeout 300 $NCU -k regex:assign_tc_kernel -c 3 -o gpurun_out/r02_assign -f python scripts/prof_step.py > gpurun_out/ncu_assign.log 2>&1; echo "ncu assign rc=$?"
 timeout 300 $NCU -k regex:attn_ -c 4 -o gpurun_out/r02_attn -f python scripts/prof_step.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
 ls -la gpurun_out/*.ncu-rep
+# per-launch DRAM traffic of the attention backward at the bench batch size (for bench.py's roofline.traffic)
+timeout 300 $NCU -k regex:attn_bwd -c 3 -o gpurun_out/r02_attn_bwd -f python scripts/prof_step.py > gpurun_out/ncu_attn_bwd.log 2>&1; echo "ncu attn_bwd rc=$?"

@@ -11,7 +11,7 @@ conf = dict(synthetic.DEFAULT_CONF, precision="bf16")
 model = LightGlue(conf)
 model.load_state_dict(synthetic.make_weights(conf, seed=0), strict=False)
 from gluefactory_b200.matchers.homography_matcher import HomographyMatcher
-trainer = MatcherTrainer(model.to(dev), lr=1e-4, ground_truth=HomographyMatcher({"th_positive": 3.0, "th_negative": 3.0}))
+trainer = MatcherTrainer(model.to(dev), lr=1e-4, ground_truth=HomographyMatcher({"th_positive": 3.0, "th_negative": 3.0, "transposed_assignment": True}))
 data = synthetic.to_device(synthetic.make_pairs(B, 2048, seed=1, with_gt=False), dev)
 for _ in range(3):
     trainer.step(data)

@@ -366,8 +366,9 @@ def test_gt_from_homography_matches_restatement_at_size(B, M, N):
     assert torch.equal(r["matches0"], m0) and torch.equal(r["matches1"], m1)
     assert torch.equal(r["assignment"], asg)
     assert int(asg.sum()) > 0
-    sparse = ops.gt_matches_from_homography(kp0, kp1, H, 3.0, 3.0, dense=False)
+    sparse = ops.gt_matches_from_homography(kp0, kp1, H, 3.0, 3.0, dense=False, dense_t=True)
     assert "assignment" not in sparse and torch.equal(sparse["matches0"], m0)
+    assert torch.equal(sparse["assignment_t"], asg.transpose(1, 2))  # the transposed mask written in the same pass
 
 
 def test_gt_from_pose_depth_matches_reference_labels():
