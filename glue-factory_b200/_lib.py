@@ -51,6 +51,8 @@ SIGNATURES = {
     "lgb200_heads_ws_bytes": (_sz, [_i, _i, _i]),
     "lgb200_log_double_softmax": (_i, [_vp, _f, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_sinkhorn": (_i, [_vp, _f, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "lgb200_sinkhorn_fwd": (_i, [_vp, _f, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lgb200_sinkhorn_bwd": (_i, [_vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_gt_homography_ws_bytes": (_sz, [_i, _i, _i]),
     "lgb200_gt_from_homography": (_i, [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_gt_from_reprojection": (_i, [_vp] * 8 + [_f, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -88,9 +88,11 @@ int make_tmap(CUtensorMap* out, const void* base, bool fp32, int rank, const uin
 }
 
 int ensure_dyn_smem(const void* func, int bytes) {
+  // remembers the largest size configured per (kernel, device); a kernel whose dynamic size varies from launch to
+  // launch (the Sinkhorn strip cache) raises the limit when a larger request comes along
   constexpr int kMaxFuncs = 64, kMaxDevs = 16;
   static const void* funcs[kMaxFuncs];
-  static unsigned done[kMaxFuncs];  // bit d: configured on device d
+  static int done[kMaxFuncs][kMaxDevs];  // bytes configured on device d (0: never)
   static int nfuncs = 0;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -98,15 +100,15 @@ int ensure_dyn_smem(const void* func, int bytes) {
   int slot = -1;
   for (int i = 0; i < nfuncs; ++i)
     if (funcs[i] == func) slot = i;
-  if (slot >= 0 && dev < kMaxDevs && (done[slot] >> dev & 1u)) return 0;
+  if (slot >= 0 && dev < kMaxDevs && done[slot][dev] >= bytes && done[slot][dev] > 0) return 0;
   e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   LGB_REQUIRE(e == cudaSuccess, kErrCuda, "cudaFuncSetAttribute(%d bytes): %s", bytes, cudaGetErrorString(e));
   if (slot < 0 && nfuncs < kMaxFuncs) {
     slot = nfuncs++;
     funcs[slot] = func;
-    done[slot] = 0;
+    for (int d = 0; d < kMaxDevs; ++d) done[slot][d] = 0;
   }
-  if (slot >= 0 && dev < kMaxDevs) done[slot] |= 1u << dev;
+  if (slot >= 0 && dev < kMaxDevs) done[slot][dev] = bytes > 0 ? bytes : 1;
   return 0;
 }
 

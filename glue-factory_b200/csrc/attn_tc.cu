@@ -27,17 +27,11 @@ constexpr int FA_STAGES = 4;
 constexpr int FA_QBYTES = FA_BM * FA_D * 2;   // 16 KiB
 constexpr int FA_KBYTES = FA_BN * FA_D * 2;   // 8 KiB
 constexpr int FA_SMEM = FA_QBYTES + FA_STAGES * 2 * FA_KBYTES + 256;
-constexpr int FA_TMEM_COLS = 256;             // S0 [0,64) S1 [64,128) (P over their first 32 columns), O [128,192)
+constexpr int FA_TMEM_COLS = 256;             // S0 [0,64) S1 [64,128), O [128,192), P0 [192,224) P1 [224,256)
 constexpr int FA_S_COL = 0, FA_O_COL = 128;
-// P_j gets its own columns [192,224) / [224,256).  The first version of this kernel wrote P over the first 32 columns of
-// the S tile it came from (as the backward kernels do) and was NOT deterministic: S(j+2) is issued right behind P V(j)
-// into the same buffer, and with the write-after-read distance of zero MMAs (the backward has >= 4 MMAs in between)
-// repeated launches differed, occasionally by a whole 128-row block (scripts/stress_attn.py).
-#ifdef LGB_FWD_PALIAS
-#define FA_P_COL(j) (FA_S_COL + ((j) & 1) * FA_BN)
-#else
+// P_j (bf16, two keys per column) has its own columns, so S(j+2) -- issued right behind P V(j) -- never writes a
+// buffer the tensor pipe may still be reading.
 #define FA_P_COL(j) (192 + ((j) & 1) * 32)
-#endif
 
 // Optional clock64 pipeline trace of CTA (0,0,0) (read back with lgb200_debug_read_trace / scripts/trace_attn.py):
 // -DLGB_TRACE=1 traces the dKV kernel, -DLGB_TRACE=3 the forward kernel.
@@ -75,13 +69,29 @@ __device__ long long g_trace[4 * 64 * 4];
 #define LGB_TR_LIFE(k) do {} while (0)
 #endif
 
+// exp2 on the FMA / ALU pipes (Cody-Waite split + cubic, relative error 7.5e-5 -- far below the bf16 rounding of P):
+// the MUFU unit does 16 exp2 / clk / SM, which bounds the forward kernel at head_dim 64; every LGB_FWD_POLY-th pair
+// of keys takes one of its two exponentials this way.
+#ifndef LGB_FWD_POLY
+#define LGB_FWD_POLY 0
+#endif
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;        // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);  // [-0.5, 0.5]
+  float p = fmaf(f, 0.0551716685f, 0.2426111251f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // token-major [B, N, H, 64] bf16 -> 4-D tensor map {64, H, N, B}, box {64, 1, rows, 1}
 // ---------------------------------------------------------------------------------------------
 // FORWARD kernel (round 2: the round-1 kernel handed P to the second MMA through shared memory and folded O into 64
 // registers per thread every tile; 226 -> 188 us at 32 sequences, profiles/r02_stage_check.md):
-//   * P never goes through shared memory: the softmax warps write it (bf16, two keys per 32-bit column) over the
-//     first 32 columns of the S tile it was computed from, and P V is a TS-form MMA (A operand in TMEM) exactly like
-//     the accumulating MMAs of the backward kernels -- no st.shared, no fence.proxy.async;
+//   * P never goes through shared memory: the softmax warps write it (bf16, two keys per 32-bit column) into 32 TMEM
+//     columns of its own, and P V is a TS-form MMA (A operand in TMEM) exactly like the accumulating MMAs of the
+//     backward kernels -- no st.shared, no fence.proxy.async;
 //   * O accumulates in TMEM across key tiles (accumulate flag); a softmax warp rescales its O rows in TMEM only when
 //     one of its 32 rows outgrew the reference maximum by more than 2^8 (lazy rescaling: exponentials relative to a
 //     stale maximum, bounded by 256, so after the first few tiles O is never touched again).
@@ -101,12 +111,14 @@ __global__ void __launch_bounds__(192, 2)
   uint64_t* s_full = kv_empty + FA_STAGES;    // [2]
   uint64_t* p_full = s_full + 2;              // [2]
   uint64_t* o_done = p_full + 2;              // one barrier, one phase per key tile (P V of tile j complete)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+  uint64_t* o_final = o_done + 1;             // P V of the LAST tile complete (see the epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
   const int kb = (b + kv_shift) % B;
   const int ntiles = (Nk + FA_BN - 1) / FA_BN;
+  LGB_TRF_LIFE(0);
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -120,6 +132,7 @@ __global__ void __launch_bounds__(192, 2)
       mbar_init(&p_full[s], 4);
     }
     mbar_init(o_done, 1);
+    mbar_init(o_final, 1);
     mbar_fence_init();
   }
   if (warp == 4 && lane == 0) {
@@ -174,6 +187,7 @@ __global__ void __launch_bounds__(192, 2)
       const int s = j % FA_STAGES;
       mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j written (and, if it was needed, O rescaled) by all 4 warps
       tc_fence_after();
+      if (leader) LGB_TRF(1, j, 0);
       if (leader) {
         const uint64_t dv = dV0 + (uint64_t)((s * FA_KBYTES) >> 4);
         const uint32_t pcol = tmem_base + FA_P_COL(j);  // keys [kk*16, +16) at P columns kk*8
@@ -183,9 +197,12 @@ __global__ void __launch_bounds__(192, 2)
                        (j | kk) != 0 ? 1u : 0u);
         umma_commit(&kv_empty[s]);
         umma_commit(o_done);
+        if (j == ntiles - 1) umma_commit(o_final);
       }
+      if (leader) LGB_TRF(1, j, 1);
       __syncwarp();
-      if (j + 2 < ntiles) issue_s(j + 2);  // overwrites the S/P buffer of tile j: ordered behind its P V by the pipe
+      if (j + 2 < ntiles) issue_s(j + 2);  // overwrites the S buffer of tile j (already read by the softmax warps)
+      if (leader) LGB_TRF(1, j, 2);
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroup
@@ -198,10 +215,12 @@ __global__ void __launch_bounds__(192, 2)
       const uint32_t sbuf = t_lane + FA_S_COL + (j & 1) * FA_BN;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      if (lane == 0 && (warp == 0 || warp == 3)) LGB_TRF(2 + (warp == 3), j, 0);
       float sv[FA_BN];
       tmem_ld32(sbuf, sv);
       tmem_ld32(sbuf + 32, sv + 32);
       tmem_ld_wait();
+      if (lane == 0 && (warp == 0 || warp == 3)) LGB_TRF(2 + (warp == 3), j, 1);
       if (tail) {
 #pragma unroll
         for (int e = 0; e < FA_BN; ++e)
@@ -216,14 +235,12 @@ __global__ void __launch_bounds__(192, 2)
       // exact running maximum, one of a warp's 32 rows moves in most tiles and the skip would rarely trigger.)
       const float m_cand = fmaxf(m, mx * scale_log2);
       float alpha = 1.f, m_new = m;
-#ifdef LGB_FWD_EAGER
-      if (true) {
-#else
       if (__any_sync(0xffffffffu, m_cand - m > 8.f)) {  // first tile: m = -inf, always taken
-#endif
         m_new = m_cand;
         alpha = fast_exp2(m - m_new);  // first tile: exp2(-inf) = 0 (O is overwritten by its P V anyway)
         if (j > 0) {                   // the P V of tile j-1 must have landed before its result is rescaled
+          // parity wait on a barrier nobody else polls: safe because S(j) is complete here, hence P V(j-2) is, so
+          // o_done is in phase j-1 or j -- never two phases away from the one awaited
           mbar_wait(o_done, (j - 1) & 1);
           tc_fence_after();
 #pragma unroll
@@ -243,21 +260,31 @@ __global__ void __launch_bounds__(192, 2)
       uint32_t pw[FA_BN / 2];
 #pragma unroll
       for (int e = 0; e < FA_BN; e += 2) {
-        const float p0 = fast_exp2(fmaf(sv[e], scale_log2, -m_new));  // masked keys: exp2(-inf) = 0
-        const float p1 = fast_exp2(fmaf(sv[e + 1], scale_log2, -m_new));
+        const float x0 = fmaf(sv[e], scale_log2, -m_new), x1 = fmaf(sv[e + 1], scale_log2, -m_new);
+        const float p0 = fast_exp2(x0);  // masked keys: exp2(-inf) = 0
+#if LGB_FWD_POLY > 0
+        const float p1 = ((e >> 1) % LGB_FWD_POLY == 0) ? poly_exp2(x1) : fast_exp2(x1);
+#else
+        const float p1 = fast_exp2(x1);
+#endif
         lsum += p0 + p1;
         pw[e >> 1] = pack_bf16(p0, p1);
       }
+      if (lane == 0 && (warp == 0 || warp == 3)) LGB_TRF(2 + (warp == 3), j, 2);
       tmem_st16(t_lane + FA_P_COL(j), pw);  // P_j (bf16, two keys per column) into its own 32 TMEM columns
       tmem_st16(t_lane + FA_P_COL(j) + 16, pw + 16);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
+      if (lane == 0 && (warp == 0 || warp == 3)) LGB_TRF(2 + (warp == 3), j, 3);
       l = l * alpha + lsum;
       m = m_new;
     }
-    mbar_wait(o_done, (ntiles - 1) & 1);
+    // NOT o_done: a warp that has just handed over P(ntiles-1) may find o_done still in phase ntiles-2 (only
+    // P V(ntiles-3) is known complete), whose parity test for phase ntiles-1 passes at once -- the output would be
+    // read before the last two P V products landed (run-to-run differences of `out`, scripts/stress_attn.py).
+    mbar_wait(o_final, 0);
     tc_fence_after();
     const int row = q0 + r;
     const float inv = 1.f / l;
@@ -284,6 +311,7 @@ __global__ void __launch_bounds__(192, 2)
   tc_fence_before();
   __syncthreads();
   if (warp == 5) tmem_dealloc(tmem_base, FA_TMEM_COLS);
+  LGB_TRF_LIFE(1);
 }
 
 static int make_qkv_tmap(CUtensorMap* tm, const void* base, int B, int N, int H, int box_rows) {

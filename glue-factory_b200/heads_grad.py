@@ -1,11 +1,11 @@
 """Backward of the two other assignment heads on the path, as closed-form tensor math.
 
 The forward of both heads is a hand-written kernel (csrc/heads.cu: `lgb200_log_double_softmax`, `lgb200_sinkhorn`).
-Their gradients are assembled here from dense tensor operations on the tensors' own device -- no N x N autograd tape
-(the reference keeps ~100 dense tensors alive for Sinkhorn, superglue.py:186-214): only the two LSE vectors /
-the per-iteration potentials u_k, v_k are kept and the softmax matrices are recomputed on the fly.
-The functions are device-agnostic tensor math, so the formulas are pinned on the CPU against gradients produced by
-the reference's autograd (tests/golden/heads_grad.npz); on the GPU they consume the kernels' outputs.
+No N x N autograd tape (the reference keeps ~100 dense tensors alive for Sinkhorn, superglue.py:186-214): only the
+two LSE vectors / the per-iteration potentials u_k, v_k are kept and the softmax matrices are recomputed on the fly.
+The Sinkhorn gradient runs as a kernel (csrc/heads.cu `sk_bwd_persistent_kernel`); the tensor-math functions below are
+device-agnostic statements of the same formulas, pinned on the CPU against gradients produced by the reference's
+autograd (tests/golden/heads_grad.npz) and used on the GPU as the checker of the kernel.
 """
 import math
 
@@ -97,19 +97,28 @@ class LogDoubleSoftmaxFn(torch.autograd.Function):
 
 
 class LogOptimalTransportFn(torch.autograd.Function):
-    """forward: lgb200_sinkhorn; backward: log_optimal_transport_backward (potentials recomputed)."""
+    """forward: lgb200_sinkhorn_fwd (keeps the O(iters (M+N)) potentials); backward: lgb200_sinkhorn_bwd, the reverse
+    sweep as one persistent kernel (`log_optimal_transport_backward` above is its tensor-math statement, used by the
+    CPU tests to pin the formulas against the reference's autograd)."""
 
     @staticmethod
     def forward(ctx, sim, alpha, iters):
         from . import ops
 
-        out = ops._log_optimal_transport_fwd(sim, float(alpha), iters)
-        ctx.save_for_backward(sim, alpha)
+        sim = sim.contiguous()
+        out, uh, vh = ops._log_optimal_transport_fwd(sim, float(alpha), iters, keep_potentials=True)
+        ctx.save_for_backward(sim, alpha, uh, vh)
         ctx.iters = iters
         return out
 
     @staticmethod
     def backward(ctx, grad):
-        sim, alpha = ctx.saved_tensors
-        dsim, dalpha = log_optimal_transport_backward(sim, alpha.to(sim.dtype), ctx.iters, grad.contiguous())
+        from . import ops
+
+        sim, alpha, uh, vh = ctx.saved_tensors
+        if ctx.iters == 0:      # out = Z - norm
+            M, N = sim.shape[1:]
+            dsim, dalpha = grad[:, :M, :N].contiguous(), grad[:, :M, N].sum() + grad[:, M, :].sum()
+        else:
+            dsim, dalpha = ops._log_optimal_transport_bwd(sim, float(alpha), ctx.iters, grad.contiguous().float(), uh, vh)
         return dsim, dalpha.to(alpha.dtype).reshape(alpha.shape), None

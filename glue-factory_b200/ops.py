@@ -536,13 +536,36 @@ def log_double_softmax(sim, bin_score):
     return _log_double_softmax_fwd(sim, float(bin_score))
 
 
-def _log_optimal_transport_fwd(sim, alpha, iters):
+def _log_optimal_transport_fwd(sim, alpha, iters, keep_potentials=False):
+    """One persistent cooperative kernel for all iterations.  keep_potentials: also return the per-iteration
+    potentials (uh [iters,B,M+1], vh [iters,B,N+1]) the backward sweep consumes."""
     _chk(sim, torch.float32)
     B, M, N = sim.shape
     out = torch.empty(B, M + 1, N + 1, device=sim.device, dtype=torch.float32)
     ws = torch.empty(_lib.load().lgb200_heads_ws_bytes(B, M, N), device=sim.device, dtype=torch.uint8)
-    call("lgb200_sinkhorn", ptr(sim), float(alpha), int(iters), ptr(out), ptr(ws), B, M, N, stream_ptr())
-    return out
+    if not keep_potentials:
+        call("lgb200_sinkhorn", ptr(sim), float(alpha), int(iters), ptr(out), ptr(ws), B, M, N, stream_ptr())
+        return out
+    uh = torch.empty(max(iters, 1), B, M + 1, device=sim.device, dtype=torch.float32)
+    vh = torch.empty(max(iters, 1), B, N + 1, device=sim.device, dtype=torch.float32)
+    call("lgb200_sinkhorn_fwd", ptr(sim), float(alpha), int(iters), ptr(out), ptr(uh), ptr(vh), ptr(ws), B, M, N,
+         stream_ptr())
+    return out, uh, vh
+
+
+def _log_optimal_transport_bwd(sim, alpha, iters, grad, uh, vh):
+    """Reverse sweep of the iterations (lgb200_sinkhorn_bwd): returns dsim [B,M,N] and d alpha (0-dim)."""
+    _chk(sim, torch.float32)
+    _chk(grad, torch.float32)
+    B, M, N = sim.shape
+    assert grad.shape == (B, M + 1, N + 1) and iters > 0
+    dsim = torch.empty_like(sim)
+    dzr = torch.empty(B, N + 1, device=sim.device, dtype=torch.float32)
+    dzc = torch.empty(B, M, device=sim.device, dtype=torch.float32)
+    ws = torch.empty(_lib.load().lgb200_heads_ws_bytes(B, M, N), device=sim.device, dtype=torch.uint8)
+    call("lgb200_sinkhorn_bwd", ptr(sim), float(alpha), int(iters), ptr(grad), ptr(uh), ptr(vh), ptr(dsim), ptr(dzr),
+         ptr(dzc), ptr(ws), B, M, N, stream_ptr())
+    return dsim, dzr.sum() + dzc.sum()
 
 
 def log_optimal_transport(sim, alpha, iters):

@@ -205,6 +205,14 @@ int lgb200_log_double_softmax(const float* sim, float bin_score, float* scores, 
                               cudaStream_t stream);
 int lgb200_sinkhorn(const float* sim, float alpha, int iters, float* out, void* ws, int B, int M, int N,
                     cudaStream_t stream);
+/* The same iterations with their potentials kept (uh [iters,B,M+1], vh [iters,B,N+1], both or neither; out may be
+ * NULL), and the reverse sweep that turns grad = dL/dout [B,M+1,N+1] into dsim [B,M,N] plus the gradient entering the
+ * dustbin row dzr [B,N+1] and column dzc [B,M] (d alpha = sum of both): the autograd of superglue.py:186-214
+ * without its tape.  One persistent cooperative launch each; iters > 0 for the backward.                     */
+int lgb200_sinkhorn_fwd(const float* sim, float alpha, int iters, float* out, float* uh, float* vh, void* ws, int B,
+                        int M, int N, cudaStream_t stream);
+int lgb200_sinkhorn_bwd(const float* sim, float alpha, int iters, const float* grad, const float* uh, const float* vh,
+                        float* dsim, float* dzr, float* dzc, void* ws, int B, int M, int N, cudaStream_t stream);
 
 /* column sums of a tall [rows, cols] matrix = bias gradient of an nn.Linear (autograd of lightglue.py:156 etc.).
  * ws: lgb200_colsum_slabs(rows, cols) * cols floats of scratch; counters: (cols+63)/64 uint32, zero before the

@@ -16,7 +16,7 @@ data = synthetic.to_device(synthetic.make_pairs(B, 2048, seed=1, with_gt=False),
 for _ in range(2):
     trainer.step(data)
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True, experimental_config=torch._C._profiler._ExperimentalConfig(verbose=True)) as prof:
     trainer.step(data)
     torch.cuda.synchronize()
 want = ("aten::copy_", "aten::add", "aten::add_", "aten::clone", "aten::contiguous", "aten::to", "aten::_to_copy", "aten::cat",
@@ -24,7 +24,8 @@ want = ("aten::copy_", "aten::add", "aten::add_", "aten::clone", "aten::contiguo
 rows = []
 for ev in prof.key_averages(group_by_stack_n=6):
     if ev.key in want and ev.device_time_total > 100:
-        rows.append((ev.device_time_total, ev.count, ev.key, [s for s in ev.stack if "repo" in s or "glue" in s][:3]))
+        st = [s for s in ev.stack if ".py" in s and "torch/" not in s] or list(ev.stack)
+        rows.append((ev.device_time_total, ev.count, ev.key, st[:4]))
 rows.sort(reverse=True)
 for t, n, k, st in rows[:25]:
-    print(f"{t:8.0f} us  x{n:3d}  {k:18s} {' <- '.join(s.split('/')[-1] for s in st)}")
+    print(f"{t:8.0f} us  x{n:3d}  {k:18s} {' <- '.join(s.split('/')[-1][:60] for s in st)}")

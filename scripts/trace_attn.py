@@ -15,7 +15,9 @@ buf = (ctypes.c_longlong * 1024)()
 rc = lib.lgb200_debug_read_trace(buf, 1024)
 t = torch.tensor(list(buf)).view(4, 64, 4)
 t0 = int(t[t > 0].min())
-names = ["producer: empty-wait done",
+fwd = len(sys.argv) > 1 and sys.argv[1] == "fwd"
+names = ["producer", "mma: P-wait done, PV issued, S(j+2) issued", "softmax w0: S-wait done, ld done, exps done, arrive done",
+         "softmax w3: same"] if fwd else ["producer: empty-wait done",
          "mma: pds-wait done, dV/dK issued, (dQ issued), sp(i+2) issued",
          "softmax w0: sp-wait done, math done, arrive done, drain done",
          "softmax w15: sp-wait done, math done, arrive done, drain done"]

@@ -337,6 +337,42 @@ def test_other_heads_backward_matches_reference_autograd():
             assert abs(beta.grad.item() - ref) < 1e-3 * max(1.0, abs(ref)), (tag, name, beta.grad.item(), ref)
 
 
+@pytest.mark.parametrize("B,M,N,iters", [(1, 2048, 2048, 50), (2, 2048, 2048, 20), (3, 1000, 777, 50),
+                                          (160, 40, 56, 10), (1, 3, 5, 1), (2, 130, 97, 0)])
+def test_sinkhorn_kernels_at_size(B, M, N, iters):
+    """Persistent Sinkhorn forward + reverse-sweep backward (csrc/heads.cu) against fp64 autograd through the
+    restated iterations (superglue.py:186-214) at the benchmark size (strip cache path), without the cache (B=2),
+    ragged shapes, more pairs than SMs, tiny and zero-iteration cases."""
+    from gluefactory_b200 import heads_grad
+
+    sim = (_rand(B, M, N, seed=31) * 3.0).requires_grad_()
+    alpha = torch.tensor(0.9, device=DEV, requires_grad=True)
+    w = _rand(B, M + 1, N + 1, seed=32)
+    out = ops.log_optimal_transport(sim, alpha, iters)
+    (out * w).sum().backward()
+    sd = sim.detach().double().requires_grad_()
+    ad = alpha.detach().double().requires_grad_()
+    Z = torch.cat([torch.cat([sd, ad.expand(B, M, 1)], 2), ad.expand(B, 1, N + 1)], 1)
+    norm = -np.log(M + N)
+    log_mu = torch.full((B, M + 1), norm, device=DEV, dtype=torch.float64)
+    log_mu[:, M] += np.log(N)
+    log_nu = torch.full((B, N + 1), norm, device=DEV, dtype=torch.float64)
+    log_nu[:, N] += np.log(M)
+    u, v = torch.zeros_like(log_mu), torch.zeros_like(log_nu)
+    for _ in range(iters):
+        u = log_mu - torch.logsumexp(Z + v[:, None, :], 2)
+        v = log_nu - torch.logsumexp(Z + u[:, :, None], 1)
+    ref = Z + u[:, :, None] + v[:, None, :] - norm
+    (ref * w.double()).sum().backward()
+    assert (out.detach().double() - ref.detach()).abs().max().item() < 2e-4
+    assert rel_err(sim.grad, sd.grad) < 1e-4, rel_err(sim.grad, sd.grad)
+    assert abs(alpha.grad.item() - ad.grad.item()) < 1e-4 * max(1.0, abs(ad.grad.item()))
+    # the tensor-math statement of the reverse sweep (pinned on the CPU to the reference's autograd) agrees too
+    if iters and M * N <= 1000 * 777:
+        ds2, da2 = heads_grad.log_optimal_transport_backward(sim.detach(), alpha.detach(), iters, w)
+        assert rel_err(sim.grad, ds2) < 1e-4 and abs(alpha.grad.item() - da2.item()) < 1e-3 * max(1.0, abs(da2.item()))
+
+
 def test_gt_from_homography_matches_reference_labels():
     """Device GT labels are bit-exact against the reference function's own output (golden) ..."""
     g = dict(np.load(os.path.join(GOLDEN, "gt_homography.npz")))
