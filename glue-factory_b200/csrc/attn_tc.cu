@@ -69,22 +69,6 @@ __device__ long long g_trace[4 * 64 * 4];
 #define LGB_TR_LIFE(k) do {} while (0)
 #endif
 
-// exp2 on the FMA / ALU pipes (Cody-Waite split + cubic, relative error 7.5e-5 -- far below the bf16 rounding of P):
-// the MUFU unit does 16 exp2 / clk / SM, which bounds the forward kernel at head_dim 64; every LGB_FWD_POLY-th pair
-// of keys takes one of its two exponentials this way.
-#ifndef LGB_FWD_POLY
-#define LGB_FWD_POLY 0
-#endif
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -125.f);
-  const float t = x + 12582912.f;        // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
-  const float f = x - (t - 12582912.f);  // [-0.5, 0.5]
-  float p = fmaf(f, 0.0551716685f, 0.2426111251f);
-  p = fmaf(p, f, 0.6932609677f);
-  p = fmaf(p, f, 0.9999280572f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
 // token-major [B, N, H, 64] bf16 -> 4-D tensor map {64, H, N, B}, box {64, 1, rows, 1}
 // ---------------------------------------------------------------------------------------------
 // FORWARD kernel (round 2: the round-1 kernel handed P to the second MMA through shared memory and folded O into 64
@@ -261,12 +245,7 @@ __global__ void __launch_bounds__(192, 2)
 #pragma unroll
       for (int e = 0; e < FA_BN; e += 2) {
         const float x0 = fmaf(sv[e], scale_log2, -m_new), x1 = fmaf(sv[e + 1], scale_log2, -m_new);
-        const float p0 = fast_exp2(x0);  // masked keys: exp2(-inf) = 0
-#if LGB_FWD_POLY > 0
-        const float p1 = ((e >> 1) % LGB_FWD_POLY == 0) ? poly_exp2(x1) : fast_exp2(x1);
-#else
-        const float p1 = fast_exp2(x1);
-#endif
+        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);  // masked keys: exp2(-inf) = 0
         lsum += p0 + p1;
         pw[e >> 1] = pack_bf16(p0, p1);
       }

@@ -280,6 +280,10 @@ class LinearFn(torch.autograd.Function):
 def _similarity(md0, md1, bf16):
     if bf16:
         return gemm_bf16(md0.to(torch.bfloat16).contiguous(), md1.to(torch.bfloat16).contiguous())
+    from . import engine
+
+    if engine.FP32_GEMM == "x3":  # split-operand tcgen05 GEMM (precision: bf16x3)
+        return gemm_bf16(engine.split3(md0.float(), 2, "hhl"), engine.split3(md1.float(), 2, "hlh"))
     return torch.bmm(md0, md1.transpose(1, 2))
 
 
