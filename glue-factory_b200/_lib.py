@@ -63,6 +63,9 @@ SIGNATURES = {
     "lgb200_cast_bf16": (_i, [_vp, _vp, _i64, _vp]),
     "lgb200_colsum_slabs": (_i, [_i64, _i]),
     "lgb200_colsum": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "lgb200_posenc_wgrad_blocks": (_i, []),
+    "lgb200_posenc_wgrad": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "lgb200_mask_counts": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_residual_add_cast": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "lgb200_residual_add_cast_pitched": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _vp]),
 }

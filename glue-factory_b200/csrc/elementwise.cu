@@ -7,6 +7,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "host_util.h"
 #include "lgb200.h"
 
 namespace lgb {
@@ -474,6 +475,80 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
   }
 }
 
+// dW[c][d] = sum_t g[t][c] * kp[t][d]: the weight gradient of the Fourier position encoder's projection
+// (lightglue.py:37-44; theta = kp Wr^T with kp [T, 2 or 4]), a tall-skinny contraction cuBLAS runs as split-K sgemm +
+// memset (0.2 ms per step).  C == 32: a warp reads one 128-byte row of g, 8 rows in flight per CTA; per-CTA partials.
+__global__ void __launch_bounds__(256) posenc_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ kp,
+                                                          float* __restrict__ part, int64_t T, int KD) {
+  __shared__ float red[8][32][4];
+  const int c = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t t = (int64_t)blockIdx.x * 8 + slot; t < T; t += (int64_t)gridDim.x * 8) {
+    const float gv = __ldg(g + t * 32 + c);
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      if (d < KD) acc[d] = fmaf(gv, __ldg(kp + t * KD + d), acc[d]);
+  }
+#pragma unroll
+  for (int d = 0; d < 4; ++d) red[slot][c][d] = acc[d];
+  __syncthreads();
+  if (slot == 0) {
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      float v = 0.f;
+#pragma unroll
+      for (int s8 = 0; s8 < 8; ++s8) v += red[s8][c][d];
+      if (d < KD) part[((int64_t)blockIdx.x * 32 + c) * KD + d] = v;
+    }
+  }
+}
+
+// Row and column counts of a 0/1 byte mask [B,M,N] in one pass (the ground-truth assignment's `gt.sum(2)` / `gt.sum(1)`,
+// lightglue.py:595-600; torch first widens the 4.2 MB/pair mask to fp32 for each of the two sums).  A warp owns whole
+// rows: per row a dp4a byte sum + shuffle reduce; the same 16-byte loads accumulate this lane's 16 columns byte-wise
+// over the warp's 8 rows, flushed as exact integer-valued float atomics (only the non-zero ones: the mask is sparse).
+constexpr int kMcRows = 64, kMcChunks = 8;
+__global__ void __launch_bounds__(256) mask_counts_kernel(const uint8_t* __restrict__ mask, float* __restrict__ rowcnt,
+                                                         float* __restrict__ colcnt, int M, int N) {
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * kMcRows, r1 = min(M, r0 + kMcRows);
+  const uint8_t* mb = mask + (int64_t)b * M * N;
+  uint32_t acc[kMcChunks][4];
+#pragma unroll
+  for (int c = 0; c < kMcChunks; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0u;
+  for (int r = r0 + warp; r < r1; r += 8) {
+    unsigned rs = 0u;
+#pragma unroll
+    for (int c = 0; c < kMcChunks; ++c) {
+      const int col = c * 512 + lane * 16;
+      if (col < N) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(mb + (int64_t)r * N + col));
+        rs = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, rs))));
+        acc[c][0] = __vadd4(acc[c][0], v.x);
+        acc[c][1] = __vadd4(acc[c][1], v.y);
+        acc[c][2] = __vadd4(acc[c][2], v.z);
+        acc[c][3] = __vadd4(acc[c][3], v.w);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    if (lane == 0) rowcnt[(int64_t)b * M + r] = (float)rs;
+  }
+#pragma unroll
+  for (int c = 0; c < kMcChunks; ++c) {
+    const int col = c * 512 + lane * 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (acc[c][k] == 0u) continue;
+#pragma unroll
+      for (int by = 0; by < 4; ++by) {
+        const uint32_t n = (acc[c][k] >> (8 * by)) & 0xffu;
+        if (n) atomicAdd(colcnt + (int64_t)b * N + col + 4 * k + by, (float)n);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // column sums of a tall [rows, cols] matrix (bias gradients): block = 32 row-lanes x 8 column-vectors
 // (8 elements = one 128-bit load for bf16), row slabs across blockIdx.y, deterministic two-stage sum.
@@ -716,6 +791,24 @@ int lgb200_colsum_slabs(int64_t rows, int cols) {
   int64_t maxs = (rows + 255) / 256;                // at least 256 rows per slab
   int64_t n = want < maxs ? want : maxs;
   return (int)(n < 1 ? 1 : n);
+}
+
+int lgb200_posenc_wgrad_blocks(void) { return 2 * device_sm_count(); }
+int lgb200_posenc_wgrad(const float* g, const float* kp, float* part, int64_t T, int C, int KD, cudaStream_t stream) {
+  LGB_REQUIRE(g && kp && part && T > 0, kErrInvalid, "posenc_wgrad: bad arguments");
+  LGB_REQUIRE(C == 32 && KD >= 1 && KD <= 4, kErrInvalid, "posenc_wgrad: C must be 32 and 1 <= KD <= 4 (got %d, %d)", C, KD);
+  posenc_wgrad_kernel<<<lgb200_posenc_wgrad_blocks(), 256, 0, stream>>>(g, kp, part, T, KD);
+  return check_launch("posenc_wgrad");
+}
+
+int lgb200_mask_counts(const uint8_t* mask, float* rowcnt, float* colcnt, int B, int M, int N, cudaStream_t stream) {
+  LGB_REQUIRE(mask && rowcnt && colcnt && B > 0 && M > 0 && N > 0, kErrInvalid, "mask_counts: bad arguments");
+  LGB_REQUIRE(N % 16 == 0 && N <= 512 * kMcChunks && (reinterpret_cast<uintptr_t>(mask) & 15) == 0, kErrInvalid,
+              "mask_counts: N must be a multiple of 16 and at most %d, mask 16-byte aligned", 512 * kMcChunks);
+  cudaError_t e = cudaMemsetAsync(colcnt, 0, sizeof(float) * (size_t)B * N, stream);
+  LGB_REQUIRE(e == cudaSuccess, kErrCuda, "mask_counts: memset: %s", cudaGetErrorString(e));
+  mask_counts_kernel<<<dim3((M + kMcRows - 1) / kMcRows, B), 256, 0, stream>>>(mask, rowcnt, colcnt, M, N);
+  return check_launch("mask_counts");
 }
 
 int lgb200_colsum(const void* a, float* out, float* ws, unsigned* counters, int64_t rows, int cols, int dtype,

@@ -321,7 +321,7 @@ class LightGlue(nn.Module):
             kpts0, kpts1 = ext(kpts0, data["scales0"], data["oris0"]), ext(kpts1, data["scales1"], data["oris1"])
         kd = kpts0.shape[-1]
         kp = torch.cat([kpts0.reshape(B * M, kd), kpts1.reshape(B * N, kd)], 0)
-        theta = F.linear(kp, self.posenc.Wr.weight.float()).float().contiguous()
+        theta = ops.PosencTheta.apply(kp.float().contiguous(), self.posenc.Wr.weight.float()).contiguous()
         sizes = (B, M, N)
         all0, all1, layers_x = [], [], []
         L = conf.n_layers
@@ -527,10 +527,9 @@ class LightGlue(nn.Module):
             (B, M, N), L = pred["_b200_sizes"], len(pred["_b200_layers"])
         gt = data["gt_assignment"]
         gt_u8 = gt.contiguous().view(torch.uint8) if gt.dtype == torch.bool else gt.to(torch.uint8).contiguous()
-        # counts with an fp32 accumulator inside the reduction (exact below 2^24); `gt.sum(2)` would first upcast the
-        # 4.2 MB/pair boolean mask to int64 (1.1 ms per step at 32 pairs, profiles/r01_roofline_table.md)
-        rowcnt = gt_u8.sum(2, dtype=torch.float32)
-        colcnt = gt_u8.sum(1, dtype=torch.float32)
+        # both counts in one pass over the 4.2 MB/pair mask (`gt.sum(2)` / `gt.sum(1)` each widen it first: int64 by
+        # default -- 1.1 ms per step at 32 pairs, profiles/r01_roofline_table.md -- fp32 with dtype=, still 0.9 ms)
+        rowcnt, colcnt = ops.mask_counts(gt_u8)
         neg0 = (data["gt_matches0"] == -1).float()
         neg1 = (data["gt_matches1"] == -1).float()
         num_pos = rowcnt.sum(1).clamp(min=1.0)

@@ -166,6 +166,41 @@ class LnGelu(torch.autograd.Function):
 _colsum_counters = {}
 
 
+class PosencTheta(torch.autograd.Function):
+    """theta = kp Wr^T (lightglue.py:37-44; kp [T, 2|4] fp32, Wr [C, kd]); the weight gradient -- a [C,T] x [T,kd]
+    contraction over all tokens -- runs as one streaming kernel + a 296-row sum instead of a split-K sgemm."""
+
+    @staticmethod
+    def forward(ctx, kp, weight):
+        ctx.save_for_backward(kp)
+        return kp @ weight.t()
+
+    @staticmethod
+    def backward(ctx, g):
+        (kp,) = ctx.saved_tensors
+        T, C = g.shape
+        kd = kp.shape[1]
+        if C != 32 or kd > 4 or not g.is_cuda:
+            return None, g.t() @ kp
+        g = g.contiguous()
+        nb = _lib.load().lgb200_posenc_wgrad_blocks()
+        part = torch.empty(nb, C, kd, device=g.device, dtype=torch.float32)
+        call("lgb200_posenc_wgrad", ptr(g), ptr(kp), ptr(part), T, C, kd, stream_ptr())
+        return None, part.sum(0)
+
+
+def mask_counts(mask_u8):
+    """0/1 byte mask [B,M,N] -> (rowcnt [B,M], colcnt [B,N]) fp32, one pass (lgb200_mask_counts); shapes the kernel does
+    not take (N not a multiple of 16, N > 4096) use the two torch reductions."""
+    B, M, N = mask_u8.shape
+    if N % 16 or N > 4096 or not mask_u8.is_contiguous() or mask_u8.data_ptr() % 16 or not mask_u8.is_cuda:
+        return mask_u8.sum(2, dtype=torch.float32), mask_u8.sum(1, dtype=torch.float32)
+    rowcnt = torch.empty(B, M, device=mask_u8.device, dtype=torch.float32)
+    colcnt = torch.empty(B, N, device=mask_u8.device, dtype=torch.float32)
+    call("lgb200_mask_counts", ptr(mask_u8), ptr(rowcnt), ptr(colcnt), B, M, N, stream_ptr())
+    return rowcnt, colcnt
+
+
 def colsum(a):
     """[rows, cols] (fp32 / bf16) -> fp32 [cols] column sums (bias gradients); one launch."""
     _chk(a)

@@ -218,6 +218,14 @@ int lgb200_sinkhorn_bwd(const float* sim, float alpha, int iters, const float* g
  * ws: lgb200_colsum_slabs(rows, cols) * cols floats of scratch; counters: (cols+63)/64 uint32, zero before the
  * FIRST call (the kernel leaves them zero again); cols % 8 == 0.  One launch, deterministic summation order. */
 int lgb200_colsum_slabs(int64_t rows, int cols);
+/* rowcnt [B,M] = sum_j mask, colcnt [B,N] = sum_i mask of a 0/1 byte mask [B,M,N] (the `gt.sum(2)` / `gt.sum(1)` of
+ * lightglue.py:595-600) in one pass; N % 16 == 0, N <= 4096, mask 16-byte aligned; counts are exact.            */
+/* Weight gradient of the position encoder's projection (autograd of lightglue.py:37-44, theta = kp Wr^T):
+ * part [lgb200_posenc_wgrad_blocks()][C][KD] per-CTA partials of sum_t g[t][c] kp[t][d]; g [T,C] fp32 with C == 32,
+ * kp [T,KD] fp32, KD <= 4.  The caller sums the partials over their first dimension.                          */
+int lgb200_posenc_wgrad_blocks(void);
+int lgb200_posenc_wgrad(const float* g, const float* kp, float* part, int64_t T, int C, int KD, cudaStream_t stream);
+int lgb200_mask_counts(const uint8_t* mask, float* rowcnt, float* colcnt, int B, int M, int N, cudaStream_t stream);
 int lgb200_colsum(const void* a, float* out, float* ws, unsigned* counters, int64_t rows, int cols, int dtype,
                   cudaStream_t stream);
 

@@ -373,6 +373,29 @@ def test_sinkhorn_kernels_at_size(B, M, N, iters):
         assert rel_err(sim.grad, ds2) < 1e-4 and abs(alpha.grad.item() - da2.item()) < 1e-3 * max(1.0, abs(da2.item()))
 
 
+@pytest.mark.parametrize("B,M,N,density", [(2, 2048, 2048, 0.0005), (3, 1000, 784, 0.3), (1, 70, 4096, 1.0),
+                                             (2, 150, 203, 0.05)])
+def test_mask_counts(B, M, N, density):
+    """One-pass row / column counts of the ground-truth mask (lightglue.py:595-600 `gt.sum(2)`, `gt.sum(1)`): exact."""
+    mask = (torch.rand(B, M, N, generator=torch.Generator().manual_seed(3)) < density).to(DEV)
+    r, c = ops.mask_counts(mask.view(torch.uint8))
+    assert torch.equal(r, mask.sum(2).float()) and torch.equal(c, mask.sum(1).float())
+
+
+@pytest.mark.parametrize("kd", [2, 4])
+def test_posenc_theta_weight_gradient(kd):
+    T = 2 * 3 * 1111
+    kp = _rand(T, kd, seed=8)
+    w = (_rand(32, kd, seed=9)).requires_grad_()
+    gth = _rand(T, 32, seed=10)
+    th = ops.PosencTheta.apply(kp, w)
+    (th * gth).sum().backward()
+    w64 = w.detach().double().requires_grad_()
+    ((kp.double() @ w64.t()) * gth.double()).sum().backward()
+    assert rel_err(th, kp.double() @ w64.t()) < 1e-6
+    assert rel_err(w.grad, w64.grad) < 1e-5
+
+
 def test_gt_from_homography_matches_reference_labels():
     """Device GT labels are bit-exact against the reference function's own output (golden) ..."""
     g = dict(np.load(os.path.join(GOLDEN, "gt_homography.npz")))
