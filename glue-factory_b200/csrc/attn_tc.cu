@@ -972,9 +972,6 @@ __global__ void __launch_bounds__(FF_THREADS, 1)
     const uint64_t dstM = make_smem_desc(smem_u32(sStage), 8192, 1024);  // MN-major view
     const uint64_t dDS = make_smem_desc(smem_u32(sDS), FB_R * 128, 1024);  // two 64-query chunks 16 KiB apart
     const uint64_t dKm = make_smem_desc(smem_u32(sK), 8192, 1024);
-#ifdef LGB_BWD_DS_KMAJOR
-    const uint64_t dDSk = make_smem_desc(smem_u32(sDS), 16, 1024);
-#endif
     const bool leader = elect_one();
     auto issue_sp = [&](int i) {
       const int s = i % FF_STAGES;
@@ -1026,15 +1023,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1)
         if (leader) {
           const uint64_t da = dDS + (uint64_t)(((pr & 1) * FF_DSBYTES) >> 4);
 #pragma unroll
-#ifdef LGB_BWD_DS_KMAJOR
-          // dS_pair stored [query][key] (K-major A): two 64-key blocks of 128 rows x 128 B, 32 B per 16-key step
-          for (int kk = 0; kk < FB_R / 16; ++kk)
-            umma_bf16(tmem_base + FF_DQ, dDSk + (uint64_t)(((pr & 1) * FF_DSBYTES) >> 4) + (uint64_t)((kk >> 2) * 1024 + (kk & 3) * 2),
-                      dKm + (uint64_t)(kk * 128), idesc_acc, kk != 0 ? 1u : 0u);
-#else
           for (int kk = 0; kk < FB_R / 16; ++kk)  // 16 keys per step: 16 rows of 128 B in both operands
             umma_bf16(tmem_base + FF_DQ, da + (uint64_t)(kk * 128), dKm + (uint64_t)(kk * 128), idesc_dq, kk != 0 ? 1u : 0u);
-#endif
           umma_commit(dq_full);
           umma_commit(&ds_free[pr & 1]);
         }
@@ -1133,25 +1123,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1)
       tmem_st8(tb + 64 + c * F3_CW, dw);   // dS^T over the dP^T columns
       // bf16 dS also goes to shared memory, [key][query] (row = this thread's key), for the dQ MMA of the pair
       if (buf == 0 && pr >= 2) mbar_wait(&ds_free[pr & 1], ((pr >> 1) & 1) ^ 1);  // pair pr-2 has been consumed
-#ifdef LGB_BWD_DS_KMAJOR
-      {  // [query][key]: this thread's key is a 2-byte column of 16 query rows; a warp covers 64 contiguous bytes per row
-        uint8_t* blk = sDS + (pr & 1) * FF_DSBYTES + (r >> 6) * (FB_R * 128) + ((r & 7) << 1);
-        const int kc = (r & 63) >> 3;
-#pragma unroll
-        for (int e = 0; e < F3_CW; ++e) {
-          const int qq = buf * FB_C + c * F3_CW + e;
-          const uint32_t w = dw[e >> 1];
-          *reinterpret_cast<unsigned short*>(blk + qq * 128 + ((kc ^ (qq & 7)) << 4)) =
-              static_cast<unsigned short>((e & 1) ? (w >> 16) : (w & 0xffffu));
-        }
-      }
-#else
       {
         uint8_t* rowp = sDS + (pr & 1) * FF_DSBYTES + buf * (FB_R * 128) + r * 128;
         *reinterpret_cast<uint4*>(rowp + (((2 * c) ^ (r & 7)) << 4)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
         *reinterpret_cast<uint4*>(rowp + (((2 * c + 1) ^ (r & 7)) << 4)) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
       }
-#endif
       fence_proxy_async_smem();
       tmem_st_wait();
       tc_fence_before();
