@@ -473,7 +473,7 @@ def kernel_roofline(trainer, pool_dev, B, dev):
     secs = sum(v["avg_launch_ms"] * v["launches_timed"] for _, v in bw) * 1e-3
     n = sum(v["launches_timed"] for _, v in bw)
     achieved = flops / secs / 1e12
-    return {"kernel": "lgb200_attn_bwd (attn_bwd_prep + attn_bwd_dq + attn_bwd_dkv; self 8C and cross 6C launches)",
+    return {"kernel": "lgb200_attn_bwd (attn_bwd_prep_fused + attn_bwd_fused + dq_convert; self 8C and cross 6C launches)",
             "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / peaks["tflops_sustained"], "traffic": traffic.get("lgb200_attn_bwd"),
             "traffic_source": "profiles/r02_roofline_traffic.json (ncu --set full of this command at this batch size)" if traffic else None,

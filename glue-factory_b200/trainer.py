@@ -15,6 +15,8 @@ changes SURVEY.md section 2.2 (C1) calls for:
 The matcher is per-pair, so image pairs shard across ranks with no other
 collective.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -22,6 +24,14 @@ from . import ops
 from .synthetic import to_device
 
 _ALIGN = 64  # elements; keeps every parameter view 256-byte aligned
+# Gradient-exchange schedule (FlatParams.exchange): "end" (default) = ONE sum-all-reduce of the flat gradient buffer
+# behind backward, issued in its synchronous form so that it runs on the step's own stream (a captured step stays a
+# linear chain of graph nodes); "chunked" = each layer's slice as soon as its backward wrote it, the rest at the end.
+# Measured on 2 B200s (scripts/diag_allreduce.py, diag_lockstep.py): the 47.4 MB all-reduce takes
+# 0.12 ms, the lock-step wait for the slower GPU ~0.4 ms, and the two schedules are within noise of each other -- there
+# is nothing left to hide, so the default is the simple one.  "none" is a DIAGNOSTIC (ranks train independently).
+_EXCHANGE = os.environ.get("LGB200_EXCHANGE", "end")
+assert _EXCHANGE in ("chunked", "end", "none"), _EXCHANGE
 
 
 class FlatParams:
@@ -57,6 +67,7 @@ class FlatParams:
         self.direct_groups = []
         self._direct_ids = set()
         self.world, self.group, self._pending = 1, None, []
+        self.exchange = _EXCHANGE
         module._b200_flat = self
 
     def enable_direct(self, groups):
@@ -79,7 +90,7 @@ class FlatParams:
     def chunk_ready(self, gi):
         """Called from backward when group gi's gradients are final: start its all-reduce now (it overlaps the backward
         of the layers below); `finish_exchange` waits for all of them."""
-        if self.world > 1:
+        if self.world > 1 and self.exchange == "chunked":
             lo, hi, _ = self.direct_groups[gi]
             self._pending.append((lo, hi, dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
                                                           async_op=True)))
@@ -87,13 +98,14 @@ class FlatParams:
     def finish_exchange(self):
         """All-reduce whatever the per-group exchanges did not cover (the head / encoding parameters and the loss slot
         behind the gradients), then wait for every outstanding chunk."""
-        if self.world > 1:
+        if self.world > 1 and self.exchange != "none":
             covered = sorted((lo, hi) for lo, hi, _ in self._pending)  # the slices whose exchange is already in flight
             pos, total = 0, self.grad_ext.numel()
             for lo, hi in covered + [(total, total)]:
                 if lo > pos:
-                    self._pending.append((pos, lo, dist.all_reduce(self.grad_ext[pos:lo], op=dist.ReduceOp.SUM,
-                                                                   group=self.group, async_op=True)))
+                    # synchronous form: the collective is enqueued on the CURRENT stream (no side stream), so a
+                    # captured step stays one linear chain of graph nodes when nothing was exchanged early
+                    dist.all_reduce(self.grad_ext[pos:lo], op=dist.ReduceOp.SUM, group=self.group)
                 pos = max(pos, hi)
             for _, _, w in self._pending:
                 w.wait()

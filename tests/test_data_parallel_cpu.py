@@ -71,6 +71,7 @@ def _chunk_worker(rank, world, port, out):
     net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 16), torch.nn.Linear(16, 16), torch.nn.Linear(16, 3))
     fp = FlatParams(net)
     fp.world = world
+    fp.exchange = "chunked"
     fp.enable_direct([list(net[1].parameters()), list(net[2].parameters())])
     assert net[1].weight.grad.data_ptr() == fp.direct_views(0)[0].data_ptr()
     fp.zero_grad()
@@ -88,6 +89,15 @@ def _chunk_worker(rank, world, port, out):
     fp.grad_ext.copy_(torch.randn(fp.grad_ext.shape, generator=g))
     want = fp.grad_ext.clone()
     dist.all_reduce(want)
+    fp.finish_exchange()
+    assert torch.equal(fp.grad_ext, want)
+    # the default schedule ("end"): chunk_ready is a no-op, everything goes through the one all-reduce at the end
+    fp.exchange = "end"
+    fp.grad_ext.copy_(torch.randn(fp.grad_ext.shape, generator=g))
+    want = fp.grad_ext.clone()
+    dist.all_reduce(want)
+    fp.chunk_ready(1)
+    assert fp._pending == []
     fp.finish_exchange()
     assert torch.equal(fp.grad_ext, want)
     out.put((rank, float(want.abs().sum())))
