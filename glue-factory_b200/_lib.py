@@ -50,6 +50,7 @@ SIGNATURES = {
     "lgb200_head_terms_bwd": (_i, [_vp] * 13 + [_f] + [_vp] * 3 + [_i, _i, _i, _vp]),
     "lgb200_heads_ws_bytes": (_sz, [_i, _i, _i]),
     "lgb200_log_double_softmax": (_i, [_vp, _f, _vp, _vp, _i, _i, _i, _vp]),
+    "lgb200_log_double_softmax_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_sinkhorn": (_i, [_vp, _f, _i, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_sinkhorn_fwd": (_i, [_vp, _f, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_sinkhorn_bwd": (_i, [_vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -23,7 +23,9 @@ __device__ __forceinline__ float logaddexp_f(float a, float b) {
 // scores from precomputed lse_row / lse_col of the UNBORDERED sim
 __global__ void __launch_bounds__(256) lds_scores_kernel(const float* __restrict__ sim, const float* __restrict__ lse_row,
                                                         const float* __restrict__ lse_col, float beta,
+                                                        const float* __restrict__ beta_dev,
                                                         float* __restrict__ scores, int M, int N) {
+  if (beta_dev) beta = __ldg(beta_dev);  // the learnt bin score read from device memory (no host read-back)
   const int b = blockIdx.y;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -426,8 +428,19 @@ size_t lgb200_heads_ws_bytes(int B, int M, int N) {
   return lds > sk ? lds : sk;
 }
 
+static int log_double_softmax_impl(const float* sim, float bin_score, const float* bin_dev, float* scores, void* ws,
+                                   int B, int M, int N, cudaStream_t stream);
 int lgb200_log_double_softmax(const float* sim, float bin_score, float* scores, void* ws, int B, int M, int N,
                               cudaStream_t stream) {
+  return log_double_softmax_impl(sim, bin_score, nullptr, scores, ws, B, M, N, stream);
+}
+int lgb200_log_double_softmax_dev(const float* sim, const float* bin_score_dev, float* scores, void* ws, int B, int M,
+                                  int N, cudaStream_t stream) {
+  LGB_REQUIRE(bin_score_dev, kErrInvalid, "log_double_softmax: null bin score pointer");
+  return log_double_softmax_impl(sim, 0.f, bin_score_dev, scores, ws, B, M, N, stream);
+}
+static int log_double_softmax_impl(const float* sim, float bin_score, const float* bin_dev, float* scores, void* ws,
+                                   int B, int M, int N, cudaStream_t stream) {
   LGB_REQUIRE(sim && scores && ws, kErrInvalid, "log_double_softmax: null pointer");
   LGB_REQUIRE(B > 0 && M > 0 && N > 0, kErrInvalid, "log_double_softmax: empty input");
   // ws layout: [lse_row B*M][lse_col B*N][assign_lse scratch]
@@ -436,7 +449,7 @@ int lgb200_log_double_softmax(const float* sim, float bin_score, float* scores, 
   void* sub = lse_col + (size_t)B * N;
   int rc = lgb200_assign_lse(sim, lse_row, lse_col, sub, B, M, N, stream);
   if (rc) return rc;
-  lds_scores_kernel<<<dim3((M + 1 + 7) / 8, B), 256, 0, stream>>>(sim, lse_row, lse_col, bin_score, scores, M, N);
+  lds_scores_kernel<<<dim3((M + 1 + 7) / 8, B), 256, 0, stream>>>(sim, lse_row, lse_col, bin_score, bin_dev, scores, M, N);
   return check_launch("log_double_softmax");
 }
 

@@ -85,7 +85,7 @@ class LogDoubleSoftmaxFn(torch.autograd.Function):
     def forward(ctx, sim, bin_score):
         from . import ops
 
-        scores = ops._log_double_softmax_fwd(sim, float(bin_score))
+        scores = ops._log_double_softmax_fwd(sim, bin_score)
         ctx.save_for_backward(sim, bin_score, scores)
         return scores
 

@@ -562,7 +562,11 @@ def _log_double_softmax_fwd(sim, bin_score):
     B, M, N = sim.shape
     out = torch.empty(B, M + 1, N + 1, device=sim.device, dtype=torch.float32)
     ws = torch.empty(_lib.load().lgb200_heads_ws_bytes(B, M, N), device=sim.device, dtype=torch.uint8)
-    call("lgb200_log_double_softmax", ptr(sim), float(bin_score), ptr(out), ptr(ws), B, M, N, stream_ptr())
+    if torch.is_tensor(bin_score) and bin_score.is_cuda:  # learnt bin: read on the device (no .item(), graph-capturable)
+        bs = bin_score.detach().reshape(-1)[:1].float().contiguous()
+        call("lgb200_log_double_softmax_dev", ptr(sim), ptr(bs), ptr(out), ptr(ws), B, M, N, stream_ptr())
+    else:
+        call("lgb200_log_double_softmax", ptr(sim), float(bin_score), ptr(out), ptr(ws), B, M, N, stream_ptr())
     return out
 
 
@@ -572,7 +576,7 @@ def log_double_softmax(sim, bin_score):
         from .heads_grad import LogDoubleSoftmaxFn
 
         return LogDoubleSoftmaxFn.apply(sim, bin_score)
-    return _log_double_softmax_fwd(sim, float(bin_score))
+    return _log_double_softmax_fwd(sim, bin_score)
 
 
 def _log_optimal_transport_fwd(sim, alpha, iters, keep_potentials=False):

@@ -203,6 +203,9 @@ int lgb200_head_terms_bwd(const float* zt, const float* rowcnt, const float* col
 size_t lgb200_heads_ws_bytes(int B, int M, int N);
 int lgb200_log_double_softmax(const float* sim, float bin_score, float* scores, void* ws, int B, int M, int N,
                               cudaStream_t stream);
+/* the same with the (learnt) bin score read from device memory: no host read-back, capturable into a CUDA graph */
+int lgb200_log_double_softmax_dev(const float* sim, const float* bin_score_dev, float* scores, void* ws, int B, int M,
+                                  int N, cudaStream_t stream);
 int lgb200_sinkhorn(const float* sim, float alpha, int iters, float* out, void* ws, int B, int M, int N,
                     cudaStream_t stream);
 /* The same iterations with their potentials kept (uh [iters,B,M+1], vh [iters,B,N+1], both or neither; out may be

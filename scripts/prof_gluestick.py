@@ -55,6 +55,23 @@ for prec in ("bf16", "fp32"):
     ms = timed(make_step(m.to(dev).train()))
     rows.append((f"plugin precision={prec}", ms))
     del m
+try:  # the same step captured into one CUDA graph by the library's trainer (flat parameters, flat Adam)
+    from gluefactory_b200.trainer import MatcherTrainer
+
+    m = GlueStick(dict(conf, precision="bf16"))
+    m.load_state_dict(w, strict=True)
+    tr = MatcherTrainer(m.to(dev).train(), lr=1e-5)
+    ms_eager = timed(lambda: tr.step(data))
+    rows.append(("plugin bf16, MatcherTrainer eager", ms_eager))
+    tr.capture(data, dev)
+    rows.append(("plugin bf16, CUDA-graph replay", timed(lambda: tr.step_graphed(data))))
+    del m, tr
+except Exception as e:  # noqa: BLE001
+    import traceback
+
+    tb = [ln for ln in traceback.format_exc().splitlines() if "glue-factory_b200" in ln or "gluefactory_b200" in ln]
+    print("graph capture failed:", type(e).__name__, str(e)[:200].replace("\n", " "), "|", " <- ".join(t.strip() for t in tb[-6:]))
+    rows.append(("graph capture failed", float("nan")))
 try:
     from oracle.stage_reference import import_reference
 
@@ -71,3 +88,21 @@ except Exception as e:  # noqa: BLE001
 print(f"GlueStick training step, B={B} pairs, N={N} points, L={L} lines per image")
 for name, ms in rows:
     print(f"  {name:32s} {ms:9.1f} ms/step  {B / ms * 1e3:8.1f} pairs/s")
+
+if os.environ.get("PROF"):
+    from torch.profiler import ProfilerActivity, profile
+
+    m = GlueStick(dict(conf, precision="bf16"))
+    m.load_state_dict(w, strict=True)
+    step = make_step(m.to(dev).train())
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    evs = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+    tot = sum(e.device_time_total for e in evs)
+    print(f"plugin bf16: total device time {tot / 1e3:.2f} ms over {sum(e.count for e in evs)} launches")
+    for e in evs[:32]:
+        print(f"  {e.device_time_total:9.0f} us {100 * e.device_time_total / tot:5.1f}% x{e.count:4d}  {e.key[:110]}")

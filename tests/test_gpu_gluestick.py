@@ -134,3 +134,20 @@ def test_gluestick_trains_and_evaluates():
         pred = model(data)
         _, metrics = model.loss(pred, data)
     assert {"match_recall", "line_match_recall", "average_precision"} <= set(metrics)
+
+
+def test_gluestick_training_step_replays_as_one_cuda_graph():
+    """The whole GlueStick step (forward, both assignment losses, backward, flat Adam) holds no host read-back -- the
+    learnt bin scores are read on the device -- so trainer.MatcherTrainer can capture it; replay == eager steps."""
+    from gluefactory_b200.trainer import MatcherTrainer
+
+    g, conf, B, N, L, seed = _case()
+    data = synthetic.to_device(synthetic.make_gluestick_batch(B, N, L, seed + 1), DEV)
+    eager = MatcherTrainer(_build(conf, seed, "bf16"), lr=1e-4)
+    graphed = MatcherTrainer(_build(conf, seed, "bf16"), lr=1e-4)
+    graphed.capture(data, torch.device(DEV))
+    for it in range(3):
+        le, _ = eager.step(data)
+        lg, _ = graphed.step_graphed(data)
+        assert torch.isfinite(lg).all()
+        assert abs(le.item() - lg.item()) < (1e-5 if it == 0 else 2e-3) * abs(le.item()), (it, le.item(), lg.item())
