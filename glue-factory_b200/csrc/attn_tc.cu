@@ -1016,6 +1016,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1)
       }
       if (leader) LGB_TR(1, i, 1);
       __syncwarp();
+#ifdef LGB_BWD_SP_FIRST
+      if (i + 2 < ntiles) issue_sp(i + 2);  // ahead of the pair's dQ product: the softmax of tile i+2 starts ~700 clk earlier
+#endif
       if ((i & 1) || i == ntiles - 1) {  // the pair is complete: dQ_pair = dS_pair K
         const int pr = i >> 1;
         mbar_wait(dq_empty, (pr & 1) ^ 1);  // the softmax warps drained the previous pair's dQ
@@ -1031,7 +1034,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1)
         __syncwarp();
       }
       if (leader) LGB_TR(1, i, 2);
+#ifndef LGB_BWD_SP_FIRST
       if (i + 2 < ntiles) issue_sp(i + 2);
+#endif
       if (leader) LGB_TR(1, i, 3);
     }
     if (leader) umma_commit(acc_done);
