@@ -2,16 +2,15 @@
 // for head_dim 64, bf16 operands, fp32 accumulation, never materialising the N x N similarity.
 // (reference: lightglue.py:118-121 self-attention; :207-216 cross-attention.)
 //
-// FORWARD.  One CTA = one (batch, head, 128-query tile).  Q/K/V tiles are brought in by TMA
+// FORWARD.  One CTA = one (batch, head, 128-query tile), two CTAs per SM.  Q/K/V tiles are brought in by TMA
 // (4-D tensor map over the token-major [B,N,H,64] layout, 128-byte swizzle) and consumed straight
 // from shared memory by tcgen05.mma:
-//     S_j (128 x 64 fp32, TMEM, double-buffered) = Q K_j^T      4 MMAs  (M128 N64 K16)
-//     O_j (128 x 64 fp32, TMEM, double-buffered) = P_j V_j      4 MMAs  (M128 N64 K16)
+//     S_j (128 x 64 fp32, TMEM, double-buffered) = Q K_j^T      4 MMAs  (M128 N64 K16, SS)
+//     O  (128 x 64 fp32, TMEM, accumulated)     += P_j V_j      4 MMAs  (M128 N64 K16, TS: P_j read from TMEM)
 // Warps 0-3 are the softmax warpgroup (thread == query row == TMEM lane): one sweep over S_j with
-// tcgen05.ld (row max, exp2 / row sum / bf16 pack), P_j written to shared memory in the
-// K-major 128B-swizzled layout the MMA expects, O_j folded into a register accumulator with the
-// usual online-softmax rescale.  Warp 4 = TMA producer, warp 5 = MMA issuer + TMEM owner.
-// Two CTAs fit per SM (112 KiB smem, 256 TMEM columns each); 4 K/V stages keep the TMA loads ~2 tiles ahead.
+// tcgen05.ld (row max, exp2 / row sum / bf16 pack), P_j written to its own TMEM columns, O rescaled in
+// TMEM only when the lazy reference maximum moves.  Warp 4 = TMA producer, warp 5 = MMA issuer + TMEM owner.
+// BACKWARD: one fused kernel (dK, dV, dQ in a single pass; see attn_bwd_fused_kernel) + the round-1 two-kernel pair.
 #include <math.h>
 
 #include "common.cuh"
