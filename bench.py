@@ -460,7 +460,8 @@ def kernel_roofline(trainer, pool_dev, B, dev):
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        if tj.get("sequences_per_launch") == 2 * B:  # only quote a capture taken at this run's batch size
+        # only quote a capture taken at this run's batch size and keypoint count
+        if tj.get("sequences_per_launch") == 2 * B and tj.get("keypoints", 2048) == N_KPTS:
             traffic = tj.get("dram_bytes_per_launch", {})
     kernels = {}
     for (name, kind), ts in sorted(groups.items()):

@@ -1,7 +1,7 @@
 """`.ncu-rep` of the attention-backward kernels inside one eager training step (scripts/gpu_final_r2.sh) ->
 profiles/r02_roofline_traffic.json: DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per lgb200_attn_bwd call
 = one attn_bwd_prep_fused + one attn_bwd_fused (+ one dq_convert when captured), averaged over the captured launches.
-Usage: python scripts/summarize_traffic.py gpurun_out/r02_attn_bwd.ncu-rep <sequences_per_launch>"""
+Usage: python scripts/summarize_traffic.py gpurun_out/r02_attn_bwd.ncu-rep <sequences_per_launch> [keypoints]"""
 import collections
 import csv
 import io
@@ -10,6 +10,7 @@ import subprocess
 import sys
 
 rep, seqs = sys.argv[1], int(sys.argv[2])
+kpts = int(sys.argv[3]) if len(sys.argv) > 3 else 2048
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics",
                       "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum"],
                      capture_output=True, text=True, check=True).stdout
@@ -38,6 +39,6 @@ for name, (rd, wr, us, n) in agg.items():
 res = {"_comment": "ncu --set full --clock-control none of the attention-backward kernels inside one eager training step "
                    "(scripts/gpu_final_r2.sh; cold caches, serialised launches); per lgb200_attn_bwd call = the sum over the "
                    "kernels below, each averaged over its captured launches",
-       "sequences_per_launch": seqs, "dram_bytes_per_launch": {"lgb200_attn_bwd": per_call}, "kernels": detail}
+       "sequences_per_launch": seqs, "keypoints": kpts, "dram_bytes_per_launch": {"lgb200_attn_bwd": per_call}, "kernels": detail}
 json.dump(res, open("profiles/r02_roofline_traffic.json", "w"), indent=1)
 print(json.dumps(res, indent=1))
