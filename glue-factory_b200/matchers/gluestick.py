@@ -177,39 +177,55 @@ class GlueStick(nn.Module):
     def _bf16(self):
         return self.conf.precision == "bf16"
 
-    def _conv(self, x, conv, w=None, b=None):
-        """Conv1d(kernel 1) on token-major x [T, C_in]; w / b override the module's parameters (permuted views)."""
+    def _conv(self, x, conv, w=None, b=None, keep_bf16=False):
+        """Conv1d(kernel 1) on token-major x [T, C_in]; w / b override the module's parameters (permuted views).
+        bf16 mode: x may already be bf16 (no second cast), and keep_bf16 leaves the GEMM's bf16 output as it is for a
+        consumer that rounds to bf16 anyway (the next GEMM, BatchNorm + ReLU in front of one, the attention kernels)."""
         w = conv.weight[:, :, 0] if w is None else w
         b = conv.bias if b is None else b
         if self._bf16 and w.shape[1] % 64 == 0 and w.shape[0] % 8 == 0:
-            return ops.LinearFn.apply(x.to(torch.bfloat16).contiguous(), w, b).float()
+            y = ops.LinearFn.apply(x.to(torch.bfloat16).contiguous(), w, b)
+            return y if keep_bf16 else y.float()
         return F.linear(x.float(), w, b)
 
     def _mlp(self, x, seq):
-        for m in seq:
+        mods = list(seq)
+        for i, m in enumerate(mods):
             if isinstance(m, nn.Conv1d):
-                x = self._conv(x, m)
+                # an inner layer's output only feeds BatchNorm / ReLU and the next GEMM, which rounds it to bf16 at the
+                # same point either way: keep it bf16 (BatchNorm still accumulates its statistics in fp32)
+                x = self._conv(x, m, keep_bf16=self._bf16 and i < len(mods) - 1)
             elif isinstance(m, nn.BatchNorm1d):
-                x = m(x.float())  # [T, C]: statistics over all tokens of this call, as BatchNorm1d over [B, C, N]
+                x = m(x if x.dtype == torch.bfloat16 else x.float())  # [T, C]: statistics over all tokens of this call
             else:
                 x = torch.relu(x)
         return x
 
-    def _attention(self, x, src, attn, B):
+    def _attn_weights(self, attn):
+        """The projection / merge weights of one MultiHeadedAttention with the head permutation applied (rows of q, k, v,
+        columns of merge); computed once per layer and shared by both images."""
+        perm = self._perm
+        return ([(p.weight[:, :, 0][perm], p.bias[perm]) for p in attn.proj], attn.merge.weight[:, :, 0][:, perm])
+
+    def _attention(self, x, src, attn, B, wts=None):
         """MultiHeadedAttention (gluestick.py:532-551): x [B*N, D] attends to src [B*M, D]."""
         D = x.shape[1]
-        perm = self._perm
-        q, k, v = (self._conv(t, p, p.weight[:, :, 0][perm], p.bias[perm]) for p, t in zip(attn.proj, (x, src, src)))
+        proj_w, merge_w = wts if wts is not None else self._attn_weights(attn)
+        if self._bf16:  # one cast per input, projections stay bf16 into the attention kernels and out of them
+            x, src = x.to(torch.bfloat16), (src.to(torch.bfloat16) if src is not x else None)
+            src = x if src is None else src
+        q, k, v = (self._conv(t, p, w, b, keep_bf16=True) for p, (w, b), t in zip(attn.proj, proj_w, (x, src, src)))
         cdt = torch.bfloat16 if self._bf16 else torch.float32
         shp = lambda t: t.to(cdt).view(B, -1, 4, D // 4)  # noqa: E731  head-major thanks to the permuted rows
         o = ops.Attention.apply(shp(q), shp(k), shp(v), 0, (D // 4) ** -0.5)
-        return self._conv(o.reshape(-1, D).float(), attn.merge, attn.merge.weight[:, :, 0][:, perm], attn.merge.bias)
+        return self._conv(o.reshape(-1, D), attn.merge, merge_w, attn.merge.bias)
 
     def _gnn_layer(self, d0, d1, layer, B):
         s0, s1 = (d1, d0) if layer.type == "cross" else (d0, d1)
+        wts = self._attn_weights(layer.update.attn)
         out = []
         for x, src in ((d0, s0), (d1, s1)):
-            msg = self._attention(x, src, layer.update.attn, B)
+            msg = self._attention(x, src, layer.update.attn, B, wts)
             out.append(x + self._mlp(torch.cat([x, msg], 1), layer.update.mlp))
         return out[0], out[1]
 
