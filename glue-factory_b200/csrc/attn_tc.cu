@@ -1201,7 +1201,7 @@ int64_t attn_bwd_ws_floats(int B, int Nq, int Nk, int H) {
 int attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
                 void* dq, void* dk, void* dv, float* delta, int B, int Nq, int Nk, int H, int kv_shift, float scale,
                 cudaStream_t stream) {
-  static const bool fused = !env_flag("LGB200_ATTN_BWD_TWO_KERNEL");  // default: the fused single-pass backward
+  const bool fused = !env_flag("LGB200_ATTN_BWD_TWO_KERNEL");  // default: the fused single-pass backward
   if (fused) return attn_bwd_fused(q, k, v, out, lse, dout, dq, dk, dv, delta, B, Nq, Nk, H, kv_shift, scale, stream);
   // workspace: delta [B*H*Nq] fp32, then the dKV side arrays qx, dox [B*H*Nq, 16] bf16 (16-byte aligned)
   const int64_t nq_all = ((int64_t)B * H * Nq + 3) & ~(int64_t)3;

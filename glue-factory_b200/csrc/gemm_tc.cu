@@ -608,7 +608,7 @@ extern "C" int lgb200_linear(const void* A, const void* B, void* C, const float*
   if (rc) return rc;
   {  // A-panel-resident kernel: K <= 256, K-major A, C reachable by TMA
     const int es = c_dtype == LGB200_F32 ? 4 : 2;
-    static const bool off = env_flag("LGB200_GEMM_NO_APANEL");
+    const bool off = env_flag("LGB200_GEMM_NO_APANEL");
     const bool c_ok = (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc * es) % 16 == 0;
     if (!off && !a_mn_major && K <= GP_KB * GB_K && c_ok && (c_dtype == LGB200_F32 || c_dtype == LGB200_BF16)) {
       CUtensorMap tc;

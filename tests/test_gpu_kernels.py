@@ -214,6 +214,36 @@ def test_attention_tc_matches_simt_lse(B, Nq, Nk, H, shift):
     assert (lse.double() - ref_lse).abs().max().item() < 2e-3
 
 
+@pytest.mark.parametrize("B,Nq,Nk,H,shift", [(2, 512, 512, 4, 1), (2, 300, 200, 4, 0)])
+def test_attention_two_kernel_backward_agrees_with_fused(B, Nq, Nk, H, shift, monkeypatch):
+    """The round-1 pair of backward kernels (dQ, dK/dV; deterministic summation order) stays selectable with
+    LGB200_ATTN_BWD_TWO_KERNEL=1 as an independent cross-check of the fused single-pass backward."""
+    q = _rand(B, Nq, H, 64, seed=1, dtype=torch.bfloat16, scale=1.5)
+    k = _rand(B, Nk, H, 64, seed=2, dtype=torch.bfloat16, scale=1.5)
+    v = _rand(B, Nk, H, 64, seed=3, dtype=torch.bfloat16)
+    go = _rand(B, Nq, H, 64, seed=4, dtype=torch.bfloat16)
+    out, lse = ops.attn_fwd(q, k, v, shift, 0.125)
+    fused = ops.attn_bwd(q, k, v, out, lse, go, shift, 0.125)
+    monkeypatch.setenv("LGB200_ATTN_BWD_TWO_KERNEL", "1")
+    two = ops.attn_bwd(q, k, v, out, lse, go, shift, 0.125)
+    monkeypatch.delenv("LGB200_ATTN_BWD_TWO_KERNEL")
+    for a, b, name in zip(fused, two, ("dq", "dk", "dv")):
+        assert rel_err(a, b.double()) < 6e-3, name
+
+
+def test_linear_generic_kernel_agrees_with_panel_resident(monkeypatch):
+    """K <= 256 projections run on the A-panel-resident GEMM by default; LGB200_GEMM_NO_APANEL=1 sends them through the
+    generic persistent kernel: same products, same accumulation -> identical results."""
+    a = _rand(3000, 256, seed=11, dtype=torch.bfloat16)
+    w = _rand(768, 256, seed=12, dtype=torch.bfloat16, scale=0.1)
+    bias = _rand(768, seed=13)
+    y0 = ops.linear(a, w, bias)
+    monkeypatch.setenv("LGB200_GEMM_NO_APANEL", "1")
+    y1 = ops.linear(a, w, bias)
+    monkeypatch.delenv("LGB200_GEMM_NO_APANEL")
+    assert torch.equal(y0, y1)
+
+
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 8e-3)])
 def test_rope_split(dtype, tol):
