@@ -68,6 +68,7 @@ SIGNATURES = {
     "lgb200_posenc_wgrad": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp]),
     "lgb200_mask_counts": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "lgb200_residual_add_cast": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "lgb200_add_f32_cast": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "lgb200_residual_add_cast_pitched": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _vp]),
 }
 

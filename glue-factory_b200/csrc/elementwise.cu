@@ -607,9 +607,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ a, fl
   }
 }
 
-// x_out = x + y (fp32 residual stream) and its compute-dtype copy for the next GEMM, in one pass
-template <typename T>
-__global__ void __launch_bounds__(256) residual_add_cast_kernel(const float* __restrict__ x, const T* __restrict__ y,
+// x_out = x + y (fp32 residual stream) and its compute-dtype copy for the next GEMM, in one pass.  TY = element type of
+// y: the compute dtype (a GEMM output added to the residual) or float (two fp32 gradient streams merged in backward).
+template <typename T, typename TY = T>
+__global__ void __launch_bounds__(256) residual_add_cast_kernel(const float* __restrict__ x, const TY* __restrict__ y,
                                                                float* __restrict__ xo, T* __restrict__ xc, int64_t n,
                                                                int64_t cols, int64_t cast_pitch) {
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -619,7 +620,7 @@ __global__ void __launch_bounds__(256) residual_add_cast_kernel(const float* __r
   if (i0 + 8 <= n) {
     Vec8<float> a = Vec8<float>::load(x + i0);
     if (y) {
-      Vec8<T> b = Vec8<T>::load(y + i0);
+      Vec8<TY> b = Vec8<TY>::load(y + i0);
 #pragma unroll
       for (int e = 0; e < 8; ++e) a.v[e] += b.v[e];
     }
@@ -845,6 +846,19 @@ int lgb200_residual_add_cast_pitched(const float* x, const void* y, float* x_out
   else
     LGB_REQUIRE(false, kErrInvalid, "residual_add_cast: bad dtype %d", dtype);
   return check_launch("residual_add_cast");
+}
+
+int lgb200_add_f32_cast(const float* x, const float* y, float* x_out, void* x_cast, int64_t n, int dtype,
+                        cudaStream_t stream) {
+  LGB_REQUIRE(x && y && (x_out || x_cast) && n > 0, kErrInvalid, "add_f32_cast: bad arguments");
+  const unsigned grid = (unsigned)(((n + 7) / 8 + 255) / 256);
+  if (dtype == LGB200_F32)
+    residual_add_cast_kernel<float, float><<<grid, 256, 0, stream>>>(x, y, x_out, (float*)x_cast, n, n, n);
+  else if (dtype == LGB200_BF16)
+    residual_add_cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>(x, y, x_out, (__nv_bfloat16*)x_cast, n, n, n);
+  else
+    LGB_REQUIRE(false, kErrInvalid, "add_f32_cast: bad dtype %d", dtype);
+  return check_launch("add_f32_cast");
 }
 
 int lgb200_residual_add_cast(const float* x, const void* y, float* x_out, void* x_cast, int64_t n, int dtype,

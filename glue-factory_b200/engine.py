@@ -181,10 +181,15 @@ _LN_SLOTS = (6, 7, 18, 19)  # LayerNorm affine stays fp32
 class LayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, theta, sizes, H, cdt, eps, w, sink, *params):
-        """sink: None, or (flat-parameter object, group index) of a trainer that owns a flat gradient buffer: the
-        backward then writes this layer's 22 parameter gradients straight into their slots of that buffer (weight
-        gradients as the GEMM output, no per-parameter copy) and tells the trainer the slice is final, so its
-        all-reduce can start while the earlier layers are still in backward."""
+        """sink: None, or (flat-parameter object or None, layer index, stash or None).
+        flat-parameter object (a trainer that owns a flat gradient buffer): the backward writes this layer's 22
+        parameter gradients straight into their slots of that buffer (weight gradients as the GEMM output, no
+        per-parameter copy) and tells the trainer the slice is final.
+        stash (dict): the supervision head that reads this layer's output leaves its gradient w.r.t. that output in
+        stash[layer index] instead of returning it to autograd (HeadFn); this backward merges it with the gradient
+        coming from the next layer in the same pass that produces the bf16 copy the first GEMMs need (autograd would
+        run a separate accumulation kernel over the [T, D] fp32 tensor, and the cast after it).  Autograd's dependency
+        rule -- a node runs after every consumer of its outputs has run -- guarantees the head has filled the stash."""
         (Wqkv, bqkv, Wo, bo, W0, b0, g1, be1, W3, b3,
          Wqk, bqk, Wv, bv, Wout, bout, W0c, b0c, g2, be2, W3c, b3c) = w
         if cdt == torch.bfloat16:  # biases are added in fp32 in the GEMM epilogue: take the master parameters
@@ -225,6 +230,7 @@ class LayerFn(torch.autograd.Function):
         ctx.meta = (sizes, H, cdt, len(lse1), len(lse2), D)
         ctx.sink = sink
         ctx.gemm_mode = FP32_GEMM
+        ctx.set_materialize_grads(False)  # the output's gradient may arrive through the stash only
         return x2
 
     @staticmethod
@@ -241,10 +247,24 @@ class LayerFn(torch.autograd.Function):
         lse1, lse2 = sv[18:18 + n1], sv[18 + n1:18 + n1 + n2]
         (Wqkv, bqkv, Wo, bo, W0, b0, g1, be1, W3, b3,
          Wqk, bqk, Wv, bv, Wout, bout, W0c, b0c, g2, be2, W3c, b3c) = sv[18 + n1 + n2:]
-        dx = dx.contiguous()
-        gv = ctx.sink[0].direct_views(ctx.sink[1]) if ctx.sink is not None else [None] * 22  # LAYER_PARAMS order
+        fp, slot, stash = ctx.sink if ctx.sink is not None else (None, None, None)
+        extra = stash.pop(slot, None) if stash is not None else None  # the supervision head's share (see forward)
+        if dx is None and extra is None:
+            return (None,) * (8 + 22)
+        if dx is None:
+            dx, dy2 = extra, extra.to(cdt)
+        elif extra is None:
+            dx = dx.contiguous()
+            dy2 = dx.to(cdt)
+        else:
+            dx = dx.contiguous()
+            if dx.dtype == torch.float32 and extra.dtype == torch.float32 and dx.is_cuda:
+                dx, dy2 = ops.add_f32_cast_(dx, extra.contiguous(), cdt)  # dx is this node's own incoming buffer
+            else:
+                dx = dx + extra
+                dy2 = dx.to(cdt)
+        gv = fp.direct_views(slot) if fp is not None else [None] * 22  # LAYER_PARAMS order
         # ---- cross block
-        dy2 = dx.to(cdt)
         dW3c, db3c = _wgrad(dy2, gg, gv[20]), _bgrad(dy2)
         dgg = _dgrad(dy2, W3c)
         dh2, dg2, dbe2, db0c = ops.ln_gelu_bwd(dgg, h2, g2, be2, mean2, rstd2, want_dxsum=True)
@@ -279,11 +299,11 @@ class LayerFn(torch.autograd.Function):
         dx0 = _dgrad_acc(dx0, dqkv, Wqkv)
         grads = (dWqkv, dbqkv, dWo, dbo, dW0, db0, dg1, dbe1, dW3, db3,
                  dWqk, dbqk, dWv, dbv, dWout, dbout, dW0c, db0c, dg2, dbe2, dW3c, db3c)
-        if ctx.sink is not None:
+        if fp is not None:
             # the nine weight gradients are already in place; the 13 vectors go in with one multi-tensor copy
             small = [i for i in range(22) if grads[i].data_ptr() != gv[i].data_ptr()]
             torch._foreach_copy_([gv[i] for i in small], [grads[i].view_as(gv[i]) for i in small])
-            ctx.sink[0].chunk_ready(ctx.sink[1])
+            fp.chunk_ready(slot)
             grads = (None,) * 22
         return (dx0, dtheta, None, None, None, None, None, None) + grads
 
@@ -294,7 +314,9 @@ class HeadFn(torch.autograd.Function):
     plus the detached nll_pos / nll_neg for logging."""
 
     @staticmethod
-    def forward(ctx, x, sizes, cdt, gt, bal, fin, wfp, bfp, Wfp_p, bfp_p, wm, bm, wt, bt):
+    def forward(ctx, x, sizes, cdt, gt, bal, fin, stash, wfp, bfp, Wfp_p, bfp_p, wm, bm, wt, bt):
+        """stash: None, or (dict, key): the backward then leaves the gradient w.r.t. x in dict[key] for the LayerFn that
+        produced x (which merges it with the next layer's gradient in one fused pass) instead of returning it."""
         B, M, N = sizes
         D = x.shape[1]
         t0 = B * M
@@ -342,6 +364,7 @@ class HeadFn(torch.autograd.Function):
         ctx.save_for_backward(*saved)
         ctx.meta = (sizes, cdt, bal, alpha, has_tok, f0 is not None, fused)
         ctx.gemm_mode = FP32_GEMM
+        ctx.stash = stash
         ctx.mark_non_differentiable(nll_pos, nll_neg)
         return nll, conf, nll_pos, nll_neg
 
@@ -392,4 +415,8 @@ class HeadFn(torch.autograd.Function):
         # dx = dmd W_fp + dzt[:,0] wm (the token-confidence head reads a detached x, lightglue.py:82-83), dW2, db2
         dx, dW2, db2 = ops.head_token_bwd(x, _dgrad(dmd, wfp), dzt, wm.view(-1))
         dwt, dbt = (dW2[1:2], db2[1:2]) if has_tok else (None, None)
-        return dx, None, None, None, None, None, None, None, dWfp, dbfp, dW2[0:1], db2[0:1], dwt, dbt
+        if ctx.stash is not None:
+            d, key = ctx.stash
+            d[key] = dx if key not in d else d[key] + dx
+            dx = None
+        return dx, None, None, None, None, None, None, None, None, dWfp, dbfp, dW2[0:1], db2[0:1], dwt, dbt

@@ -330,11 +330,14 @@ class LightGlue(nn.Module):
             self._refresh_shadow()
         if adaptive:
             return self._forward_adaptive(x, theta, sizes)
+        # head -> layer gradient hand-over of the fused training step (engine.LayerFn / HeadFn docstrings)
+        stash = {} if (fused and self.training and torch.is_grad_enabled()) else None
         for i in range(L):
             if fused:
                 w, params = self._layer_weights(i)
                 fp = getattr(self, "_b200_flat", None)
-                sink = (fp, i) if (fp is not None and fp.direct_groups and torch.is_grad_enabled()) else None
+                fp = fp if (fp is not None and fp.direct_groups) else None
+                sink = (fp, i, stash) if torch.is_grad_enabled() else None
                 x = engine.LayerFn.apply(x, theta, sizes, conf.num_heads, self._cdt, self.transformers[i].self_attn.ffn[1].eps,
                                          w, sink, *params)
             else:
@@ -369,6 +372,7 @@ class LightGlue(nn.Module):
             # row_norm monitor, both by-products of the dense pass.
             pred["_b200_layers"] = layers_x
             pred["_b200_sizes"] = sizes
+            pred["_b200_stash"] = stash
             du0, du1 = F.logsigmoid(-z0), F.logsigmoid(-z1)
             pred["_b200_final_arg"] = (
                 self._argmax_with_dustbin(st["rowmax"], st["rowarg"], du0, N).contiguous(),
@@ -472,7 +476,10 @@ class LightGlue(nn.Module):
             la_i = self.log_assignment[hi]
             pre = f"log_assignment.{hi}.final_proj."
             tok = self.token_confidence[i].token[0] if (i < L - 1 and self.training) else None
-            return engine.HeadFn.apply(layers_x[i], (B, M, N), self._cdt, gtd, conf.loss.nll_balancing, fin,
+            stash = pred.get("_b200_stash")
+            # layers_x[i] is the output of transformer layer i only when every layer's state was kept (training)
+            slot = (stash, i) if (stash is not None and L == conf.n_layers) else None
+            return engine.HeadFn.apply(layers_x[i], (B, M, N), self._cdt, gtd, conf.loss.nll_balancing, fin, slot,
                                        self._shadow[pre + "weight"], self._shadow[pre + "bias"],
                                        la_i.final_proj.weight, la_i.final_proj.bias, la_i.matchability.weight,
                                        la_i.matchability.bias, tok.weight if tok is not None else None,

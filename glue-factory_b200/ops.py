@@ -237,6 +237,15 @@ def residual_add_cast(x, y, cdt, want_sum=True, out_cast=None):
     return (xo if xo is not None else x), xc
 
 
+def add_f32_cast_(x, y, cdt):
+    """x += y (both fp32, in place) and the compute-dtype copy of the sum, one pass (lgb200_add_f32_cast)."""
+    _chk(x, torch.float32), _chk(y, torch.float32)
+    assert x.shape == y.shape
+    xc = torch.empty(x.shape, device=x.device, dtype=cdt)
+    call("lgb200_add_f32_cast", ptr(x), ptr(y), ptr(x), ptr(xc), x.numel(), _code(cdt), stream_ptr())
+    return x, xc
+
+
 def gluestick_attention(query, key, value):
     """GlueStick's attention core (models/matchers/gluestick.py:524-529) on the same kernels: query [B, 64, H, N],
     key/value [B, 64, H, M] (channels first, channel = d * H + h) -> [B, 64, H, N].  The reference forces fp32 here

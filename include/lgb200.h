@@ -252,6 +252,11 @@ int lgb200_flat_grad_check(const float* g, int64_t n, float* found_inf, cudaStre
 int lgb200_amp_update(const float* found_inf, int* step_dev, float* loss_scale, int* growth_tracker,
                       float growth_factor, float backoff_factor, int growth_interval, cudaStream_t stream);
 int lgb200_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream);
+/* x_out = x + y for two fp32 streams (x_out may alias x) and the compute-dtype copy of the sum: the merge of the two
+ * gradients that reach a layer's output (from the next layer and from the layer's supervision head) fused with the cast
+ * the layer's backward starts with -- replaces autograd's accumulation kernel + a cast.  n elements, dtype of x_cast. */
+int lgb200_add_f32_cast(const float* x, const float* y, float* x_out, void* x_cast, int64_t n, int dtype,
+                        cudaStream_t stream);
 /* residual update of the fp32 stream fused with the cast for the next GEMM (lightglue.py:163, 219-220):
  * x_out = x + y (y in `dtype`, may be NULL), x_cast = (dtype) x_out; either output may be NULL.   */
 int lgb200_residual_add_cast(const float* x, const void* y, float* x_out, void* x_cast, int64_t n, int dtype,
